@@ -1,0 +1,260 @@
+/* krylov_b200.h -- C ABI of the B200-native Krylov iteration engine.
+ *
+ * This is the drop-in boundary for the per-iteration hot path of
+ * PythonOptimizers/pykrylov.  The reference has no FFI of
+ * its own (it is pure Python + NumPy); each entry point below therefore cites
+ * the *reference code whose work it absorbs* (paths relative to
+ * /root/reference/pykrylov/).  The Python host side (pykrylov_b200/) binds
+ * these symbols with ctypes and nothing else; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - plain C: opaque handles, pointers and sizes; no C++/torch types.
+ *   - every function returns 0 on success and a negative kry_status on error;
+ *     kry_last_error() returns the message of the last failure on this thread.
+ *   - no exceptions and no callbacks cross the ABI.
+ *   - the caller owns every host buffer; the library copies on upload and never
+ *     retains a host pointer after the call returns.
+ *   - one CUDA stream per context; a context is not thread-safe.
+ *   - all floating point data is IEEE fp64; all CSR indices are int32
+ *     (what scipy.sparse produces for the configs of BASELINE.json).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point
+ *     fails with KRY_ERR_CUDA.
+ */
+#ifndef KRYLOV_B200_H
+#define KRYLOV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KRY_ABI_VERSION 1
+
+typedef enum kry_status {
+    KRY_OK              =  0,
+    KRY_ERR_INVALID     = -1,   /* bad argument (NULL handle, negative size, ...)     */
+    KRY_ERR_SHAPE       = -2,   /* operand sizes do not match (linop.py:283-296)       */
+    KRY_ERR_CUDA        = -3,   /* CUDA runtime error / no device                      */
+    KRY_ERR_NOMEM       = -4,   /* device allocation failed                            */
+    KRY_ERR_UNSUPPORTED = -5,   /* e.g. nnz >= 2^31                                    */
+    KRY_ERR_COMM        = -6,   /* NCCL error / communicator not initialised           */
+    KRY_ERR_STATE       = -7    /* call out of order (iterate before setup, ...)       */
+} kry_status;
+
+typedef struct kry_ctx    kry_ctx;     /* device + stream + reduction workspace      */
+typedef struct kry_csr    kry_csr;     /* device-resident CSR operator               */
+typedef struct kry_vec    kry_vec;     /* device-resident fp64 vector                */
+typedef struct kry_solver kry_solver;  /* device-resident Krylov iteration state     */
+
+/* ------------------------------------------------------------------ misc */
+int         kry_abi_version(void);
+const char *kry_last_error(void);
+int         kry_device_count(int *count);
+
+/* ---------------------------------------------------------------- context */
+int kry_ctx_create(int device, kry_ctx **out);
+int kry_ctx_destroy(kry_ctx *ctx);
+int kry_ctx_sync(kry_ctx *ctx);                       /* cudaStreamSynchronize        */
+/* props[0]=SM count, [1]=total bytes, [2]=free bytes, [3]=cc major*10+minor,
+ * [4]=L2 bytes, [5]=max smem/block optin                                            */
+int kry_ctx_props(kry_ctx *ctx, int64_t props[6]);
+/* CUDA-event timing on the context's stream (bench.py measures with these).         */
+int kry_timer_start(kry_ctx *ctx);
+int kry_timer_stop(kry_ctx *ctx, double *elapsed_ms); /* synchronises                 */
+/* Overwrite a scratch buffer larger than L2 (timing hygiene between samples).       */
+int kry_flush_l2(kry_ctx *ctx);
+/* Number of kernels this library has launched on this context so far.               */
+int kry_launch_count(kry_ctx *ctx, int64_t *count);
+
+/* Pinned host staging memory (for the end-to-end H2D/D2H legs). */
+int kry_host_alloc(int64_t bytes, void **out);
+int kry_host_free(void *p);
+
+/* ---------------------------------------------------------------- vectors */
+int kry_vec_create(kry_ctx *ctx, int64_t n, kry_vec **out);
+int kry_vec_destroy(kry_vec *v);
+int kry_vec_size(const kry_vec *v, int64_t *n);
+int kry_vec_upload(kry_vec *v, const double *host, int64_t n);
+int kry_vec_download(const kry_vec *v, double *host, int64_t n);
+int kry_vec_fill(kry_vec *v, double value);
+int kry_vec_copy(kry_vec *dst, const kry_vec *src);
+
+/* -------------------------------------------------------------- operators */
+#define KRY_CSR_SYMMETRIC        1u   /* A^T == A: op.T is op (linop.py:148-152)      */
+#define KRY_CSR_BUILD_TRANSPOSE  2u   /* build the CSR of A^T on device at creation   */
+
+/* Device CSR operator: replaces the user matvec closure behind
+ * LinearOperator.__mul__ (linop/linop.py:362-369 -> :356-360 -> :271-298), i.e.
+ * PysparseLinearOperator's `A*x` / `y*A` (linop.py:697-717).  Column indices
+ * must be in [0, ncols); rows need not be sorted (the summation order of a row
+ * is its storage order -- sorted columns reproduce scipy's csr_matvec
+ * bit-for-bit).  ncols_ext >= ncols may be passed through kry_csr_create_ext for
+ * a row shard whose columns address [local | halo] (section 8e).                */
+int kry_csr_create(kry_ctx *ctx, int64_t nrows, int64_t ncols, int64_t nnz,
+                   const int32_t *rowptr, const int32_t *col, const double *val,
+                   uint32_t flags, kry_csr **out);
+int kry_csr_destroy(kry_csr *A);
+int kry_csr_shape(const kry_csr *A, int64_t *nrows, int64_t *ncols, int64_t *nnz);
+/* Copy the device CSR back (integer-parity tests: device-built == scipy).           */
+int kry_csr_download(const kry_csr *A, int transposed,
+                     int32_t *rowptr, int32_t *col, double *val);
+int kry_csr_build_transpose(kry_csr *A);
+/* Main diagonal (PysparseMatrix.takeDiagonal, examples/bmark.py:19).                */
+int kry_csr_diagonal(const kry_csr *A, double *diag_host);
+
+/* Device-side gallery: CSR of the reference's matrix-free stencils, rows
+ * [row_begin,row_end) with *global* column ids, generated directly in HBM.
+ *   poisson2d : gallery/gallery.py:10-29 on a g x g grid (diag 4, off -1).
+ *   poisson1d : gallery/gallery.py:3-8 (diag 2, off -1).
+ *   convdiff3d: 7-pt convection-diffusion of BASELINE.json config 4 (not in the
+ *               reference): diag 6+3*gamma, upstream -1-gamma, downstream -1.    */
+int kry_csr_create_poisson1d(kry_ctx *ctx, int64_t n, int64_t row_begin, int64_t row_end,
+                             uint32_t flags, kry_csr **out);
+int kry_csr_create_poisson2d(kry_ctx *ctx, int64_t g, int64_t row_begin, int64_t row_end,
+                             uint32_t flags, kry_csr **out);
+int kry_csr_create_convdiff3d(kry_ctx *ctx, int64_t m, double gamma,
+                              int64_t row_begin, int64_t row_end,
+                              uint32_t flags, kry_csr **out);
+
+/* SpMV kernel selection (tuning / A-B measurement; default KRY_SPMV_AUTO). */
+#define KRY_SPMV_AUTO    0
+#define KRY_SPMV_ROW     1   /* one thread per row, direct global loads              */
+#define KRY_SPMV_STREAM  2   /* coalesced nnz stream staged in smem, row-sum pass    */
+#define KRY_SPMV_TMA     3   /* persistent CTAs, cp.async.bulk (TMA) multi-stage     */
+int kry_csr_set_kernel(kry_csr *A, int kind, int tile_nnz, int threads);
+
+/* ------------------------------------------------------- hot-path kernels */
+/* y = A x (trans=0) or y = A^T x (trans=1).  Replaces `self.op * p`
+ * (cg/cg.py:115, bicgstab/bicgstab.py:101,125, minres/minres.py:239,
+ *  cgs/cgs.py:84,96, tfqmr/tfqmr.py:84,114,146) and `A.T * u`
+ * (lls/lsqr.py:200,264, lls/lsmr.py:224,322, lls/craig.py:224,321).              */
+int kry_spmv(kry_csr *A, int trans, const kry_vec *x, kry_vec *y);
+
+/* y = A x fused with up to 3 row-local inner products in the same launch:
+ * dot k = sum_i w_k[i] * y[i], with w_k = dot_with[k], or y itself when
+ * dot_with[k] == NULL.  Results land in the context's scalar slots
+ * [slot0, slot0+n_dots).  Replaces `Ap = op*p; pAp = dot(p,Ap)` (cg.py:115-117),
+ * `v = A q; dot(r0,v)` (bicgstab.py:101-103), `t = A z; dot(t,s), dot(t,t),
+ * dot(r0,t)` (bicgstab.py:125-127), `y = A v; alfa = dot(v,y)` (minres.py:239-245). */
+int kry_spmv_dot(kry_csr *A, int trans, const kry_vec *x, kry_vec *y,
+                 int n_dots, const kry_vec *const *dot_with, int slot0);
+
+/* One pass over up to 4 fused updates  z_k <- a_k*u_k + b_k*w_k  (executed in
+ * order per element, un-fused multiply then add exactly like the NumPy
+ * expressions they replace) followed by up to 3 inner products u.w in the same
+ * launch.  Coefficients are immediate doubles, or read on device from scalar
+ * slot `a_slot`/`b_slot` when that slot index is >= 0 (optionally negated).
+ * Replaces `x += alpha*p; r += alpha*Ap; dot(r,r)` (cg.py:130-146),
+ * `p *= beta; p -= r` (cg.py:150-151) and the AXPY groups of bicgstab.py:91-93,
+ * 104-107, 130-139, cgs.py:86-114, tfqmr.py:92-99,133-150, minres.py:246-251.   */
+typedef struct kry_axpby {
+    kry_vec       *z;        /* output (may alias u or w)                         */
+    const kry_vec *u;        /* may be NULL: term a*u omitted                     */
+    const kry_vec *w;        /* may be NULL: term b*w omitted                     */
+    double a, b;             /* immediates, used when the slot is < 0             */
+    int    a_slot, b_slot;   /* scalar-slot index or -1                           */
+    int    a_neg,  b_neg;    /* negate the slot value                             */
+} kry_axpby;
+typedef struct kry_dotspec { const kry_vec *u, *w; } kry_dotspec;
+int kry_multi_axpy_dot(kry_ctx *ctx, int n_ops, const kry_axpby *ops,
+                       int n_dots, const kry_dotspec *dots, int slot0);
+
+/* The only per-check-interval device->host traffic: read scalar slots. */
+#define KRY_NUM_SLOTS 64
+int kry_scalars_read(kry_ctx *ctx, int first, int count, double *host);
+int kry_scalars_write(kry_ctx *ctx, int first, int count, const double *host);
+
+/* -------------------------------------------- device-resident iterations */
+typedef enum kry_method {
+    KRY_CG       = 1,   /* cg/cg.py:113-158                                         */
+    KRY_BICGSTAB = 2,   /* bicgstab/bicgstab.py:85-145                              */
+    KRY_CGS      = 3,   /* cgs/cgs.py:76-117                                        */
+    KRY_TFQMR    = 4,   /* tfqmr/tfqmr.py:85-153                                    */
+    KRY_MINRES   = 5    /* minres/minres.py:218-383                                 */
+} kry_method;
+
+typedef struct kry_solver_params {
+    double  abstol;          /* generic/generic.py:74  (default 1e-8)               */
+    double  reltol;          /* generic/generic.py:75  (default 1e-6)               */
+    int64_t matvec_max;      /* solve kwarg, default 2n (cg.py:82); MINRES: itnlim  */
+    int32_t check_curvature; /* CG only (cg.py:119-124)                             */
+    int32_t guess_supplied;  /* whether `guess` was passed (matvec counting quirk)  */
+    double  shift;           /* MINRES (minres.py:122)                              */
+    double  rtol;            /* MINRES (minres.py:126)                              */
+    double  etol;            /* MINRES (minres.py:127)                              */
+    int32_t window;          /* MINRES (minres.py:130), <= 16                       */
+    int32_t reserved;
+} kry_solver_params;
+
+/* Snapshot of the device scalar block (one small D2H per check interval).
+ * Field use per method is documented in DESIGN.md.                                  */
+typedef struct kry_solver_status {
+    int32_t done;            /* the loop condition of the reference turned false    */
+    int32_t converged;
+    int32_t definite;        /* CG: 0 after non-positive curvature (cg.py:119-124)  */
+    int32_t istop;           /* MINRES (minres.py:349-361)                          */
+    int64_t n_matvec;        /* reference nMatvec counter                           */
+    int64_t n_iter;          /* iterations executed on device                       */
+    int64_t hist_count;      /* residual-history entries produced so far            */
+    double  resid_norm0;
+    double  resid_norm;
+    double  threshold;
+    double  aux[16];         /* method specific (CG: ry,pAp,alpha,beta; MINRES:
+                                Anorm,Acond,ynorm,Arnorm,beta1,...)                 */
+} kry_solver_status;
+
+int kry_solver_create(kry_ctx *ctx, kry_method method, kry_csr *A, kry_solver **out);
+int kry_solver_destroy(kry_solver *S);
+/* Optional diagonal preconditioner applied on device.
+ *   mode 1: y = d .* r   (precon = DiagonalOperator(d), linop.py:473-503)
+ *   mode 2: y = r ./ d   (examples/bmark.py:14-22 DiagonalPrec, doc/source/bmark.rst:91-93)
+ * NULL or mode 0 clears it.                                                         */
+int kry_solver_set_precon_diag(kry_solver *S, const double *diag_host, int mode);
+/* Pre-loop part of solve(): initial residual, residNorm0, threshold, p/r0/...
+ * (cg.py:61-111, bicgstab.py:52-83, cgs.py:49-74, tfqmr.py:48-85,
+ * minres.py:132-209).  `guess` may be NULL.                                        */
+int kry_solver_setup(kry_solver *S, const double *rhs_host, const double *guess_host,
+                     const kry_solver_params *params);
+/* Same, with rhs/guess already resident in HBM (bench `value` leg, shards).        */
+int kry_solver_setup_dev(kry_solver *S, const kry_vec *rhs, const kry_vec *guess,
+                         const kry_solver_params *params);
+/* Enqueue up to n_iters iterations on the context's stream.  No host
+ * synchronisation: the stopping tests run on device with the reference's
+ * formulas and latch `done`; launches after that are no-ops.                       */
+int kry_solver_iterate(kry_solver *S, int64_t n_iters);
+int kry_solver_status_read(kry_solver *S, kry_solver_status *out);   /* synchronises */
+/* Per-iteration scalars recorded on device (residHistory replay, log lines):
+ * `width` doubles per entry (CG: residNorm,pAp; others: residNorm).                */
+int kry_solver_history(kry_solver *S, int64_t first, int64_t count, double *host,
+                       int32_t *width);
+int kry_solver_solution(kry_solver *S, double *x_host);
+/* Named state vectors for single-step parity tests.      */
+int kry_solver_get_vector(kry_solver *S, const char *name, double *host);
+int kry_solver_set_vector(kry_solver *S, const char *name, const double *host);
+int kry_solver_set_scalar(kry_solver *S, const char *name, double value);
+int kry_solver_get_scalar(kry_solver *S, const char *name, double *value);
+
+/* ------------------------------------------------------------- multi-GPU */
+/* One process per GPU; rank 0 creates the id, the host side broadcasts the
+ * 128 bytes out of band (pykrylov_b200/comm.py), every rank then joins.            */
+#define KRY_COMM_ID_BYTES 128
+int kry_comm_unique_id(void *id128);
+int kry_comm_init(kry_ctx *ctx, int nranks, int rank, const void *id128);
+int kry_comm_destroy(kry_ctx *ctx);
+int kry_comm_size(kry_ctx *ctx, int *nranks, int *rank);
+int kry_comm_barrier(kry_ctx *ctx);
+/* Host-buffer collectives for setup-time plumbing (halo analysis, timing max).     */
+int kry_comm_allgather_host(kry_ctx *ctx, const void *send, void *recv, int64_t bytes_per_rank);
+int kry_comm_allreduce_host(kry_ctx *ctx, double *inout, int count, int op /*0 sum,1 max*/);
+
+/* Row shard of a square operator (section 8e): local rows [row_begin,row_end)
+ * with global column ids.  The library analyses the off-shard columns,
+ * exchanges the boundary sets once, remaps columns to [local | halo] and, per
+ * SpMV, packs + ncclAllGathers only the boundary entries of x.                     */
+int kry_csr_shard_finalize(kry_csr *A_local, int64_t n_global, int64_t row_begin);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KRYLOV_B200_H */

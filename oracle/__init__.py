@@ -1,0 +1,5 @@
+"""Oracle = CPU restatement of the reference's hot path.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this package; the product (pykrylov_b200) never does.
+"""

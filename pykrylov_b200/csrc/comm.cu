@@ -1,0 +1,387 @@
+// comm.cu -- multi-GPU plumbing: one process per GPU, NCCL
+// over NVLink/NVSwitch.  NCCL is dlopen()ed so that the single-GPU library has
+// no link-time dependency on it.
+//
+// Data path per sharded SpMV:  pack boundary entries of x (one small kernel) ->
+// ONE ncclAllGather of the packed boundary sets into the halo tail of x ->
+// local SpMV over columns remapped to [local | halo].  Per fused inner product:
+// ONE ncclAllReduce of <= 3 doubles, then a one-thread kernel runs the scalar
+// recurrence.  Nothing else crosses NVLink.
+#include <cub/cub.cuh>
+#include <dlfcn.h>
+#include <nccl.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                              cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t,
+                              cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+} g_nccl;
+
+int nccl_load()
+{
+    if (g_nccl.lib) return KRY_OK;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *n : names) {
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    KRY_REQUIRE(h, KRY_ERR_COMM, "NCCL not found: %s", dlerror());
+#define LOAD(field, sym)                                                     \
+    *(void **)(&g_nccl.field) = dlsym(h, sym);                               \
+    KRY_REQUIRE(g_nccl.field, KRY_ERR_COMM, "NCCL symbol %s missing", sym)
+    LOAD(GetUniqueId, "ncclGetUniqueId");
+    LOAD(CommInitRank, "ncclCommInitRank");
+    LOAD(CommDestroy, "ncclCommDestroy");
+    LOAD(AllReduce, "ncclAllReduce");
+    LOAD(AllGather, "ncclAllGather");
+    LOAD(GetErrorString, "ncclGetErrorString");
+#undef LOAD
+    g_nccl.lib = h;
+    return KRY_OK;
+}
+
+#define KRY_NCCL(call)                                                                \
+    do {                                                                              \
+        ncclResult_t r_ = (call);                                                     \
+        if (r_ != ncclSuccess) {                                                      \
+            kry_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,               \
+                          g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?");   \
+            return KRY_ERR_COMM;                                                      \
+        }                                                                             \
+    } while (0)
+
+}  // namespace
+
+static_assert(sizeof(ncclUniqueId) == KRY_COMM_ID_BYTES, "ncclUniqueId size");
+
+extern "C" int kry_comm_unique_id(void *id128)
+{
+    KRY_REQUIRE(id128, KRY_ERR_INVALID, "kry_comm_unique_id: NULL output");
+    KRY_TRY(nccl_load());
+    ncclUniqueId id;
+    KRY_NCCL(g_nccl.GetUniqueId(&id));
+    memcpy(id128, &id, sizeof(id));
+    return KRY_OK;
+}
+
+extern "C" int kry_comm_init(kry_ctx *c, int nranks, int rank, const void *id128)
+{
+    KRY_REQUIRE(c && id128, KRY_ERR_INVALID, "kry_comm_init: NULL argument");
+    KRY_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, KRY_ERR_INVALID,
+                "kry_comm_init: rank %d of %d", rank, nranks);
+    KRY_REQUIRE(!c->nccl, KRY_ERR_STATE, "kry_comm_init: communicator already initialised");
+    KRY_TRY(nccl_load());
+    KRY_CUDA(cudaSetDevice(c->device));
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    ncclComm_t comm;
+    KRY_NCCL(g_nccl.CommInitRank(&comm, nranks, id, rank));
+    c->nccl = (void *)comm;
+    c->nranks = nranks;
+    c->rank = rank;
+    return KRY_OK;
+}
+
+extern "C" int kry_comm_destroy(kry_ctx *c)
+{
+    if (!c || !c->nccl) return KRY_OK;
+    cudaStreamSynchronize(c->stream);
+    g_nccl.CommDestroy((ncclComm_t)c->nccl);
+    c->nccl = nullptr;
+    c->nranks = 1;
+    c->rank = 0;
+    return KRY_OK;
+}
+
+extern "C" int kry_comm_size(kry_ctx *c, int *nranks, int *rank)
+{
+    KRY_REQUIRE(c, KRY_ERR_INVALID, "kry_comm_size: NULL context");
+    if (nranks) *nranks = c->nranks;
+    if (rank) *rank = c->rank;
+    return KRY_OK;
+}
+
+// all-reduce of the fused-reduction totals (c->sums[0..n)) in place, on the stream
+int kry_allreduce_sums(kry_ctx *c, int n)
+{
+    if (c->nranks <= 1) return KRY_OK;
+    KRY_REQUIRE(c->nccl, KRY_ERR_COMM, "all-reduce: communicator not initialised");
+    KRY_NCCL(g_nccl.AllReduce(c->sums, c->sums, (size_t)n, ncclDouble, ncclSum, (ncclComm_t)c->nccl,
+                              c->stream));
+    return KRY_OK;
+}
+
+extern "C" int kry_comm_allreduce_host(kry_ctx *c, double *inout, int count, int op)
+{
+    KRY_REQUIRE(c && inout && count >= 0 && count <= 64, KRY_ERR_INVALID,
+                "kry_comm_allreduce_host: bad argument");
+    if (c->nranks <= 1 || count == 0) return KRY_OK;
+    KRY_REQUIRE(c->nccl, KRY_ERR_COMM, "kry_comm_allreduce_host: communicator not initialised");
+    double *d = nullptr;
+    KRY_TRY(kry_alloc((void **)&d, 64 * sizeof(double)));
+    cudaError_t e = cudaMemcpyAsync(d, inout, count * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    ncclResult_t r = ncclSuccess;
+    if (e == cudaSuccess)
+        r = g_nccl.AllReduce(d, d, (size_t)count, ncclDouble, op == 1 ? ncclMax : ncclSum,
+                             (ncclComm_t)c->nccl, c->stream);
+    if (e == cudaSuccess && r == ncclSuccess)
+        e = cudaMemcpyAsync(inout, d, count * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    KRY_REQUIRE(r == ncclSuccess, KRY_ERR_COMM, "kry_comm_allreduce_host: %s", g_nccl.GetErrorString(r));
+    KRY_CUDA(e);
+    return KRY_OK;
+}
+
+extern "C" int kry_comm_barrier(kry_ctx *c)
+{
+    KRY_REQUIRE(c, KRY_ERR_INVALID, "kry_comm_barrier: NULL context");
+    double z = 0.0;
+    KRY_TRY(kry_comm_allreduce_host(c, &z, 1, 0));
+    KRY_CUDA(cudaStreamSynchronize(c->stream));
+    return KRY_OK;
+}
+
+extern "C" int kry_comm_allgather_host(kry_ctx *c, const void *send, void *recv, int64_t bytes)
+{
+    KRY_REQUIRE(c && send && recv && bytes >= 0, KRY_ERR_INVALID, "kry_comm_allgather_host: bad argument");
+    if (c->nranks <= 1) {
+        memcpy(recv, send, (size_t)bytes);
+        return KRY_OK;
+    }
+    KRY_REQUIRE(c->nccl, KRY_ERR_COMM, "kry_comm_allgather_host: communicator not initialised");
+    if (bytes == 0) return KRY_OK;
+    char *d_s = nullptr, *d_r = nullptr;
+    KRY_TRY(kry_alloc((void **)&d_s, (size_t)bytes));
+    int rc = kry_alloc((void **)&d_r, (size_t)bytes * c->nranks);
+    if (rc != KRY_OK) {
+        cudaFree(d_s);
+        return rc;
+    }
+    cudaError_t e = cudaMemcpyAsync(d_s, send, (size_t)bytes, cudaMemcpyHostToDevice, c->stream);
+    ncclResult_t r = ncclSuccess;
+    if (e == cudaSuccess)
+        r = g_nccl.AllGather(d_s, d_r, (size_t)bytes, ncclChar, (ncclComm_t)c->nccl, c->stream);
+    if (e == cudaSuccess && r == ncclSuccess)
+        e = cudaMemcpyAsync(recv, d_r, (size_t)bytes * c->nranks, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_s);
+    cudaFree(d_r);
+    KRY_REQUIRE(r == ncclSuccess, KRY_ERR_COMM, "kry_comm_allgather_host: %s", g_nccl.GetErrorString(r));
+    KRY_CUDA(e);
+    return KRY_OK;
+}
+
+// ------------------------------------------------------------ halo exchange
+__global__ void halo_pack_kernel(const double *x, const int *idx, int n_send, int max_send, double *buf)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < max_send) buf[i] = (i < n_send) ? x[idx[i]] : 0.0;
+}
+
+// x_dev: [n_local | nranks*max_send] -- fills the tail.  No-op for unsharded operators.
+int kry_halo_exchange(kry_csr *M, double *x_dev)
+{
+    HaloPlan &h = M->halo;
+    if (!h.active) return KRY_OK;
+    kry_ctx *c = M->ctx;
+    if (h.max_send == 0) return KRY_OK;
+    halo_pack_kernel<<<(h.max_send + 255) / 256, 256, 0, c->stream>>>(x_dev, h.send_idx, h.n_send,
+                                                                      h.max_send, h.send_buf);
+    c->launches++;
+    KRY_CUDA(cudaGetLastError());
+    double *tail = x_dev + M->A.nrows;
+    if (c->nranks <= 1) {
+        KRY_CUDA(cudaMemcpyAsync(tail, h.send_buf, (size_t)h.max_send * sizeof(double),
+                                 cudaMemcpyDeviceToDevice, c->stream));
+        return KRY_OK;
+    }
+    KRY_REQUIRE(c->nccl, KRY_ERR_COMM, "halo exchange: communicator not initialised");
+    KRY_NCCL(g_nccl.AllGather(h.send_buf, tail, (size_t)h.max_send, ncclDouble, (ncclComm_t)c->nccl,
+                              c->stream));
+    return KRY_OK;
+}
+
+// ------------------------------------------------------- shard finalisation
+struct OffShard {
+    int lo, hi;
+    __device__ bool operator()(int c) const { return c < lo || c >= hi; }
+};
+
+__global__ void remap_cols_kernel(int *col, int nnz, int lo, int hi, const int *halo_cols,
+                                  const int *halo_map, int n_halo)
+{
+    const int stride = gridDim.x * blockDim.x;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += stride) {
+        const int c = col[k];
+        if (c >= lo && c < hi) {
+            col[k] = c - lo;
+        } else {
+            int a = 0, b = n_halo;          // lower_bound in the sorted unique halo columns
+            while (a < b) {
+                const int m = (a + b) >> 1;
+                if (halo_cols[m] < c) a = m + 1; else b = m;
+            }
+            col[k] = halo_map[a];
+        }
+    }
+}
+
+extern "C" int kry_csr_shard_finalize(kry_csr *M, int64_t n_global, int64_t row_begin)
+{
+    KRY_REQUIRE(M, KRY_ERR_INVALID, "kry_csr_shard_finalize: NULL operator");
+    KRY_REQUIRE(!M->halo.active, KRY_ERR_STATE, "kry_csr_shard_finalize: already finalised");
+    kry_ctx *c = M->ctx;
+    const int P = c->nranks, me = c->rank;
+    const int64_t n_local = M->A.nrows;
+    KRY_REQUIRE(M->A.ncols == n_global && row_begin >= 0 && row_begin + n_local <= n_global,
+                KRY_ERR_SHAPE, "kry_csr_shard_finalize: shard rows [%lld,%lld) of %lld, operator has %lld columns",
+                (long long)row_begin, (long long)(row_begin + n_local), (long long)n_global,
+                (long long)M->A.ncols);
+    KRY_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const int nnz = (int)M->A.nnz;
+    const int lo = (int)row_begin, hi = (int)(row_begin + n_local);
+
+    // 1. unique off-shard columns (device: select -> sort -> unique)
+    int *d_sel = nullptr, *d_sorted = nullptr, *d_count = nullptr;
+    void *tmp = nullptr;
+    std::vector<int> need;
+    {
+        KRY_TRY(kry_alloc((void **)&d_sel, (size_t)(nnz + 1) * sizeof(int)));
+        KRY_TRY(kry_alloc((void **)&d_sorted, (size_t)(nnz + 1) * sizeof(int)));
+        KRY_TRY(kry_alloc((void **)&d_count, 256));
+        size_t b1 = 0, b2 = 0, b3 = 0;
+        OffShard pred{lo, hi};
+        cub::DeviceSelect::If(nullptr, b1, M->A.col, d_sel, d_count, nnz, pred, st);
+        cub::DeviceRadixSort::SortKeys(nullptr, b2, d_sel, d_sorted, nnz, 0, 32, st);
+        cub::DeviceSelect::Unique(nullptr, b3, d_sorted, d_sel, d_count, nnz, st);
+        size_t bytes = std::max(b1, std::max(b2, b3)) + 256;
+        KRY_TRY(kry_alloc(&tmp, bytes));
+        int n_off = 0, n_uni = 0;
+        cub::DeviceSelect::If(tmp, bytes, M->A.col, d_sel, d_count, nnz, pred, st);
+        KRY_CUDA(cudaMemcpyAsync(&n_off, d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+        KRY_CUDA(cudaStreamSynchronize(st));
+        if (n_off > 0) {
+            cub::DeviceRadixSort::SortKeys(tmp, bytes, d_sel, d_sorted, n_off, 0, 32, st);
+            cub::DeviceSelect::Unique(tmp, bytes, d_sorted, d_sel, d_count, n_off, st);
+            KRY_CUDA(cudaMemcpyAsync(&n_uni, d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+            KRY_CUDA(cudaStreamSynchronize(st));
+            need.resize(n_uni);
+            KRY_CUDA(cudaMemcpyAsync(need.data(), d_sel, (size_t)n_uni * sizeof(int),
+                                     cudaMemcpyDeviceToHost, st));
+            KRY_CUDA(cudaStreamSynchronize(st));
+        }
+        cudaFree(tmp);
+        cudaFree(d_sorted);
+        cudaFree(d_count);
+        cudaFree(d_sel);
+    }
+
+    // 2. everyone learns every shard's row range and need list
+    std::vector<int64_t> ranges((size_t)2 * P);
+    int64_t mine[2] = {row_begin, row_begin + n_local};
+    KRY_TRY(kry_comm_allgather_host(c, mine, ranges.data(), sizeof(mine)));
+    std::vector<int64_t> counts(P);
+    int64_t my_count = (int64_t)need.size();
+    KRY_TRY(kry_comm_allgather_host(c, &my_count, counts.data(), sizeof(int64_t)));
+    int64_t max_need = 0;
+    for (int q = 0; q < P; ++q) max_need = std::max(max_need, counts[q]);
+    std::vector<int> need_pad((size_t)std::max<int64_t>(max_need, 1), -1), all_need;
+    std::copy(need.begin(), need.end(), need_pad.begin());
+    all_need.resize(need_pad.size() * P);
+    KRY_TRY(kry_comm_allgather_host(c, need_pad.data(), all_need.data(),
+                                    (int64_t)need_pad.size() * sizeof(int)));
+
+    // 3. my boundary set = union of what the others need from my rows (sorted, unique)
+    std::vector<int> send;
+    for (int q = 0; q < P; ++q) {
+        if (q == me) continue;
+        const int *lst = all_need.data() + (size_t)q * need_pad.size();
+        for (int64_t i = 0; i < counts[q]; ++i)
+            if (lst[i] >= lo && lst[i] < hi) send.push_back(lst[i]);
+    }
+    std::sort(send.begin(), send.end());
+    send.erase(std::unique(send.begin(), send.end()), send.end());
+
+    // 4. everyone learns every boundary set
+    std::vector<int64_t> scounts(P);
+    int64_t my_send = (int64_t)send.size();
+    KRY_TRY(kry_comm_allgather_host(c, &my_send, scounts.data(), sizeof(int64_t)));
+    int64_t max_send = 0;
+    for (int q = 0; q < P; ++q) max_send = std::max(max_send, scounts[q]);
+    std::vector<int> send_pad((size_t)std::max<int64_t>(max_send, 1), -1), all_send;
+    std::copy(send.begin(), send.end(), send_pad.begin());
+    all_send.resize(send_pad.size() * P);
+    KRY_TRY(kry_comm_allgather_host(c, send_pad.data(), all_send.data(),
+                                    (int64_t)send_pad.size() * sizeof(int)));
+    KRY_REQUIRE(n_local + (int64_t)P * max_send < (int64_t)INT32_MAX - (1 << 20), KRY_ERR_UNSUPPORTED,
+                "kry_csr_shard_finalize: [local | halo] index space exceeds int32");
+
+    // 5. halo column -> index in [n_local + owner*max_send + position in owner's set]
+    std::vector<int> halo_map(need.size());
+    for (size_t i = 0; i < need.size(); ++i) {
+        const int col = need[i];
+        int owner = -1;
+        for (int q = 0; q < P; ++q)
+            if (col >= ranges[2 * q] && col < ranges[2 * q + 1]) { owner = q; break; }
+        KRY_REQUIRE(owner >= 0 && owner != me, KRY_ERR_INVALID,
+                    "kry_csr_shard_finalize: column %d is owned by no other shard", col);
+        const int *lst = all_send.data() + (size_t)owner * send_pad.size();
+        const int *pos = std::lower_bound(lst, lst + scounts[owner], col);
+        KRY_REQUIRE(pos != lst + scounts[owner] && *pos == col, KRY_ERR_COMM,
+                    "kry_csr_shard_finalize: column %d missing from shard %d's boundary set", col, owner);
+        halo_map[i] = (int)(n_local + (int64_t)owner * max_send + (pos - lst));
+    }
+
+    // 6. remap on device, install the plan
+    int *d_need = nullptr, *d_map = nullptr;
+    KRY_TRY(kry_alloc((void **)&d_need, (need.size() + 1) * sizeof(int)));
+    KRY_TRY(kry_alloc((void **)&d_map, (need.size() + 1) * sizeof(int)));
+    if (!need.empty()) {
+        KRY_CUDA(cudaMemcpyAsync(d_need, need.data(), need.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        KRY_CUDA(cudaMemcpyAsync(d_map, halo_map.data(), need.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    }
+    if (nnz > 0) {
+        remap_cols_kernel<<<c->sm_count * 8, 256, 0, st>>>(M->A.col, nnz, lo, hi, d_need, d_map,
+                                                           (int)need.size());
+        c->launches++;
+    }
+    KRY_CUDA(cudaStreamSynchronize(st));
+    KRY_CUDA(cudaGetLastError());
+    cudaFree(d_need);
+    cudaFree(d_map);
+
+    HaloPlan &h = M->halo;
+    h.n_global = n_global;
+    h.row_begin = row_begin;
+    h.n_send = (int)send.size();
+    h.max_send = (int)max_send;
+    KRY_TRY(kry_alloc((void **)&h.send_idx, (send.size() + 1) * sizeof(int)));
+    KRY_TRY(kry_alloc((void **)&h.send_buf, (size_t)(max_send + 1) * sizeof(double)));
+    if (!send.empty()) {
+        std::vector<int> local(send.size());
+        for (size_t i = 0; i < send.size(); ++i) local[i] = send[i] - lo;
+        KRY_CUDA(cudaMemcpyAsync(h.send_idx, local.data(), local.size() * sizeof(int),
+                                 cudaMemcpyHostToDevice, st));
+        KRY_CUDA(cudaStreamSynchronize(st));
+    }
+    M->A.ncols = n_local + (int64_t)P * max_send;
+    h.active = true;
+    return KRY_OK;
+}

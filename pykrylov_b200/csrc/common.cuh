@@ -1,0 +1,242 @@
+// common.cuh -- shared host/device plumbing of libkrylov_b200 (sm_100a only).
+//
+// * error reporting for the C ABI (include/krylov_b200.h)
+// * the context / vector / CSR handle structs
+// * the deterministic two-stage reduction with fused "last block finalises"
+//   scalar recurrence, used by every kernel on the hot path:
+//     stage 1: warp-shuffle butterfly -> per-warp smem -> one partial per CTA
+//     stage 2: the CTA that retires last (threadfence + atomic ticket) sums the
+//              partials in a fixed order and runs the solver's scalar update
+//              (alpha, beta, rho, omega, Givens ...) on device, so no host
+//              round-trip and no extra launch is needed per inner product.
+//   The summation order depends only on (grid, block) -- never on which CTA
+//   happens to be last -- so results are reproducible run to run.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/krylov_b200.h"
+
+// ---------------------------------------------------------------- errors
+void kry_set_error(const char *fmt, ...);
+
+#define KRY_CUDA(call)                                                              \
+    do {                                                                            \
+        cudaError_t e_ = (call);                                                    \
+        if (e_ != cudaSuccess) {                                                    \
+            kry_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,             \
+                          cudaGetErrorString(e_));                                  \
+            return (e_ == cudaErrorMemoryAllocation) ? KRY_ERR_NOMEM : KRY_ERR_CUDA;\
+        }                                                                           \
+    } while (0)
+
+#define KRY_REQUIRE(cond, code, ...)                                                \
+    do {                                                                            \
+        if (!(cond)) {                                                              \
+            kry_set_error(__VA_ARGS__);                                             \
+            return (code);                                                          \
+        }                                                                           \
+    } while (0)
+
+#define KRY_TRY(expr)                                                               \
+    do {                                                                            \
+        int rc_ = (expr);                                                           \
+        if (rc_ != KRY_OK) return rc_;                                              \
+    } while (0)
+
+// ---------------------------------------------------------------- handles
+constexpr int KRY_MAX_DOTS = 4;
+
+struct ReduceWs {
+    double   *partials;   // [KRY_MAX_DOTS][stride] one partial per CTA
+    double   *sums;       // [KRY_MAX_DOTS] totals (input of the NCCL all-reduce when sharded)
+    unsigned *counter;    // retirement ticket, self-resetting
+    int       stride;
+    int       defer;      // 1: only write sums[]; the finalize functor runs after the all-reduce
+};
+
+struct kry_ctx {
+    int          device;
+    cudaStream_t stream;
+    cudaEvent_t  ev0, ev1;
+    int          sm_count;
+    int64_t      l2_bytes;
+    int64_t      smem_optin;
+    double      *scalars;      // KRY_NUM_SLOTS user-visible scalar slots
+    double      *partials;
+    double      *sums;
+    unsigned    *counter;
+    int          partial_stride;
+    int         *never_done;   // device int == 0: "done" flag of the stand-alone ops
+    void        *flush_buf;
+    size_t       flush_bytes;
+    int64_t      launches;
+    // multi-GPU
+    void        *nccl;         // ncclComm_t
+    int          nranks, rank;
+};
+
+struct CsrDev {
+    int     *rowptr = nullptr;
+    int     *col    = nullptr;
+    double  *val    = nullptr;
+    int     *rowblk = nullptr;   // first row of each nnz tile, [nblocks+1]
+    int      nblocks = 0;
+    int      tile_nnz = 0;       // tile the rowblk partition was built for
+    int      max_row = 0;        // longest row
+    int64_t  nrows = 0, ncols = 0, nnz = 0;
+};
+
+struct HaloPlan {                // 1-D row sharding
+    bool     active = false;
+    int64_t  n_global = 0, row_begin = 0;
+    int      n_send = 0;         // boundary entries this rank publishes
+    int      max_send = 0;       // padded per-rank slot in the all-gather
+    int     *send_idx = nullptr; // local indices to pack
+    double  *send_buf = nullptr; // [max_send]
+};
+
+struct kry_csr {
+    kry_ctx *ctx;
+    CsrDev   A, T;
+    bool     has_T = false;
+    uint32_t flags = 0;
+    int      kind = KRY_SPMV_AUTO;
+    int      tile_nnz = 0, threads = 0;
+    HaloPlan halo;
+};
+
+struct kry_vec {
+    kry_ctx *ctx;
+    double  *d;
+    int64_t  n;        // logical length
+    int64_t  cap;      // allocated length (>= n; sharded x vectors carry the halo tail)
+    bool     owned;
+};
+
+int  kry_ctx_ensure_partials(kry_ctx *ctx, int nblocks);
+int  kry_alloc(void **p, size_t bytes);
+ReduceWs kry_ws(kry_ctx *ctx);
+
+// ---------------------------------------------------------------- device
+#ifdef __CUDACC__
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+    // xor butterfly: every lane ends with the same, order-fixed sum
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block-wide sum of ND accumulators; result valid in thread 0.
+template <int ND>
+__device__ __forceinline__ void block_sum(double (&acc)[ND], double (*s_warp)[32])
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+        acc[d] = warp_sum(acc[d]);
+        if (lane == 0) s_warp[d][warp] = acc[d];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            double v = (lane < nwarps) ? s_warp[d][lane] : 0.0;
+            acc[d] = warp_sum(v);
+        }
+    }
+}
+
+// Stage 1 + stage 2 + fused scalar recurrence. Must be reached by all threads of
+// all CTAs of the launch. `fin(const double *totals)` runs in exactly one thread.
+template <int ND, class Fin>
+__device__ __forceinline__ void block_reduce_finalize(double (&acc)[ND], const ReduceWs &ws, Fin &fin)
+{
+    __shared__ double s_warp[ND][32];
+    __shared__ int    s_last;
+    block_sum<ND>(acc, s_warp);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int d = 0; d < ND; ++d) ws.partials[(size_t)d * ws.stride + blockIdx.x] = acc[d];
+        __threadfence();
+        const unsigned ticket = atomicAdd(ws.counter, 1u);
+        s_last = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double tot[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+        double a = 0.0;
+        const volatile double *p = ws.partials + (size_t)d * ws.stride;
+        for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) a = __dadd_rn(a, p[i]);
+        tot[d] = a;
+    }
+    __syncthreads();            // s_warp reuse
+    block_sum<ND>(tot, s_warp);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int d = 0; d < ND; ++d) ws.sums[d] = tot[d];
+        *ws.counter = 0u;
+        if (!ws.defer) fin(tot);
+    }
+}
+
+struct NoFin {
+    __device__ void operator()(const double *) const {}
+};
+
+// Finalize that publishes the totals into the context's scalar slots.
+struct SlotFin {
+    double *slots;
+    int     n;
+    __device__ void operator()(const double *t) const
+    {
+        for (int d = 0; d < n; ++d) slots[d] = t[d];
+    }
+};
+
+// Deferred scalar update (after an ncclAllReduce of ws.sums on sharded runs).
+template <class Fin>
+__global__ void finalize_kernel(Fin fin, const double *sums, const int *done)
+{
+    if (*done) return;
+    if (threadIdx.x == 0 && blockIdx.x == 0) fin(sums);
+}
+
+// Generic fused vector pass: body(i, acc) over all elements + reduction + finalize.
+template <int ND, class Body, class Fin>
+__global__ void __launch_bounds__(256)
+vec_pass_kernel(int64_t n, Body body, ReduceWs ws, Fin fin, const int *done)
+{
+    static_assert(ND >= 1 && ND <= KRY_MAX_DOTS, "1..KRY_MAX_DOTS fused inner products");
+    if (*done) return;
+    body.init();
+    double acc[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) acc[d] = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        body(i, acc);
+    block_reduce_finalize<ND>(acc, ws, fin);
+}
+
+// Same without inner products (pure element-wise update).
+template <class Body>
+__global__ void __launch_bounds__(256)
+vec_map_kernel(int64_t n, Body body, const int *done)
+{
+    if (*done) return;
+    body.init();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        body(i);
+}
+
+#endif  // __CUDACC__

@@ -1,0 +1,123 @@
+// launch.cuh -- host-side launch helpers shared by ops.cu and the solvers.
+#pragma once
+
+#include "spmv.cuh"
+
+constexpr int KRY_DEFAULT_TILE    = 4096;
+constexpr int KRY_DEFAULT_THREADS = 256;
+constexpr int KRY_TMA_STAGES      = 3;
+
+int csr_build_partition(kry_ctx *c, CsrDev &m, int tile_nnz);
+int kry_halo_exchange(kry_csr *M, double *x_dev);    // comm.cu; no-op unless sharded
+
+template <class K>
+static inline int set_max_smem(K kernel, kry_ctx *c, size_t bytes)
+{
+    if (bytes <= 48 * 1024) return KRY_OK;
+    KRY_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)c->smem_optin));
+    return KRY_OK;
+}
+
+static inline int vec_grid(kry_ctx *c, int64_t n)
+{
+    int64_t need = (n + 255) / 256;
+    int64_t cap = (int64_t)c->sm_count * 8;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+// y-side work is described by Epi, x-side by Gather; ND fused inner products are
+// reduced on device and handed to Fin (see common.cuh).
+template <int ND, class Gather, class Epi, class Fin>
+int spmv_launch(kry_csr *M, bool trans, Gather g, Epi epi, Fin fin, const int *done, int defer)
+{
+    kry_ctx *c = M->ctx;
+    CsrDev *m = &M->A;
+    if (trans && !(M->flags & KRY_CSR_SYMMETRIC)) {
+        KRY_REQUIRE(M->has_T, KRY_ERR_STATE, "spmv: transpose requested but not built "
+                    "(create with KRY_CSR_BUILD_TRANSPOSE or call kry_csr_build_transpose)");
+        m = &M->T;
+    }
+    int kind = M->kind == KRY_SPMV_AUTO ? KRY_SPMV_STREAM : M->kind;
+    const int tile = M->tile_nnz ? M->tile_nnz : KRY_DEFAULT_TILE;
+    const int threads = M->threads ? M->threads : KRY_DEFAULT_THREADS;
+    const size_t budget = (size_t)c->smem_optin - 1024;
+    size_t smem = 0;
+    int grid = 1, cap = 0;
+
+    if (kind == KRY_SPMV_STREAM) {
+        smem = ((size_t)tile + m->max_row) * sizeof(double);
+        if (smem > budget) kind = KRY_SPMV_ROW;
+    } else if (kind == KRY_SPMV_TMA) {
+        cap = (tile + m->max_row + 8 + 3) & ~3;
+        smem = (size_t)KRY_TMA_STAGES * cap * 12;
+        if (smem > budget) kind = KRY_SPMV_ROW;
+    }
+    if (kind == KRY_SPMV_ROW) {
+        int64_t need = (m->nrows + 255) / 256;
+        if (need < 1) need = 1;
+        const int64_t capg = (int64_t)c->sm_count * 64;
+        grid = (int)(need < capg ? need : capg);
+    } else {
+        KRY_TRY(csr_build_partition(c, *m, tile));
+        grid = m->nblocks;
+        if (kind == KRY_SPMV_TMA) {
+            int per_sm = (int)((size_t)(c->smem_optin) / (smem + 1024));
+            if (per_sm > 2048 / threads) per_sm = 2048 / threads;
+            if (per_sm < 1) per_sm = 1;
+            const int g2 = c->sm_count * per_sm;
+            if (grid > g2) grid = g2;
+        }
+    }
+    KRY_TRY(kry_ctx_ensure_partials(c, grid));
+    ReduceWs ws = kry_ws(c);
+    ws.defer = defer;
+    const CsrView A = csr_view(*m);
+
+    if (kind == KRY_SPMV_ROW) {
+        spmv_row_kernel<ND, Gather, Epi, Fin><<<grid, 256, 0, c->stream>>>(A, g, epi, ws, fin, done);
+    } else if (kind == KRY_SPMV_STREAM) {
+        auto k = spmv_stream_kernel<ND, Gather, Epi, Fin>;
+        KRY_TRY(set_max_smem(k, c, smem));
+        k<<<grid, threads, smem, c->stream>>>(A, g, epi, ws, fin, done);
+    } else {
+        auto k = spmv_tma_kernel<ND, KRY_TMA_STAGES, Gather, Epi, Fin>;
+        KRY_TRY(set_max_smem(k, c, smem));
+        k<<<grid, threads, smem, c->stream>>>(A, cap, g, epi, ws, fin, done);
+    }
+    c->launches++;
+    KRY_CUDA(cudaGetLastError());
+    return KRY_OK;
+}
+
+template <int ND, class Body, class Fin>
+int vec_pass_launch(kry_ctx *c, int64_t n, Body body, Fin fin, const int *done, int defer)
+{
+    const int grid = vec_grid(c, n);
+    KRY_TRY(kry_ctx_ensure_partials(c, grid));
+    ReduceWs ws = kry_ws(c);
+    ws.defer = defer;
+    vec_pass_kernel<ND, Body, Fin><<<grid, 256, 0, c->stream>>>(n, body, ws, fin, done);
+    c->launches++;
+    KRY_CUDA(cudaGetLastError());
+    return KRY_OK;
+}
+
+template <class Body>
+int vec_map_launch(kry_ctx *c, int64_t n, Body body, const int *done)
+{
+    vec_map_kernel<Body><<<vec_grid(c, n), 256, 0, c->stream>>>(n, body, done);
+    c->launches++;
+    KRY_CUDA(cudaGetLastError());
+    return KRY_OK;
+}
+
+template <class Fin>
+int finalize_launch(kry_ctx *c, Fin fin, const int *done)
+{
+    finalize_kernel<Fin><<<1, 32, 0, c->stream>>>(fin, c->sums, done);
+    c->launches++;
+    KRY_CUDA(cudaGetLastError());
+    return KRY_OK;
+}

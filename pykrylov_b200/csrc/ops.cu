@@ -1,0 +1,224 @@
+// ops.cu -- stand-alone hot-path entry points of the C ABI:
+//   kry_spmv, kry_spmv_dot, kry_multi_axpy_dot
+// (the device-resident solver loops in solvers.cu use the same kernels with
+//  solver-specific epilogues; these generic forms back LinearOperator.__mul__
+//  and user-composed iterations).
+#include "launch.cuh"
+
+// y = A x, plus up to 3 fused  w_k . y  (w_k == nullptr means y . y)
+template <int ND>
+struct EpiStoreDots {
+    double       *y;
+    const double *w[ND > 0 ? ND : 1];
+    __device__ void init() {}
+    __device__ void operator()(int row, double ax, double *acc) const
+    {
+        y[row] = ax;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            const double wv = w[d] ? w[d][row] : ax;
+            acc[d] = __dadd_rn(acc[d], __dmul_rn(wv, ax));
+        }
+    }
+};
+
+static int check_spmv_args(const char *who, kry_csr *A, int trans, const kry_vec *x, const kry_vec *y)
+{
+    KRY_REQUIRE(A && x && y, KRY_ERR_INVALID, "%s: NULL argument", who);
+    KRY_REQUIRE(x->ctx == A->ctx && y->ctx == A->ctx, KRY_ERR_INVALID,
+                "%s: operands belong to different contexts", who);
+    KRY_REQUIRE(x->d != y->d, KRY_ERR_INVALID, "%s: x and y must not alias", who);
+    const int64_t nin = trans ? A->A.nrows : (A->halo.active ? A->A.nrows : A->A.ncols);
+    const int64_t nout = trans ? A->A.ncols : A->A.nrows;
+    // the reference raises ValueError on a size mismatch (linop/linop.py:283-296)
+    KRY_REQUIRE(x->n == nin, KRY_ERR_SHAPE, "%s: input has %lld entries, operator expects %lld",
+                who, (long long)x->n, (long long)nin);
+    KRY_REQUIRE(y->n == nout, KRY_ERR_SHAPE, "%s: output has %lld entries, operator produces %lld",
+                who, (long long)y->n, (long long)nout);
+    KRY_REQUIRE(!(trans && A->halo.active), KRY_ERR_UNSUPPORTED,
+                "%s: transpose product of a row shard is not supported", who);
+    if (A->halo.active)
+        KRY_REQUIRE(x->cap >= A->A.ncols, KRY_ERR_SHAPE,
+                    "%s: sharded operator needs an x vector with halo capacity %lld (has %lld)",
+                    who, (long long)A->A.ncols, (long long)x->cap);
+    return KRY_OK;
+}
+
+extern "C" int kry_spmv(kry_csr *A, int trans, const kry_vec *x, kry_vec *y)
+{
+    KRY_TRY(check_spmv_args("kry_spmv", A, trans, x, y));
+    KRY_CUDA(cudaSetDevice(A->ctx->device));
+    KRY_TRY(kry_halo_exchange(A, x->d));
+    GatherPlain g{x->d};
+    EpiStoreDots<0> e;
+    e.y = y->d;
+    e.w[0] = nullptr;
+    return spmv_launch<0>(A, trans != 0, g, e, NoFin(), A->ctx->never_done, 0);
+}
+
+template <int ND>
+static int spmv_dot_nd(kry_csr *A, int trans, const kry_vec *x, kry_vec *y,
+                       const kry_vec *const *dot_with, int slot0)
+{
+    kry_ctx *c = A->ctx;
+    GatherPlain g{x->d};
+    EpiStoreDots<ND> e;
+    e.y = y->d;
+    for (int d = 0; d < ND; ++d) e.w[d] = (dot_with && dot_with[d]) ? dot_with[d]->d : nullptr;
+    SlotFin fin{c->scalars + slot0, ND};
+    if (c->nranks > 1 && A->halo.active) {
+        // sharded: local sums -> all-reduce -> publish
+        extern int kry_allreduce_sums(kry_ctx * c, int n);
+        KRY_TRY(spmv_launch<ND>(A, trans != 0, g, e, fin, c->never_done, 1));
+        KRY_TRY(kry_allreduce_sums(c, ND));
+        return finalize_launch(c, fin, c->never_done);
+    }
+    return spmv_launch<ND>(A, trans != 0, g, e, fin, c->never_done, 0);
+}
+
+extern "C" int kry_spmv_dot(kry_csr *A, int trans, const kry_vec *x, kry_vec *y, int n_dots,
+                            const kry_vec *const *dot_with, int slot0)
+{
+    KRY_TRY(check_spmv_args("kry_spmv_dot", A, trans, x, y));
+    KRY_REQUIRE(n_dots >= 0 && n_dots <= 3, KRY_ERR_INVALID, "kry_spmv_dot: n_dots=%d", n_dots);
+    KRY_REQUIRE(slot0 >= 0 && slot0 + n_dots <= KRY_NUM_SLOTS, KRY_ERR_INVALID,
+                "kry_spmv_dot: scalar slots [%d,%d) out of range", slot0, slot0 + n_dots);
+    for (int d = 0; d < n_dots; ++d)
+        if (dot_with && dot_with[d])
+            KRY_REQUIRE(dot_with[d]->n == y->n, KRY_ERR_SHAPE,
+                        "kry_spmv_dot: dot operand %d has %lld entries, y has %lld", d,
+                        (long long)dot_with[d]->n, (long long)y->n);
+    if (n_dots == 0) return kry_spmv(A, trans, x, y);
+    KRY_CUDA(cudaSetDevice(A->ctx->device));
+    KRY_TRY(kry_halo_exchange(A, x->d));
+    switch (n_dots) {
+        case 1: return spmv_dot_nd<1>(A, trans, x, y, dot_with, slot0);
+        case 2: return spmv_dot_nd<2>(A, trans, x, y, dot_with, slot0);
+        default: return spmv_dot_nd<3>(A, trans, x, y, dot_with, slot0);
+    }
+}
+
+// ------------------------------------------------------------- multi-AXPY
+struct AxpbyDev {
+    double       *z;
+    const double *u, *w;
+    double        a, b;
+    int           a_slot, b_slot, a_neg, b_neg;
+};
+
+template <int ND>
+struct MultiAxpyBody {
+    AxpbyDev      op[4];
+    int           n_ops;
+    const double *du[ND > 0 ? ND : 1], *dw[ND > 0 ? ND : 1];
+    const double *slots;
+    __device__ void init()
+    {
+        for (int k = 0; k < n_ops; ++k) {
+            if (op[k].a_slot >= 0) op[k].a = op[k].a_neg ? -slots[op[k].a_slot] : slots[op[k].a_slot];
+            if (op[k].b_slot >= 0) op[k].b = op[k].b_neg ? -slots[op[k].b_slot] : slots[op[k].b_slot];
+        }
+    }
+    __device__ void update(int64_t i) const
+    {
+        for (int k = 0; k < n_ops; ++k) {
+            const AxpbyDev &o = op[k];
+            double r;
+            if (o.u && o.w)
+                r = __dadd_rn(__dmul_rn(o.a, o.u[i]), __dmul_rn(o.b, o.w[i]));
+            else if (o.u)
+                r = __dmul_rn(o.a, o.u[i]);
+            else if (o.w)
+                r = __dmul_rn(o.b, o.w[i]);
+            else
+                r = 0.0;
+            o.z[i] = r;
+        }
+    }
+    __device__ void operator()(int64_t i, double *acc) const
+    {
+        update(i);
+#pragma unroll
+        for (int d = 0; d < ND; ++d) acc[d] = __dadd_rn(acc[d], __dmul_rn(du[d][i], dw[d][i]));
+    }
+    __device__ void operator()(int64_t i) const { update(i); }
+};
+
+template <int ND>
+static int multi_axpy_nd(kry_ctx *c, int64_t n, int n_ops, const kry_axpby *ops,
+                         const kry_dotspec *dots, int slot0)
+{
+    MultiAxpyBody<ND> b;
+    b.n_ops = n_ops;
+    b.slots = c->scalars;
+    for (int k = 0; k < n_ops; ++k) {
+        b.op[k].z = ops[k].z->d;
+        b.op[k].u = ops[k].u ? ops[k].u->d : nullptr;
+        b.op[k].w = ops[k].w ? ops[k].w->d : nullptr;
+        b.op[k].a = ops[k].a;
+        b.op[k].b = ops[k].b;
+        b.op[k].a_slot = ops[k].a_slot;
+        b.op[k].b_slot = ops[k].b_slot;
+        b.op[k].a_neg = ops[k].a_neg;
+        b.op[k].b_neg = ops[k].b_neg;
+    }
+    if constexpr (ND == 0) {
+        b.du[0] = b.dw[0] = nullptr;
+        return vec_map_launch(c, n, b, c->never_done);
+    } else {
+        for (int d = 0; d < ND; ++d) {
+            b.du[d] = dots[d].u->d;
+            b.dw[d] = dots[d].w->d;
+        }
+        SlotFin fin{c->scalars + slot0, ND};
+        if (c->nranks > 1) {
+            extern int kry_allreduce_sums(kry_ctx * c, int n);
+            KRY_TRY((vec_pass_launch<ND>(c, n, b, fin, c->never_done, 1)));
+            KRY_TRY(kry_allreduce_sums(c, ND));
+            return finalize_launch(c, fin, c->never_done);
+        }
+        return vec_pass_launch<ND>(c, n, b, fin, c->never_done, 0);
+    }
+}
+
+extern "C" int kry_multi_axpy_dot(kry_ctx *c, int n_ops, const kry_axpby *ops, int n_dots,
+                                  const kry_dotspec *dots, int slot0)
+{
+    KRY_REQUIRE(c, KRY_ERR_INVALID, "kry_multi_axpy_dot: NULL context");
+    KRY_REQUIRE(n_ops >= 0 && n_ops <= 4 && n_dots >= 0 && n_dots <= 3 && n_ops + n_dots > 0,
+                KRY_ERR_INVALID, "kry_multi_axpy_dot: n_ops=%d n_dots=%d", n_ops, n_dots);
+    KRY_REQUIRE((n_ops == 0 || ops) && (n_dots == 0 || dots), KRY_ERR_INVALID,
+                "kry_multi_axpy_dot: NULL op/dot array");
+    KRY_REQUIRE(slot0 >= 0 && slot0 + n_dots <= KRY_NUM_SLOTS, KRY_ERR_INVALID,
+                "kry_multi_axpy_dot: scalar slots [%d,%d) out of range", slot0, slot0 + n_dots);
+    int64_t n = -1;
+    auto chk = [&](const kry_vec *v) -> bool {
+        if (!v) return true;
+        if (v->ctx != c) return false;
+        if (n < 0) n = v->n;
+        return v->n == n;
+    };
+    for (int k = 0; k < n_ops; ++k) {
+        KRY_REQUIRE(ops[k].z, KRY_ERR_INVALID, "kry_multi_axpy_dot: op %d has no output", k);
+        KRY_REQUIRE(chk(ops[k].z) && chk(ops[k].u) && chk(ops[k].w), KRY_ERR_SHAPE,
+                    "kry_multi_axpy_dot: op %d operand size/context mismatch", k);
+        KRY_REQUIRE(ops[k].a_slot < KRY_NUM_SLOTS && ops[k].b_slot < KRY_NUM_SLOTS, KRY_ERR_INVALID,
+                    "kry_multi_axpy_dot: op %d scalar slot out of range", k);
+    }
+    for (int d = 0; d < n_dots; ++d) {
+        KRY_REQUIRE(dots[d].u && dots[d].w, KRY_ERR_INVALID, "kry_multi_axpy_dot: dot %d NULL", d);
+        KRY_REQUIRE(chk(dots[d].u) && chk(dots[d].w), KRY_ERR_SHAPE,
+                    "kry_multi_axpy_dot: dot %d operand size/context mismatch", d);
+    }
+    KRY_CUDA(cudaSetDevice(c->device));
+    if (n <= 0) {                       // empty vectors: inner products are exactly 0
+        if (n_dots > 0) KRY_CUDA(cudaMemsetAsync(c->scalars + slot0, 0, n_dots * sizeof(double), c->stream));
+        return KRY_OK;
+    }
+    switch (n_dots) {
+        case 0: return multi_axpy_nd<0>(c, n, n_ops, ops, dots, slot0);
+        case 1: return multi_axpy_nd<1>(c, n, n_ops, ops, dots, slot0);
+        case 2: return multi_axpy_nd<2>(c, n, n_ops, ops, dots, slot0);
+        default: return multi_axpy_nd<3>(c, n, n_ops, ops, dots, slot0);
+    }
+}

@@ -1,0 +1,114 @@
+// solver.cuh -- shared state of the device-resident Krylov iterations.
+//
+// Every solver keeps (a) its vectors in one HBM slab, (b) one DevScalars block
+// holding the scalar recurrence, the reference's counters and the latched
+// `done` flag, (c) a ring buffer of per-iteration scalars that the host drains
+// at its check interval to replay residHistory / log lines.  The host never
+// synchronises inside kry_solver_iterate().
+#pragma once
+
+#include "launch.cuh"
+
+constexpr int KRY_HIST_CAP = 1 << 16;   // ring entries; the host drains more often than this
+
+struct DevScalars {
+    int       done;          // reference loop condition turned false (latched)
+    int       converged;
+    int       definite;      // CG curvature flag (cg/cg.py:119-124)
+    int       istop;         // MINRES
+    int       skip_half;     // Bi-CGSTAB early exit pending (bicgstab.py:110-113)
+    int       pad0;
+    long long n_matvec, n_iter, hist_count, matvec_max;
+    double    resid0, resid, threshold, abstol, reltol;
+    int       check_curvature, window;
+    double    shift, rtol, etol;
+    double    s[64];         // method specific scalars, indices below
+    double    derr[16];      // MINRES truncated direct-error window
+};
+
+// method specific slots in DevScalars::s
+enum {
+    // CG (cg/cg.py); ALPHA/BETA are shared by all methods
+    S_RY = 0, S_PAP, S_ALPHA, S_BETA,
+    // Bi-CGSTAB / CGS / TFQMR
+    S_RHO, S_RHO_NEXT, S_OMEGA, S_R0V, S_TS, S_TT, S_R0T, S_SIGMA,
+    S_THETA, S_ETA, S_TAU, S_K, S_M, S_DCOEF,
+    // MINRES (minres/minres.py:201-205 and the loop scalars)
+    M_BETA1, M_BETA, M_OLDB, M_ALFA, M_DBAR, M_EPSLN, M_OLDEPS, M_DELTA, M_GBAR, M_PHIBAR,
+    M_RHS1, M_RHS2, M_TNORM2, M_YNORM2, M_CS, M_SN, M_GMAX, M_GMIN, M_PHI, M_DENOM,
+    M_ANORM, M_ACOND, M_YNORM, M_ARNORM, M_XNRG2, M_INVBETA, M_TEST1, M_TEST2,
+    M_C_R1, M_C_R2, M_TRNC,
+    S_COUNT
+};
+constexpr int KRY_NSCAL = 64;
+static_assert(S_COUNT <= KRY_NSCAL, "DevScalars::s too small");
+
+struct NamedVec {
+    const char *name;
+    double     *d;
+    int64_t     n;
+};
+
+struct kry_solver {
+    kry_ctx          *ctx;
+    kry_csr          *A;
+    kry_method        method;
+    int64_t           n;        // local rows
+    int64_t           ncap;     // length of vectors that are SpMV inputs (n + halo)
+    double           *slab;
+    NamedVec          vecs[16];
+    int               nvecs;
+    DevScalars       *ds;
+    double           *hist;
+    int               hist_width;
+    double           *dinv;     // optional diagonal preconditioner
+    int               precon_mode;  // 0 none, 1 y = d .* r, 2 y = r ./ d
+    long long         rot;      // MINRES: trips enqueued (buffer rotation schedule)
+    kry_solver_params params;
+    bool              ready;
+    bool              sharded;
+};
+
+static inline double *solver_vec(kry_solver *S, const char *name)
+{
+    for (int i = 0; i < S->nvecs; ++i)
+        if (strcmp(S->vecs[i].name, name) == 0) return S->vecs[i].d;
+    return nullptr;
+}
+
+int kry_allreduce_sums(kry_ctx *c, int n);
+
+#ifdef __CUDACC__
+// append one history entry (width doubles)
+__device__ __forceinline__ void hist_push(DevScalars *s, double *hist, int width, double a, double b)
+{
+    const long long slot = s->hist_count % KRY_HIST_CAP;
+    hist[slot * width] = a;
+    if (width > 1) hist[slot * width + 1] = b;
+    s->hist_count++;
+}
+#endif
+
+// Launch wrappers that route the fused reduction through NCCL on sharded runs.
+template <int ND, class Gather, class Epi, class Fin>
+int solver_spmv(kry_solver *S, Gather g, Epi e, Fin f, const int *done, double *x_dev)
+{
+    if (S->sharded) {
+        KRY_TRY(kry_halo_exchange(S->A, x_dev));
+        KRY_TRY((spmv_launch<ND>(S->A, false, g, e, f, done, 1)));
+        KRY_TRY(kry_allreduce_sums(S->ctx, ND));
+        return finalize_launch(S->ctx, f, done);
+    }
+    return spmv_launch<ND>(S->A, false, g, e, f, done, 0);
+}
+
+template <int ND, class Body, class Fin>
+int solver_pass(kry_solver *S, Body b, Fin f, const int *done)
+{
+    if (S->sharded) {
+        KRY_TRY((vec_pass_launch<ND>(S->ctx, S->n, b, f, done, 1)));
+        KRY_TRY(kry_allreduce_sums(S->ctx, ND));
+        return finalize_launch(S->ctx, f, done);
+    }
+    return vec_pass_launch<ND>(S->ctx, S->n, b, f, done, 0);
+}

@@ -1,0 +1,1490 @@
+// solvers.cu -- device-resident Krylov iterations (C ABI: kry_solver_*).
+//
+// Each method restates the *recurrence* of the reference loop (same operation
+// order per element, un-fused multiply/add, same scalar formulas, same
+// stopping tests) but is laid out for the GPU: every pass over HBM is one
+// fused kernel (SpMV + row-local epilogue + inner products, or several AXPYs +
+// inner products), and the scalar step that follows an inner product runs in
+// the last CTA of the same launch.  Reference line numbers are relative to
+// /root/reference/pykrylov/.
+#include <string.h>
+
+#include <new>
+
+#include "solver.cuh"
+
+// ======================================================================= CG
+// cg/cg.py:113-158.   3 launches per iteration:
+//   K1  Ap = A p ; pAp = p.Ap ; alpha = ry/pAp (+ curvature test)       [spmv]
+//   K2  x += alpha p ; r += alpha Ap ; y = M r ; ry' = r.y ; beta, residNorm, stop test
+//   K3  p = beta p - r
+struct CgEpiAp {
+    double       *Ap;
+    const double *p;
+    __device__ void init() {}
+    __device__ void operator()(int row, double ax, double *acc) const
+    {
+        Ap[row] = ax;
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(p[row], ax));          // cg.py:117
+    }
+};
+
+struct CgFinAp {
+    DevScalars *s;
+    __device__ void operator()(const double *t) const
+    {
+        const double pAp = t[0];
+        s->s[S_PAP] = pAp;
+        s->n_matvec++;                                               // cg.py:116
+        if (s->check_curvature && pAp <= 0.0) {                      // cg.py:119-124
+            s->definite = 0;
+            s->done = 1;
+            return;
+        }
+        s->s[S_ALPHA] = s->s[S_RY] / pAp;                            // cg.py:127
+    }
+};
+
+// precon_mode: 0 none, 1 y = d .* r (DiagonalOperator), 2 y = r ./ d (bmark.py DiagonalPrec)
+__device__ __forceinline__ double apply_diag(const double *d, int mode, int64_t i, double r)
+{
+    if (mode == 1) return __dmul_rn(d[i], r);
+    if (mode == 2) return __ddiv_rn(r, d[i]);
+    return r;
+}
+
+struct CgUpdateBody {
+    double       *x, *r;
+    const double *p, *Ap, *pd;
+    int           pmode;
+    DevScalars   *s;
+    double        alpha;
+    __device__ void init() { alpha = s->s[S_ALPHA]; }
+    __device__ void operator()(int64_t i, double *acc) const
+    {
+        x[i] = __dadd_rn(x[i], __dmul_rn(alpha, p[i]));              // cg.py:130
+        const double rn = __dadd_rn(r[i], __dmul_rn(alpha, Ap[i]));  // cg.py:131
+        r[i] = rn;
+        const double y = apply_diag(pd, pmode, i, rn);               // cg.py:137-140
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(rn, y));                // cg.py:146
+    }
+};
+
+struct CgFinRy {
+    DevScalars *s;
+    double     *hist;
+    __device__ void operator()(const double *t) const
+    {
+        const double ry_next = t[0];
+        s->s[S_BETA] = ry_next / s->s[S_RY];                         // cg.py:149
+        s->s[S_RY] = ry_next;                                        // cg.py:153
+        const double resid = fabs(sqrt(ry_next));                    // cg.py:154
+        s->resid = resid;
+        s->n_iter++;
+        hist_push(s, hist, 2, resid, s->s[S_PAP]);                   // cg.py:155-158
+        if (!(resid > s->threshold && s->n_matvec < s->matvec_max)) s->done = 1;   // cg.py:113
+    }
+};
+
+struct CgDirBody {
+    double       *p;
+    const double *r;
+    DevScalars   *s;
+    double        beta;
+    __device__ void init() { beta = s->s[S_BETA]; }
+    __device__ void operator()(int64_t i) const
+    {
+        p[i] = __dsub_rn(__dmul_rn(beta, p[i]), r[i]);               // cg.py:150-151
+    }
+};
+
+// setup, cg.py:85-104:  r = -rhs (+ A x);  y = M r;  ry = r.y;  p = -r
+struct CgSetupEpi {               // with an initial guess: runs as the SpMV epilogue of A x
+    double       *r, *p;
+    const double *rhs, *pd;
+    int           pmode;
+    __device__ void init() {}
+    __device__ void operator()(int row, double ax, double *acc) const
+    {
+        const double rn = __dadd_rn(-rhs[row], ax);                  // cg.py:85,87
+        r[row] = rn;
+        p[row] = -rn;                                                // cg.py:104
+        const double y = apply_diag(pd, pmode, row, rn);
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(rn, y));                // cg.py:99
+    }
+};
+
+struct CgSetupBody {              // zero initial guess
+    double       *r, *p;
+    const double *rhs, *pd;
+    int           pmode;
+    __device__ void init() {}
+    __device__ void operator()(int64_t i, double *acc) const
+    {
+        const double rn = -rhs[i];
+        r[i] = rn;
+        p[i] = -rn;
+        const double y = apply_diag(pd, pmode, i, rn);
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(rn, y));
+    }
+};
+
+struct CgSetupFin {
+    DevScalars *s;
+    double     *hist;
+    int         guess;
+    __device__ void operator()(const double *t) const
+    {
+        s->s[S_RY] = t[0];
+        const double resid = fabs(sqrt(t[0]));                       // cg.py:100
+        s->resid0 = s->resid = resid;
+        s->threshold = fmax(s->abstol, s->reltol * resid);           // cg.py:102
+        s->n_matvec = guess ? 1 : 0;                                 // cg.py:88
+        hist_push(s, hist, 2, resid, nan(""));
+        if (!(resid > s->threshold && s->n_matvec < s->matvec_max)) s->done = 1;
+    }
+};
+
+static int cg_setup(kry_solver *S, int guess)
+{
+    double *x = solver_vec(S, "x"), *r = solver_vec(S, "r"), *p = solver_vec(S, "p");
+    double *rhs = solver_vec(S, "rhs");
+    CgSetupFin fin{S->ds, S->hist, guess};
+    if (guess) {
+        CgSetupEpi e{r, p, rhs, S->dinv, S->precon_mode};
+        return solver_spmv<1>(S, GatherPlain{x}, e, fin, &S->ds->done, x);
+    }
+    CgSetupBody b{r, p, rhs, S->dinv, S->precon_mode};
+    return solver_pass<1>(S, b, fin, &S->ds->done);
+}
+
+static int cg_iterate(kry_solver *S)
+{
+    double *x = solver_vec(S, "x"), *r = solver_vec(S, "r"), *p = solver_vec(S, "p");
+    double *Ap = solver_vec(S, "Ap");
+    const int *done = &S->ds->done;
+    KRY_TRY((solver_spmv<1>(S, GatherPlain{p}, CgEpiAp{Ap, p}, CgFinAp{S->ds}, done, p)));
+    CgUpdateBody ub{x, r, p, Ap, S->dinv, S->precon_mode, S->ds, 0.0};
+    KRY_TRY((solver_pass<1>(S, ub, CgFinRy{S->ds, S->hist}, done)));
+    CgDirBody db{p, r, S->ds, 0.0};
+    return vec_map_launch(S->ctx, S->n, db, done);
+}
+
+// ================================================================ Bi-CGSTAB
+// bicgstab/bicgstab.py:85-145.  4 launches per iteration (the p update of the
+// next iteration rides in the last one):
+//   KB  v = A q ; r0.v ; alpha = rho/(r0.v)                               [spmv]
+//   KC  s = r - alpha v ; |s| ; early-exit test
+//   KD  t = A z ; t.s, t.t, r0.t ; omega, rho', beta                      [spmv]
+//   KE  r = s - omega t ; z *= omega ; x += z ; x += alpha q ; |r| ; stop test ;
+//       p = beta p - beta omega v + r ; q = M p
+struct BcgEpiV {
+    double       *v;
+    const double *r0;
+    __device__ void init() {}
+    __device__ void operator()(int row, double ax, double *acc) const
+    {
+        v[row] = ax;
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(r0[row], ax));          // bicgstab.py:103
+    }
+};
+
+struct BcgFinV {
+    DevScalars *s;
+    __device__ void operator()(const double *t) const
+    {
+        s->n_matvec++;                                               // :101
+        s->s[S_R0V] = t[0];
+        s->s[S_ALPHA] = s->s[S_RHO] / t[0];                          // :103
+    }
+};
+
+struct BcgBodyS {
+    double       *sv, *z;
+    const double *r, *v, *pd;
+    int           pmode;
+    DevScalars   *s;
+    double        alpha;
+    __device__ void init() { alpha = s->s[S_ALPHA]; }
+    __device__ void operator()(int64_t i, double *acc) const
+    {
+        const double si = __dsub_rn(r[i], __dmul_rn(alpha, v[i]));   // :104
+        sv[i] = si;
+        if (pmode) z[i] = apply_diag(pd, pmode, i, si);              // :120-123
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(si, si));               // :107
+    }
+};
+
+struct BcgFinS {
+    DevScalars *s;
+    double     *hist;
+    __device__ void operator()(const double *t) const
+    {
+        const double resid = sqrt(t[0]);
+        s->resid = resid;
+        hist_push(s, hist, 1, resid, 0.0);                           // :109
+        if (resid <= s->threshold) {                                 // :110-113
+            s->skip_half = 1;      // KE applies x += alpha q and latches done
+        } else if (s->n_matvec >= s->matvec_max) {                   // :115-117
+            s->skip_half = 2;      // nothing more to do; KE latches done
+        }
+    }
+};
+
+struct BcgEpiT {
+    double       *t;
+    const double *sv, *r0;
+    __device__ void init() {}
+    __device__ void operator()(int row, double ax, double *acc) const
+    {
+        t[row] = ax;
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(ax, sv[row]));          // t.s  :126
+        acc[1] = __dadd_rn(acc[1], __dmul_rn(ax, ax));               // t.t  :126
+        acc[2] = __dadd_rn(acc[2], __dmul_rn(r0[row], ax));          // r0.t :127
+    }
+};
+
+struct BcgFinT {
+    DevScalars *s;
+    __device__ void operator()(const double *t) const
+    {
+        s->n_matvec++;                                               // :125
+        s->s[S_TS] = t[0];
+        s->s[S_TT] = t[1];
+        s->s[S_R0T] = t[2];
+        const double omega = t[0] / t[1];                            // :126
+        s->s[S_OMEGA] = omega;
+        const double rho_next = -omega * t[2];                       // :127
+        s->s[S_RHO_NEXT] = rho_next;
+        // scalars of the next trip, bicgstab.py:87-88
+        s->s[S_BETA] = rho_next / s->s[S_RHO] * s->s[S_ALPHA] / omega;
+        s->s[S_RHO] = rho_next;
+    }
+};
+
+struct BcgBodyX {
+    double       *x, *r, *p, *q, *sv, *z;
+    const double *t, *v, *pd;
+    int           pmode;
+    DevScalars   *s;
+    double        alpha, omega, beta, bo;
+    int           half;
+    __device__ void init()
+    {
+        alpha = s->s[S_ALPHA];
+        omega = s->s[S_OMEGA];
+        beta = s->s[S_BETA];
+        bo = __dmul_rn(beta, omega);
+        half = s->skip_half;
+    }
+    __device__ void operator()(int64_t i, double *acc) const
+    {
+        const double qi = pmode ? q[i] : p[i];
+        if (half) {
+            if (half == 1) x[i] = __dadd_rn(x[i], __dmul_rn(alpha, qi));     // :111
+            return;
+        }
+        const double ri = __dsub_rn(sv[i], __dmul_rn(omega, t[i]));          // :130
+        r[i] = ri;
+        const double zi = __dmul_rn(pmode ? z[i] : sv[i], omega);            // :135
+        double xi = __dadd_rn(x[i], zi);                                     // :136
+        xi = __dadd_rn(xi, __dmul_rn(alpha, qi));                            // :137
+        x[i] = xi;
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(ri, ri));                       // :139
+        // next trip's direction, bicgstab.py:91-93
+        double pi = __dmul_rn(p[i], beta);
+        pi = __dsub_rn(pi, __dmul_rn(bo, v[i]));
+        pi = __dadd_rn(pi, ri);
+        p[i] = pi;
+        if (pmode) q[i] = apply_diag(pd, pmode, i, pi);                      // :96-99
+    }
+};
+
+struct BcgFinX {
+    DevScalars *s;
+    double     *hist;
+    __device__ void operator()(const double *t) const
+    {
+        s->n_iter++;
+        if (s->skip_half) {          // stays latched: it also gates the second SpMV
+            s->done = 1;
+            return;
+        }
+        const double resid = sqrt(t[0]);
+        s->resid = resid;
+        hist_push(s, hist, 1, resid, 0.0);                                   // :141
+        if (resid <= s->threshold || s->n_matvec >= s->matvec_max) {         // :142
+            s->done = 1;
+            s->skip_half = 3;
+        }
+    }
+};
+
+// setup, bicgstab.py:62-83
+struct R0SetupEpi {      // r0 = rhs - A x, fused rho = r0.r0, copies into the work vectors
+    double       *r0, *a, *b;      // a, b: optional copies (r / p ...), may be null
+    const double *rhs;
+    __device__ void init() {}
+    __device__ void operator()(int row, double ax, double *acc) const
+    {
+        const double v = __dsub_rn(rhs[row], ax);                            // :64
+        r0[row] = v;
+        if (a) a[row] = v;
+        if (b) b[row] = v;
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(v, v));                         // :68
+    }
+};
+
+struct R0SetupBody {     // zero guess: r0 = rhs
+    double       *r0, *a, *b;
+    const double *rhs;
+    __device__ void init() {}
+    __device__ void operator()(int64_t i, double *acc) const
+    {
+        const double v = rhs[i];
+        r0[i] = v;
+        if (a) a[i] = v;
+        if (b) b[i] = v;
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(v, v));
+    }
+};
+
+struct BcgSetupFin {
+    DevScalars *s;
+    double     *hist;
+    int         guess;
+    __device__ void operator()(const double *t) const
+    {
+        const double rho_next = t[0];
+        const double resid = fabs(sqrt(rho_next));                           // :69
+        s->resid0 = s->resid = resid;
+        s->threshold = fmax(s->abstol, s->reltol * resid);
+        s->n_matvec = guess ? 1 : 0;                                         // :65
+        hist_push(s, hist, 1, resid, 0.0);
+        s->s[S_ALPHA] = 1.0;                                                 // :67
+        s->s[S_OMEGA] = 1.0;
+        s->s[S_RHO_NEXT] = rho_next;
+        s->s[S_BETA] = rho_next / 1.0 * 1.0 / 1.0;                           // :87 first trip
+        s->s[S_RHO] = rho_next;                                              // :88
+        if (resid <= s->threshold || s->n_matvec >= s->matvec_max) {         // :72
+            s->done = 1;
+            s->skip_half = 3;
+        }
+    }
+};
+
+struct DiagApplyBody {   // q = M p
+    double       *q;
+    const double *p, *pd;
+    int           pmode;
+    __device__ void init() {}
+    __device__ void operator()(int64_t i) const { q[i] = apply_diag(pd, pmode, i, p[i]); }
+};
+
+static int bicgstab_setup(kry_solver *S, int guess)
+{
+    double *x = solver_vec(S, "x"), *r0 = solver_vec(S, "r0"), *r = solver_vec(S, "r");
+    double *p = solver_vec(S, "p"), *rhs = solver_vec(S, "rhs"), *v = solver_vec(S, "v");
+    BcgSetupFin fin{S->ds, S->hist, guess};
+    KRY_CUDA(cudaMemsetAsync(v, 0, (size_t)S->n * sizeof(double), S->ctx->stream));   // :83
+    // first trip: p = beta*0 - beta*omega*0 + r = r  (bicgstab.py:82,91-93)
+    if (guess) {
+        R0SetupEpi e{r0, r, p, rhs};
+        KRY_TRY((solver_spmv<1>(S, GatherPlain{x}, e, fin, &S->ds->done, x)));
+    } else {
+        R0SetupBody b{r0, r, p, rhs};
+        KRY_TRY((solver_pass<1>(S, b, fin, &S->ds->done)));
+    }
+    if (S->precon_mode) {
+        DiagApplyBody q{solver_vec(S, "q"), p, S->dinv, S->precon_mode};
+        KRY_TRY(vec_map_launch(S->ctx, S->n, q, &S->ds->done));
+    }
+    return KRY_OK;
+}
+
+static int bicgstab_iterate(kry_solver *S)
+{
+    double *x = solver_vec(S, "x"), *r0 = solver_vec(S, "r0"), *r = solver_vec(S, "r");
+    double *p = solver_vec(S, "p"), *v = solver_vec(S, "v"), *sv = solver_vec(S, "s");
+    double *t = solver_vec(S, "t"), *q = solver_vec(S, "q"), *z = solver_vec(S, "z");
+    const int pm = S->precon_mode;
+    const int *done = &S->ds->done;
+    const int *skip = &S->ds->skip_half;
+    double *qin = pm ? q : p;
+    KRY_TRY((solver_spmv<1>(S, GatherPlain{qin}, BcgEpiV{v, r0}, BcgFinV{S->ds}, done, qin)));
+    BcgBodyS bs{sv, z, r, v, S->dinv, pm, S->ds, 0.0};
+    KRY_TRY((solver_pass<1>(S, bs, BcgFinS{S->ds, S->hist}, done)));
+    double *zin = pm ? z : sv;
+    // `skip` doubles as the early-out flag of the second half
+    KRY_TRY((solver_spmv<3>(S, GatherPlain{zin}, BcgEpiT{t, sv, r0}, BcgFinT{S->ds}, skip, zin)));
+    BcgBodyX bx{x, r, p, q, sv, z, t, v, S->dinv, pm, S->ds, 0, 0, 0, 0, 0};
+    return solver_pass<1>(S, bx, BcgFinX{S->ds, S->hist}, done);
+}
+
+// ====================================================================== CGS
+// cgs/cgs.py:76-117.  4 launches per iteration:
+//   K1  v = A y ; sigma = r0.v ; alpha = rho/sigma                        [spmv]
+//   K2  q = u - alpha v ; z = M (u + q) ; x += alpha z
+//   K3  r -= alpha (A z) ; |r| ; rho' = r0.r ; stop test ; beta           [spmv]
+//   K4  u = r + beta q ; p = beta (beta p + q) + u ; y = M p
+struct CgsEpiV {
+    double       *v;
+    const double *r0;
+    __device__ void init() {}
+    __device__ void operator()(int row, double ax, double *acc) const
+    {
+        v[row] = ax;
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(r0[row], ax));                  // cgs.py:85
+    }
+};
+
+struct CgsFinV {
+    DevScalars *s;
+    __device__ void operator()(const double *t) const
+    {
+        s->n_matvec++;                                                       // :84
+        s->s[S_SIGMA] = t[0];
+        s->s[S_ALPHA] = s->s[S_RHO] / t[0];                                  // :86
+    }
+};
+
+struct CgsBodyQ {
+    double       *q, *z, *x;
+    const double *u, *v, *pd;
+    int           pmode;
+    DevScalars   *s;
+    double        alpha;
+    __device__ void init() { alpha = s->s[S_ALPHA]; }
+    __device__ void operator()(int64_t i) const
+    {
+        const double qi = __dsub_rn(u[i], __dmul_rn(alpha, v[i]));           // :87
+        q[i] = qi;
+        const double zi = apply_diag(pd, pmode, i, __dadd_rn(u[i], qi));     // :89-92
+        z[i] = zi;
+        x[i] = __dadd_rn(x[i], __dmul_rn(alpha, zi));                        // :95
+    }
+};
+
+struct CgsEpiR {
+    double       *r;
+    const double *r0;
+    DevScalars   *s;
+    double        alpha;
+    __device__ void init() { alpha = s->s[S_ALPHA]; }
+    __device__ void operator()(int row, double ax, double *acc) const
+    {
+        const double ri = __dsub_rn(r[row], __dmul_rn(alpha, ax));           // :97
+        r[row] = ri;
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(ri, ri));                       // :100
+        acc[1] = __dadd_rn(acc[1], __dmul_rn(r0[row], ri));                  // :106
+    }
+};
+
+struct CgsFinR {
+    DevScalars *s;
+    double     *hist;
+    __device__ void operator()(const double *t) const
+    {
+        s->n_matvec++;                                                       // :96
+        s->n_iter++;
+        const double resid = sqrt(t[0]);
+        s->resid = resid;
+        hist_push(s, hist, 1, resid, 0.0);
+        if (resid <= s->threshold || s->n_matvec >= s->matvec_max) {         // :102-104
+            s->done = 1;
+            return;
+        }
+        const double rho_next = t[1];
+        s->s[S_BETA] = rho_next / s->s[S_RHO];                               // :107
+        s->s[S_RHO] = rho_next;                                              // :108
+    }
+};
+
+struct CgsBodyP {
+    double       *u, *p, *y;
+    const double *r, *q, *pd;
+    int           pmode;
+    DevScalars   *s;
+    double        beta;
+    __device__ void init() { beta = s->s[S_BETA]; }
+    __device__ void operator()(int64_t i) const
+    {
+        const double ui = __dadd_rn(r[i], __dmul_rn(beta, q[i]));            // :109
+        u[i] = ui;
+        double pi = __dmul_rn(p[i], beta);                                   // :112-115
+        pi = __dadd_rn(pi, q[i]);
+        pi = __dmul_rn(pi, beta);
+        pi = __dadd_rn(pi, ui);
+        p[i] = pi;
+        if (pmode) y[i] = apply_diag(pd, pmode, i, pi);                      // :79-82
+    }
+};
+
+struct RhoSetupFin {     // CGS / TFQMR: rho = r0.r0, residNorm0, threshold (matvec NOT counted)
+    DevScalars *s;
+    double     *hist;
+    long long   nmv0;
+    __device__ void operator()(const double *t) const
+    {
+        s->s[S_RHO] = t[0];                                                  // cgs.py:62, tfqmr.py:61
+        const double resid = fabs(sqrt(t[0]));
+        s->resid0 = s->resid = resid;
+        s->threshold = fmax(s->abstol, s->reltol * resid);
+        s->n_matvec = nmv0;
+        hist_push(s, hist, 1, resid, 0.0);
+        if (resid <= s->threshold || s->n_matvec >= s->matvec_max) s->done = 1;
+    }
+};
+
+static int cgs_setup(kry_solver *S, int guess)
+{
+    double *x = solver_vec(S, "x"), *r0 = solver_vec(S, "r0"), *r = solver_vec(S, "r");
+    double *p = solver_vec(S, "p"), *u = solver_vec(S, "u"), *rhs = solver_vec(S, "rhs");
+    RhoSetupFin fin{S->ds, S->hist, 0};
+    if (guess) {
+        R0SetupEpi e{r0, r, p, rhs};
+        KRY_TRY((solver_spmv<1>(S, GatherPlain{x}, e, fin, &S->ds->done, x)));
+    } else {
+        R0SetupBody b{r0, r, p, rhs};
+        KRY_TRY((solver_pass<1>(S, b, fin, &S->ds->done)));
+    }
+    KRY_CUDA(cudaMemcpyAsync(u, r0, (size_t)S->n * sizeof(double), cudaMemcpyDeviceToDevice,
+                             S->ctx->stream));                               // cgs.py:73
+    if (S->precon_mode) {
+        DiagApplyBody y{solver_vec(S, "y"), p, S->dinv, S->precon_mode};
+        KRY_TRY(vec_map_launch(S->ctx, S->n, y, &S->ds->done));
+    }
+    return KRY_OK;
+}
+
+static int cgs_iterate(kry_solver *S)
+{
+    double *x = solver_vec(S, "x"), *r0 = solver_vec(S, "r0"), *r = solver_vec(S, "r");
+    double *p = solver_vec(S, "p"), *u = solver_vec(S, "u"), *q = solver_vec(S, "q");
+    double *v = solver_vec(S, "v"), *z = solver_vec(S, "z"), *y = solver_vec(S, "y");
+    const int pm = S->precon_mode;
+    const int *done = &S->ds->done;
+    double *yin = pm ? y : p;
+    KRY_TRY((solver_spmv<1>(S, GatherPlain{yin}, CgsEpiV{v, r0}, CgsFinV{S->ds}, done, yin)));
+    CgsBodyQ bq{q, z, x, u, v, S->dinv, pm, S->ds, 0.0};
+    KRY_TRY(vec_map_launch(S->ctx, S->n, bq, done));
+    CgsEpiR er{r, r0, S->ds, 0.0};
+    KRY_TRY((solver_spmv<2>(S, GatherPlain{z}, er, CgsFinR{S->ds, S->hist}, done, z)));
+    CgsBodyP bp{u, p, y, r, q, S->dinv, pm, S->ds, 0.0};
+    return vec_map_launch(S->ctx, S->n, bp, done);
+}
+
+// ==================================================================== TFQMR
+// tfqmr/tfqmr.py:85-153.  State: x, r0, y, w, d, u, v (+ z = M y).  The two
+// half-steps share one kernel (`TfqHalfBody`); launches per iteration:
+//   K1  sigma = r0.v -> alpha                (fused into the tail of the previous trip's
+//                                             SpMV when possible; a plain dot on trip 1)
+//   K2  w -= alpha u ; |w|                                       first half, :92,95
+//   K3  d = coef d + z ; x += eta d ; y -= alpha v ; z = M y     :93-94,99,109  (needs theta, eta)
+//   K4  u = A z ; w -= alpha u ; |w|                             :114-118       [spmv]
+//   K5  d = coef d + z ; x += eta d ; (rho' = r0.w)              :117-123,128
+//   K6  y = beta y + w ; v = beta (beta v + u) ; z = M y          :133-139
+//   K7  u = A z ; v += u ; sigma = r0.v -> alpha of next trip     :146-149       [spmv]
+struct TfqBodyW {             // w -= alpha u ; |w|^2
+    double       *w;
+    const double *u;
+    DevScalars   *s;
+    double        alpha;
+    __device__ void init() { alpha = s->s[S_ALPHA]; }
+    __device__ void operator()(int64_t i, double *acc) const
+    {
+        const double wi = __dsub_rn(w[i], __dmul_rn(alpha, u[i]));           // :92 / :116
+        w[i] = wi;
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(wi, wi));
+    }
+};
+
+// scalar part shared by both halves, tfqmr.py:93,95-98 / :117,119-122
+__device__ __forceinline__ void tfq_half_scalars(DevScalars *s, double *hist, double wnorm2, double m)
+{
+    const double theta_old = s->s[S_THETA], eta_old = s->s[S_ETA], alpha = s->s[S_ALPHA];
+    s->s[S_DCOEF] = theta_old * theta_old * eta_old / alpha;                 // :93 (uses OLD theta, eta)
+    const double theta = sqrt(wnorm2) / s->resid;                            // :95
+    const double c = 1.0 / sqrt(1 + theta * theta);                          // :96
+    s->resid = s->resid * (theta * c);                                       // :97
+    s->s[S_THETA] = theta;
+    s->s[S_ETA] = c * c * alpha;                                             // :98
+    s->s[S_M] = m;
+    hist_push(s, hist, 1, s->resid, 0.0);
+}
+
+struct TfqFinW1 {
+    DevScalars *s;
+    double     *hist;
+    __device__ void operator()(const double *t) const
+    {
+        const double m = 2.0 * s->s[S_K] - 1.0;                              // :101
+        tfq_half_scalars(s, hist, t[0], m);
+        // stop test is applied after x has been updated (K3 latches it): :103-105
+        if (s->resid * sqrt(m + 1) < s->threshold || s->n_matvec >= s->matvec_max) s->skip_half = 1;
+    }
+};
+
+struct TfqBodyD1 {            // d = coef d + z ; x += eta d ; then (if continuing) y -= alpha v ; z = M y
+    double       *d, *x, *y, *z;
+    const double *v, *pd;
+    int           pmode;
+    DevScalars   *s;
+    double        coef, eta, alpha;
+    int           stop;
+    __device__ void init()
+    {
+        coef = s->s[S_DCOEF];
+        eta = s->s[S_ETA];
+        alpha = s->s[S_ALPHA];
+        stop = s->skip_half;
+    }
+    __device__ void operator()(int64_t i, double *acc) const
+    {
+        const double zi = pmode ? z[i] : y[i];
+        const double di = __dadd_rn(__dmul_rn(d[i], coef), zi);              // :93-94
+        d[i] = di;
+        x[i] = __dadd_rn(x[i], __dmul_rn(eta, di));                          // :99
+        if (stop) return;
+        const double yi = __dsub_rn(y[i], __dmul_rn(alpha, v[i]));           // :109
+        y[i] = yi;
+        if (pmode) z[i] = apply_diag(pd, pmode, i, yi);                      // :110-113
+    }
+};
+
+struct TfqFinD1 {
+    DevScalars *s;
+    __device__ void operator()(const double *) const
+    {
+        if (s->skip_half) {
+            s->skip_half = 0;
+            s->n_iter++;
+            s->done = 1;
+        }
+    }
+};
+
+struct TfqEpiU2 {             // u = A z ; w -= alpha u ; |w|^2
+    double     *u, *w;
+    DevScalars *s;
+    double      alpha;
+    __device__ void init() { alpha = s->s[S_ALPHA]; }
+    __device__ void operator()(int row, double ax, double *acc) const
+    {
+        u[row] = ax;                                                         // :114
+        const double wi = __dsub_rn(w[row], __dmul_rn(alpha, ax));           // :116
+        w[row] = wi;
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(wi, wi));
+    }
+};
+
+struct TfqFinW2 {
+    DevScalars *s;
+    double     *hist;
+    __device__ void operator()(const double *t) const
+    {
+        s->n_matvec++;                                                       // :114
+        const double m = 2.0 * s->s[S_K];                                    // :108
+        tfq_half_scalars(s, hist, t[0], m);
+        if (s->resid * sqrt(m + 1) < s->threshold || s->n_matvec >= s->matvec_max) s->skip_half = 1;
+    }
+};
+
+struct TfqBodyD2 {            // d = coef d + z ; x += eta d ; rho' = r0.w
+    double       *d, *x;
+    const double *y, *z, *r0, *w;
+    int           pmode;
+    DevScalars   *s;
+    double        coef, eta;
+    __device__ void init()
+    {
+        coef = s->s[S_DCOEF];
+        eta = s->s[S_ETA];
+    }
+    __device__ void operator()(int64_t i, double *acc) const
+    {
+        const double zi = pmode ? z[i] : y[i];
+        const double di = __dadd_rn(__dmul_rn(d[i], coef), zi);              // :117-118
+        d[i] = di;
+        x[i] = __dadd_rn(x[i], __dmul_rn(eta, di));                          // :123
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(r0[i], w[i]));                  // :128
+    }
+};
+
+struct TfqFinD2 {
+    DevScalars *s;
+    __device__ void operator()(const double *t) const
+    {
+        s->n_iter++;
+        if (s->skip_half) {                                                  // :125-127
+            s->skip_half = 0;
+            s->done = 1;
+            return;
+        }
+        s->s[S_BETA] = t[0] / s->s[S_RHO];                                   // :129
+        s->s[S_RHO] = t[0];                                                  // :130
+    }
+};
+
+struct TfqBodyYV {            // y = beta y + w ; v = beta (beta v + u) ; z = M y
+    double       *y, *v, *z;
+    const double *w, *u, *pd;
+    int           pmode;
+    DevScalars   *s;
+    double        beta;
+    __device__ void init() { beta = s->s[S_BETA]; }
+    __device__ void operator()(int64_t i) const
+    {
+        const double yi = __dadd_rn(__dmul_rn(y[i], beta), w[i]);            // :133-134
+        y[i] = yi;
+        double vi = __dmul_rn(v[i], beta);                                   // :137-139
+        vi = __dadd_rn(vi, u[i]);
+        vi = __dmul_rn(vi, beta);
+        v[i] = vi;
+        if (pmode) z[i] = apply_diag(pd, pmode, i, yi);                      // :142-145
+    }
+};
+
+struct TfqEpiU3 {             // u = A z ; v += u ; sigma = r0.v (next trip)
+    double       *u, *v;
+    const double *r0;
+    __device__ void init() {}
+    __device__ void operator()(int row, double ax, double *acc) const
+    {
+        u[row] = ax;                                                         // :146
+        const double vi = __dadd_rn(v[row], ax);                             // :149
+        v[row] = vi;
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(r0[row], vi));                  // :88 of the next trip
+    }
+};
+
+struct TfqFinU3 {
+    DevScalars *s;
+    __device__ void operator()(const double *t) const
+    {
+        s->n_matvec++;                                                       // :146
+        s->s[S_K] += 1.0;                                                    // :87 next trip
+        s->s[S_SIGMA] = t[0];
+        s->s[S_ALPHA] = s->s[S_RHO] / t[0];                                  // :89
+    }
+};
+
+struct TfqSetupEpiU {         // u = A z ; v = u  (tfqmr.py:84-85) ; sigma = r0.v for trip 1
+    double       *u, *v;
+    const double *r0;
+    __device__ void init() {}
+    __device__ void operator()(int row, double ax, double *acc) const
+    {
+        u[row] = ax;
+        v[row] = ax;
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(r0[row], ax));
+    }
+};
+
+struct TfqSetupFinU {
+    DevScalars *s;
+    __device__ void operator()(const double *t) const
+    {
+        s->n_matvec++;                                                       // :84
+        s->s[S_K] = 1.0;                                                     // :87 first trip
+        s->s[S_SIGMA] = t[0];
+        s->s[S_ALPHA] = s->s[S_RHO] / t[0];                                  // :89
+        s->s[S_THETA] = 0.0;                                                 // :76-77
+        s->s[S_ETA] = 0.0;
+    }
+};
+
+static int tfqmr_setup(kry_solver *S, int guess)
+{
+    double *x = solver_vec(S, "x"), *r0 = solver_vec(S, "r0"), *y = solver_vec(S, "y");
+    double *w = solver_vec(S, "w"), *d = solver_vec(S, "d"), *u = solver_vec(S, "u");
+    double *v = solver_vec(S, "v"), *z = solver_vec(S, "z"), *rhs = solver_vec(S, "rhs");
+    const int pm = S->precon_mode;
+    RhoSetupFin fin{S->ds, S->hist, 0};
+    if (guess) {
+        R0SetupEpi e{r0, y, w, rhs};
+        KRY_TRY((solver_spmv<1>(S, GatherPlain{x}, e, fin, &S->ds->done, x)));
+    } else {
+        R0SetupBody b{r0, y, w, rhs};
+        KRY_TRY((solver_pass<1>(S, b, fin, &S->ds->done)));
+    }
+    KRY_CUDA(cudaMemsetAsync(d, 0, (size_t)S->n * sizeof(double), S->ctx->stream));     // :75
+    if (pm) {
+        DiagApplyBody zb{z, y, S->dinv, pm};
+        KRY_TRY(vec_map_launch(S->ctx, S->n, zb, &S->ds->done));
+    }
+    double *zin = pm ? z : y;
+    return solver_spmv<1>(S, GatherPlain{zin}, TfqSetupEpiU{u, v, r0}, TfqSetupFinU{S->ds},
+                          &S->ds->done, zin);
+}
+
+static int tfqmr_iterate(kry_solver *S)
+{
+    double *x = solver_vec(S, "x"), *r0 = solver_vec(S, "r0"), *y = solver_vec(S, "y");
+    double *w = solver_vec(S, "w"), *d = solver_vec(S, "d"), *u = solver_vec(S, "u");
+    double *v = solver_vec(S, "v"), *z = solver_vec(S, "z");
+    const int pm = S->precon_mode;
+    const int *done = &S->ds->done;
+    // first half
+    TfqBodyW bw{w, u, S->ds, 0.0};
+    KRY_TRY((solver_pass<1>(S, bw, TfqFinW1{S->ds, S->hist}, done)));
+    TfqBodyD1 bd1{d, x, y, z, v, S->dinv, pm, S->ds, 0, 0, 0, 0};
+    KRY_TRY((solver_pass<1>(S, bd1, TfqFinD1{S->ds}, done)));
+    // second half
+    double *zin = pm ? z : y;
+    TfqEpiU2 eu2{u, w, S->ds, 0.0};
+    KRY_TRY((solver_spmv<1>(S, GatherPlain{zin}, eu2, TfqFinW2{S->ds, S->hist}, done, zin)));
+    TfqBodyD2 bd2{d, x, y, z, r0, w, pm, S->ds, 0, 0};
+    KRY_TRY((solver_pass<1>(S, bd2, TfqFinD2{S->ds}, done)));
+    // final updates
+    TfqBodyYV byv{y, v, z, w, u, S->dinv, pm, S->ds, 0.0};
+    KRY_TRY(vec_map_launch(S->ctx, S->n, byv, done));
+    return solver_spmv<1>(S, GatherPlain{zin}, TfqEpiU3{u, v, r0}, TfqFinU3{S->ds}, done, zin);
+}
+
+// =================================================================== MINRES
+// minres/minres.py:218-383.  3 launches per iteration:
+//   K1  v = y/beta (on the fly) ; y' = A v - shift v - (beta/oldb) r1 ; alfa = v.y'   [spmv]
+//   K2  y = y' - (alfa/beta) r2 ; r1 <- r2 ; r2 <- y ; (y = M r2) ; beta' = r2.y ;
+//       whole scalar QR step, norms and the five stopping tests on device
+//   K3  w = (v - oldeps w1 - delta w2)/gamma ; x += phi w      (w1 <- w2 <- w rotate)
+// Vectors rotate by pointer on the host side (the launch sequence is static, so
+// the rotation is a fixed period-3 / period-2 schedule, see minres_iterate()).
+struct MinGather {            // x[c] * (1/beta): v = s*y with s = 1.0/beta, minres.py:236-237
+    const double *y;
+    DevScalars   *s;
+    double        inv;
+    __device__ void   init() { inv = 1.0 / s->s[M_BETA]; }
+    __device__ double operator()(int c) const { return __dmul_rn(inv, __ldg(y + c)); }
+};
+
+struct MinEpiY {
+    double       *yn;         // y' (becomes r2 after K2)
+    const double *y, *r1;
+    DevScalars   *s;
+    double        inv, shift, c_r1;
+    int           first;
+    __device__ void init()
+    {
+        inv = 1.0 / s->s[M_BETA];
+        shift = s->shift;
+        first = (s->n_iter == 0);
+        c_r1 = first ? 0.0 : s->s[M_BETA] / s->s[M_OLDB];                    // :243
+    }
+    __device__ void operator()(int row, double ax, double *acc) const
+    {
+        const double vi = __dmul_rn(inv, y[row]);                            // :237
+        double yi = __dsub_rn(ax, __dmul_rn(shift, vi));                     // :240
+        if (!first) yi = __dsub_rn(yi, __dmul_rn(c_r1, r1[row]));            // :242-243
+        yn[row] = yi;
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(vi, yi));                       // :245
+    }
+};
+
+struct MinFinAlfa {
+    DevScalars *s;
+    __device__ void operator()(const double *t) const
+    {
+        s->s[M_ALFA] = t[0];
+        s->s[M_C_R2] = -t[0] / s->s[M_BETA];                                 // :246
+    }
+};
+
+struct MinBodyR2 {            // y = (-alfa/beta) r2 + y' ; beta'^2 = r2new . (M r2new)
+    double       *yn, *ypre;
+    const double *r2, *pd;
+    int           pmode;
+    DevScalars   *s;
+    double        c;
+    __device__ void init() { c = s->s[M_C_R2]; }
+    __device__ void operator()(int64_t i, double *acc) const
+    {
+        const double yi = __dadd_rn(__dmul_rn(c, r2[i]), yn[i]);             // :246
+        yn[i] = yi;                                                          // :248 (new r2)
+        const double yp = apply_diag(pd, pmode, i, yi);                      // :249
+        if (pmode) ypre[i] = yp;
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(yi, yp));                       // :251
+    }
+};
+
+struct MinFinQR {
+    DevScalars *s;
+    double     *hist;
+    __device__ void operator()(const double *t) const
+    {
+        const double eps = 2.220446049250313e-16;
+        double *v = s->s;
+        s->n_iter++;
+        s->n_matvec++;
+        const long long itn = s->n_iter;
+        const double alfa = v[M_ALFA];
+        const double oldb = v[M_BETA];                                       // :250
+        v[M_OLDB] = oldb;
+        double beta = t[0];                                                  // :251
+        if (beta < 0) {                                                      // :252-254
+            s->istop = 6;
+            s->done = 1;
+            return;
+        }
+        beta = sqrt(beta);                                                   // :255
+        v[M_BETA] = beta;
+        v[M_TNORM2] = v[M_TNORM2] + alfa * alfa + oldb * oldb + beta * beta; // :256
+        if (itn == 1) {                                                      // :258-264
+            if (beta / v[M_BETA1] <= 10 * eps) s->istop = -1;
+            v[M_GMAX] = fabs(alfa);
+            v[M_GMIN] = v[M_GMAX];
+        }
+        const double cs = v[M_CS], sn = v[M_SN], dbar = v[M_DBAR];
+        const double oldeps = v[M_EPSLN];                                    // :270
+        const double delta = cs * dbar + sn * alfa;                          // :271
+        const double gbar = sn * dbar - cs * alfa;                           // :272
+        const double epsln = sn * beta;                                      // :277
+        v[M_DBAR] = -cs * beta;                                              // :278
+        const double root = sqrt(gbar * gbar + v[M_DBAR] * v[M_DBAR]);       // :279
+        v[M_ARNORM] = v[M_PHIBAR] * root;                                    // :280
+        double gamma = sqrt(gbar * gbar + beta * beta);                      // :284
+        gamma = fmax(gamma, eps);                                            // :285
+        v[M_CS] = gbar / gamma;                                              // :286
+        v[M_SN] = beta / gamma;                                              // :287
+        const double phi = v[M_CS] * v[M_PHIBAR];                            // :288
+        v[M_PHIBAR] = v[M_SN] * v[M_PHIBAR];                                 // :289
+        v[M_OLDEPS] = oldeps;
+        v[M_DELTA] = delta;
+        v[M_GBAR] = gbar;
+        v[M_EPSLN] = epsln;
+        v[M_PHI] = phi;
+        v[M_DENOM] = 1.0 / gamma;                                            // :293
+        v[M_INVBETA] = 1.0 / oldb;     // s of this trip (v = s*y), for K3
+        // energy norm / truncated direct error, :303-310
+        v[M_XNRG2] += phi * phi;
+        const int window = s->window;
+        s->derr[itn % window] = phi;
+        if (itn > window) {
+            double ss = 0.0;           // np.linalg.norm(dErr): sqrt of the ordered sum of squares
+            for (int k = 0; k < window; ++k) ss += s->derr[k] * s->derr[k];
+            const double trnc = sqrt(ss);
+            v[M_TRNC] = trnc;
+            const double xnrg = sqrt(v[M_XNRG2]);
+            if (trnc < s->etol * xnrg) s->istop = 10;
+        }
+        v[M_GMAX] = fmax(v[M_GMAX], gamma);                                  // :314-319
+        v[M_GMIN] = fmin(v[M_GMIN], gamma);
+        const double z = v[M_RHS1] / gamma;
+        v[M_YNORM2] = z * z + v[M_YNORM2];
+        v[M_RHS1] = v[M_RHS2] - delta * z;
+        v[M_RHS2] = -epsln * z;
+        const double Anorm = sqrt(v[M_TNORM2]);                              // :323-334
+        const double ynorm = sqrt(v[M_YNORM2]);
+        const double epsx = Anorm * ynorm * eps;
+        const double rnorm = v[M_PHIBAR];
+        const double test1 = rnorm / (Anorm * ynorm);
+        const double test2 = root / Anorm;
+        v[M_ANORM] = Anorm;
+        v[M_YNORM] = ynorm;
+        v[M_TEST1] = test1;
+        v[M_TEST2] = test2;
+        s->resid = rnorm;
+        hist_push(s, hist, 1, rnorm, 0.0);                                   // :336
+        const double Acond = v[M_GMAX] / v[M_GMIN];                          // :344
+        v[M_ACOND] = Acond;
+        if (s->istop == 0) {                                                 // :349-361
+            const double t1 = 1 + test1, t2 = 1 + test2;
+            if (t2 <= 1) s->istop = 2;
+            if (t1 <= 1) s->istop = 1;
+            if (itn >= s->matvec_max) s->istop = 6;
+            if (Acond >= 0.1 / eps) s->istop = 4;
+            if (epsx >= v[M_BETA1]) s->istop = 3;
+            if (test2 <= s->rtol) s->istop = 2;
+            if (test1 <= s->rtol) s->istop = 1;
+        }
+        // `done` is latched by K3 (the x update of this trip must still run)
+        if (s->istop > 0 || itn >= s->matvec_max) s->skip_half = 1;          // :381, :218
+    }
+};
+
+struct MinBodyW {             // w = (v - oldeps w1 - delta w2) * denom ; x += phi w
+    double       *wnew, *x;   // wnew overwrites the w1 buffer (w1 dies here)
+    const double *w2, *yold;  // yold: the y this trip's v was built from
+    DevScalars   *s;
+    double        inv, oldeps, delta, denom, phi;
+    __device__ void init()
+    {
+        inv = s->s[M_INVBETA];
+        oldeps = s->s[M_OLDEPS];
+        delta = s->s[M_DELTA];
+        denom = s->s[M_DENOM];
+        phi = s->s[M_PHI];
+    }
+    __device__ void operator()(int64_t i, double *acc) const
+    {
+        const double vi = __dmul_rn(inv, yold[i]);                           // :237
+        double wi = __dsub_rn(vi, __dmul_rn(oldeps, wnew[i]));               // :296 (wnew holds w1)
+        wi = __dsub_rn(wi, __dmul_rn(delta, w2[i]));
+        wi = __dmul_rn(wi, denom);
+        wnew[i] = wi;
+        x[i] = __dadd_rn(x[i], __dmul_rn(phi, wi));                          // :297
+    }
+};
+
+struct MinFinW {
+    DevScalars *s;
+    __device__ void operator()(const double *) const
+    {
+        if (s->skip_half) {
+            s->skip_half = 0;
+            s->done = 1;
+        }
+    }
+};
+
+struct MinSetupBody {         // y = M b ; beta1^2 = b.y   (minres.py:160-166)
+    double       *y;
+    const double *b, *pd;
+    int           pmode;
+    __device__ void init() {}
+    __device__ void operator()(int64_t i, double *acc) const
+    {
+        const double yi = apply_diag(pd, pmode, i, b[i]);
+        y[i] = yi;
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(b[i], yi));
+    }
+};
+
+struct MinSetupFin {
+    DevScalars *s;
+    __device__ void operator()(const double *t) const
+    {
+        double *v = s->s;
+        double beta1 = t[0];
+        if (beta1 < 0) {                                                     // :170-173
+            s->istop = 9;
+            s->done = 1;
+        }
+        if (beta1 == 0.0) s->done = 1;                                       // :175-177
+        if (beta1 > 0) beta1 = sqrt(beta1);                                  // :179-180
+        v[M_BETA1] = beta1;
+        s->resid0 = beta1;
+        s->resid = 0.0;
+        v[M_OLDB] = 0.0;                                                     // :201-205
+        v[M_BETA] = beta1;
+        v[M_DBAR] = 0.0;
+        v[M_EPSLN] = 0.0;
+        v[M_PHIBAR] = beta1;
+        v[M_RHS1] = beta1;
+        v[M_RHS2] = 0.0;
+        v[M_TNORM2] = 0.0;
+        v[M_YNORM2] = 0.0;
+        v[M_CS] = -1.0;
+        v[M_SN] = 0.0;
+        v[M_ARNORM] = 0.0;
+        v[M_XNRG2] = 0.0;
+        v[M_ANORM] = v[M_ACOND] = v[M_YNORM] = 0.0;
+        if (s->matvec_max <= 0) s->done = 1;                                 // :218
+    }
+};
+
+static int minres_setup(kry_solver *S, int)
+{
+    // y = b.copy() lives in R[0]; r2 == y value-wise (no preconditioner), r1 is
+    // first read on trip 2, when it is the rotated r2 (minres.py:160-165, 208).
+    MinSetupBody sb{solver_vec(S, "ra"), solver_vec(S, "rhs"), S->dinv, 0};
+    KRY_TRY((solver_pass<1>(S, sb, MinSetupFin{S->ds}, &S->ds->done)));
+    const size_t bytes = (size_t)S->n * sizeof(double);
+    KRY_CUDA(cudaMemsetAsync(solver_vec(S, "wa"), 0, bytes, S->ctx->stream));   // :206-207
+    KRY_CUDA(cudaMemsetAsync(solver_vec(S, "wb"), 0, bytes, S->ctx->stream));
+    S->rot = 0;
+    return KRY_OK;
+}
+
+static int minres_iterate(kry_solver *S)
+{
+    // r buffers rotate with period 3: r2 (== y without precon) = R[k], r1 = R[k-1],
+    // R[k+1] receives this trip's y.  w buffers rotate with period 2: w = W[j],
+    // w2 = W[1-j]; the new w overwrites w2's buffer (w1 := w2 dies in the same pass).
+    double *R[3] = {solver_vec(S, "ra"), solver_vec(S, "rb"), solver_vec(S, "rc")};
+    double *W[2] = {solver_vec(S, "wa"), solver_vec(S, "wb")};
+    double *x = solver_vec(S, "x");
+    const int k = (int)(S->rot % 3), j = (int)(S->rot % 2);
+    double *r2 = R[k], *r1 = R[(k + 2) % 3], *rn = R[(k + 1) % 3];
+    const int *done = &S->ds->done;
+    MinGather g{r2, S->ds, 0.0};
+    MinEpiY e{rn, r2, r1, S->ds, 0, 0, 0, 0};
+    KRY_TRY((solver_spmv<1>(S, g, e, MinFinAlfa{S->ds}, done, r2)));
+    MinBodyR2 b2{rn, nullptr, r2, S->dinv, 0, S->ds, 0.0};
+    KRY_TRY((solver_pass<1>(S, b2, MinFinQR{S->ds, S->hist}, done)));
+    MinBodyW bw{W[1 - j], x, W[j], r2, S->ds, 0, 0, 0, 0, 0};
+    KRY_TRY((solver_pass<1>(S, bw, MinFinW{S->ds}, done)));
+    S->rot++;
+    return KRY_OK;
+}
+
+// ============================================================ C ABI plumbing
+struct VecSpec {
+    const char *name;
+    bool        gathered;    // SpMV input: needs the halo tail on sharded runs
+};
+
+static const VecSpec *method_vectors(kry_method m, int *count)
+{
+    static const VecSpec cg[] = {{"x", true}, {"p", true}, {"r", false}, {"Ap", false}, {"rhs", false}};
+    static const VecSpec bcg[] = {{"x", true}, {"p", true}, {"s", true}, {"q", true}, {"z", true},
+                                  {"r0", false}, {"r", false}, {"v", false}, {"t", false}, {"rhs", false}};
+    static const VecSpec cgs[] = {{"x", true}, {"p", true}, {"z", true}, {"y", true}, {"r0", false},
+                                  {"r", false}, {"u", false}, {"q", false}, {"v", false}, {"rhs", false}};
+    static const VecSpec tfq[] = {{"x", true}, {"y", true}, {"z", true}, {"r0", false}, {"w", false},
+                                  {"d", false}, {"u", false}, {"v", false}, {"rhs", false}};
+    static const VecSpec mr[] = {{"x", false}, {"ra", true}, {"rb", true}, {"rc", true},
+                                 {"wa", false}, {"wb", false}, {"rhs", false}};
+    switch (m) {
+        case KRY_CG: *count = 5; return cg;
+        case KRY_BICGSTAB: *count = 10; return bcg;
+        case KRY_CGS: *count = 10; return cgs;
+        case KRY_TFQMR: *count = 9; return tfq;
+        case KRY_MINRES: *count = 7; return mr;
+    }
+    *count = 0;
+    return nullptr;
+}
+
+extern "C" int kry_solver_create(kry_ctx *c, kry_method method, kry_csr *A, kry_solver **out)
+{
+    KRY_REQUIRE(c && A && out, KRY_ERR_INVALID, "kry_solver_create: NULL argument");
+    *out = nullptr;
+    KRY_REQUIRE(A->ctx == c, KRY_ERR_INVALID, "kry_solver_create: operator belongs to another context");
+    int nv = 0;
+    const VecSpec *specs = method_vectors(method, &nv);
+    KRY_REQUIRE(specs, KRY_ERR_INVALID, "kry_solver_create: unknown method %d", (int)method);
+    const int64_t n = A->A.nrows;
+    const int64_t n_in = A->halo.active ? A->A.nrows : A->A.ncols;
+    KRY_REQUIRE(n == n_in, KRY_ERR_SHAPE, "kry_solver_create: operator is %lld x %lld, not square",
+                (long long)n, (long long)n_in);
+    KRY_CUDA(cudaSetDevice(c->device));
+    kry_solver *S = new (std::nothrow) kry_solver();
+    KRY_REQUIRE(S, KRY_ERR_NOMEM, "kry_solver_create: host allocation failed");
+    memset(S, 0, sizeof(*S));
+    S->ctx = c;
+    S->A = A;
+    S->method = method;
+    S->n = n;
+    S->ncap = A->halo.active ? A->A.ncols : n;
+    S->sharded = A->halo.active && c->nranks > 1;
+    S->hist_width = (method == KRY_CG) ? 2 : 1;
+    auto pad = [](int64_t v) { return (v + 31) & ~(int64_t)31; };
+    int64_t total = 0;
+    for (int i = 0; i < nv; ++i) total += pad(specs[i].gathered ? S->ncap : n);
+    total += pad(n);   // preconditioner diagonal
+    int rc = kry_alloc((void **)&S->slab, (size_t)total * sizeof(double));
+    if (rc == KRY_OK) rc = kry_alloc((void **)&S->ds, sizeof(DevScalars));
+    if (rc == KRY_OK)
+        rc = kry_alloc((void **)&S->hist, (size_t)KRY_HIST_CAP * S->hist_width * sizeof(double));
+    if (rc != KRY_OK) {
+        cudaFree(S->slab);
+        cudaFree(S->ds);
+        cudaFree(S->hist);
+        delete S;
+        return rc;
+    }
+    cudaMemsetAsync(S->slab, 0, (size_t)total * sizeof(double), c->stream);
+    int64_t off = 0;
+    for (int i = 0; i < nv; ++i) {
+        S->vecs[i].name = specs[i].name;
+        S->vecs[i].d = S->slab + off;
+        S->vecs[i].n = n;
+        off += pad(specs[i].gathered ? S->ncap : n);
+    }
+    S->nvecs = nv;
+    S->dinv = S->slab + off;
+    S->precon_mode = 0;
+    *out = S;
+    return KRY_OK;
+}
+
+extern "C" int kry_solver_destroy(kry_solver *S)
+{
+    if (!S) return KRY_OK;
+    cudaStreamSynchronize(S->ctx->stream);
+    cudaFree(S->slab);
+    cudaFree(S->ds);
+    cudaFree(S->hist);
+    delete S;
+    return KRY_OK;
+}
+
+extern "C" int kry_solver_set_precon_diag(kry_solver *S, const double *diag_host, int mode)
+{
+    KRY_REQUIRE(S, KRY_ERR_INVALID, "kry_solver_set_precon_diag: NULL solver");
+    if (!diag_host || mode == 0) {
+        S->precon_mode = 0;
+        return KRY_OK;
+    }
+    KRY_REQUIRE(mode == 1 || mode == 2, KRY_ERR_INVALID, "kry_solver_set_precon_diag: mode %d", mode);
+    KRY_CUDA(cudaMemcpyAsync(S->dinv, diag_host, (size_t)S->n * sizeof(double),
+                             cudaMemcpyHostToDevice, S->ctx->stream));
+    KRY_CUDA(cudaStreamSynchronize(S->ctx->stream));
+    S->precon_mode = mode;
+    return KRY_OK;
+}
+
+static int solver_setup_common(kry_solver *S, int guess, const kry_solver_params *p)
+{
+    KRY_REQUIRE(p, KRY_ERR_INVALID, "kry_solver_setup: NULL params");
+    KRY_REQUIRE(S->method != KRY_MINRES || (p->window >= 1 && p->window <= 16), KRY_ERR_INVALID,
+                "kry_solver_setup: MINRES window %d not in [1,16]", p->window);
+    KRY_REQUIRE(!(S->method == KRY_MINRES && S->precon_mode), KRY_ERR_UNSUPPORTED,
+                "kry_solver_setup: preconditioned MINRES is not device-resident yet");
+    S->params = *p;
+    DevScalars h;
+    memset(&h, 0, sizeof(h));
+    h.definite = 1;
+    h.matvec_max = p->matvec_max;
+    h.abstol = p->abstol;
+    h.reltol = p->reltol;
+    h.check_curvature = p->check_curvature;
+    h.window = p->window;
+    h.shift = p->shift;
+    h.rtol = p->rtol;
+    h.etol = p->etol;
+    h.s[S_RHO] = 1.0;
+    cudaStream_t st = S->ctx->stream;
+    KRY_CUDA(cudaMemcpyAsync(S->ds, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+    KRY_CUDA(cudaStreamSynchronize(st));       // `h` is on the stack
+    int rc = KRY_OK;
+    switch (S->method) {
+        case KRY_CG: rc = cg_setup(S, guess); break;
+        case KRY_BICGSTAB: rc = bicgstab_setup(S, guess); break;
+        case KRY_CGS: rc = cgs_setup(S, guess); break;
+        case KRY_TFQMR: rc = tfqmr_setup(S, guess); break;
+        case KRY_MINRES: rc = minres_setup(S, guess); break;
+    }
+    S->ready = (rc == KRY_OK);
+    return rc;
+}
+
+extern "C" int kry_solver_setup(kry_solver *S, const double *rhs_host, const double *guess_host,
+                                const kry_solver_params *params)
+{
+    KRY_REQUIRE(S && rhs_host, KRY_ERR_INVALID, "kry_solver_setup: NULL argument");
+    KRY_CUDA(cudaSetDevice(S->ctx->device));
+    cudaStream_t st = S->ctx->stream;
+    const size_t bytes = (size_t)S->n * sizeof(double);
+    KRY_CUDA(cudaMemcpyAsync(solver_vec(S, "rhs"), rhs_host, bytes, cudaMemcpyHostToDevice, st));
+    if (guess_host)
+        KRY_CUDA(cudaMemcpyAsync(solver_vec(S, "x"), guess_host, bytes, cudaMemcpyHostToDevice, st));
+    else
+        KRY_CUDA(cudaMemsetAsync(solver_vec(S, "x"), 0, bytes, st));
+    KRY_CUDA(cudaStreamSynchronize(st));
+    return solver_setup_common(S, guess_host != nullptr, params);
+}
+
+extern "C" int kry_solver_setup_dev(kry_solver *S, const kry_vec *rhs, const kry_vec *guess,
+                                    const kry_solver_params *params)
+{
+    KRY_REQUIRE(S && rhs, KRY_ERR_INVALID, "kry_solver_setup_dev: NULL argument");
+    KRY_REQUIRE(rhs->n == S->n && (!guess || guess->n == S->n), KRY_ERR_SHAPE,
+                "kry_solver_setup_dev: rhs/guess size does not match the operator (%lld rows)",
+                (long long)S->n);
+    KRY_CUDA(cudaSetDevice(S->ctx->device));
+    cudaStream_t st = S->ctx->stream;
+    const size_t bytes = (size_t)S->n * sizeof(double);
+    KRY_CUDA(cudaMemcpyAsync(solver_vec(S, "rhs"), rhs->d, bytes, cudaMemcpyDeviceToDevice, st));
+    if (guess)
+        KRY_CUDA(cudaMemcpyAsync(solver_vec(S, "x"), guess->d, bytes, cudaMemcpyDeviceToDevice, st));
+    else
+        KRY_CUDA(cudaMemsetAsync(solver_vec(S, "x"), 0, bytes, st));
+    return solver_setup_common(S, guess != nullptr, params);
+}
+
+extern "C" int kry_solver_iterate(kry_solver *S, int64_t n_iters)
+{
+    KRY_REQUIRE(S, KRY_ERR_INVALID, "kry_solver_iterate: NULL solver");
+    KRY_REQUIRE(S->ready, KRY_ERR_STATE, "kry_solver_iterate: call kry_solver_setup first");
+    KRY_REQUIRE(n_iters >= 0 && n_iters < KRY_HIST_CAP / 2, KRY_ERR_INVALID,
+                "kry_solver_iterate: n_iters=%lld not in [0,%d)", (long long)n_iters, KRY_HIST_CAP / 2);
+    KRY_CUDA(cudaSetDevice(S->ctx->device));
+    for (int64_t it = 0; it < n_iters; ++it) {
+        int rc = KRY_OK;
+        switch (S->method) {
+            case KRY_CG: rc = cg_iterate(S); break;
+            case KRY_BICGSTAB: rc = bicgstab_iterate(S); break;
+            case KRY_CGS: rc = cgs_iterate(S); break;
+            case KRY_TFQMR: rc = tfqmr_iterate(S); break;
+            case KRY_MINRES: rc = minres_iterate(S); break;
+        }
+        if (rc != KRY_OK) return rc;
+    }
+    return KRY_OK;
+}
+
+extern "C" int kry_solver_status_read(kry_solver *S, kry_solver_status *out)
+{
+    KRY_REQUIRE(S && out, KRY_ERR_INVALID, "kry_solver_status_read: NULL argument");
+    DevScalars h;
+    KRY_CUDA(cudaMemcpyAsync(&h, S->ds, sizeof(h), cudaMemcpyDeviceToHost, S->ctx->stream));
+    KRY_CUDA(cudaStreamSynchronize(S->ctx->stream));
+    KRY_CUDA(cudaGetLastError());
+    memset(out, 0, sizeof(*out));
+    out->done = h.done;
+    out->definite = h.definite;
+    out->istop = h.istop;
+    out->n_matvec = h.n_matvec;
+    out->n_iter = h.n_iter;
+    out->hist_count = h.hist_count;
+    out->resid_norm0 = h.resid0;
+    out->resid_norm = h.resid;
+    out->threshold = h.threshold;
+    switch (S->method) {
+        case KRY_MINRES:
+            out->converged = (h.istop == 1 || h.istop == 2 || h.istop == 3 || h.istop == 4 ||
+                              h.istop == 10);                                // minres.py:395
+            out->aux[0] = h.s[M_ANORM];
+            out->aux[1] = h.s[M_ACOND];
+            out->aux[2] = h.s[M_YNORM];
+            out->aux[3] = h.s[M_ARNORM];
+            out->aux[4] = h.s[M_BETA1];
+            out->aux[5] = h.s[M_ALFA];
+            out->aux[6] = h.s[M_BETA];
+            out->aux[7] = h.s[M_PHI];
+            out->aux[8] = h.s[M_TEST1];
+            out->aux[9] = h.s[M_TEST2];
+            out->aux[10] = h.s[M_TRNC];
+            out->aux[11] = h.s[M_XNRG2];
+            out->aux[12] = h.s[M_GBAR];
+            break;
+        case KRY_TFQMR:
+            out->converged = (h.n_iter > 0 || h.hist_count > 1)
+                                 ? (h.resid * sqrt(h.s[S_M] + 1) < h.threshold)   // tfqmr.py:156
+                                 : 0;
+            out->aux[0] = h.s[S_RHO];
+            out->aux[1] = h.s[S_SIGMA];
+            out->aux[2] = h.s[S_ALPHA];
+            out->aux[3] = h.s[S_BETA];
+            out->aux[4] = h.s[S_THETA];
+            out->aux[5] = h.s[S_ETA];
+            out->aux[6] = h.s[S_M];
+            break;
+        default:
+            out->converged = (h.resid <= h.threshold);                       // cg.py:161 etc.
+            out->aux[0] = h.s[S_RY];
+            out->aux[1] = h.s[S_PAP];
+            out->aux[2] = h.s[S_ALPHA];
+            out->aux[3] = h.s[S_BETA];
+            out->aux[4] = h.s[S_RHO];
+            out->aux[5] = h.s[S_OMEGA];
+            out->aux[6] = h.s[S_SIGMA];
+            out->aux[7] = h.s[S_RHO_NEXT];
+            break;
+    }
+    return KRY_OK;
+}
+
+extern "C" int kry_solver_history(kry_solver *S, int64_t first, int64_t count, double *host,
+                                  int32_t *width)
+{
+    KRY_REQUIRE(S && (host || count == 0), KRY_ERR_INVALID, "kry_solver_history: NULL argument");
+    if (width) *width = S->hist_width;
+    KRY_REQUIRE(first >= 0 && count >= 0 && count <= KRY_HIST_CAP, KRY_ERR_INVALID,
+                "kry_solver_history: range [%lld,+%lld) invalid", (long long)first, (long long)count);
+    cudaStream_t st = S->ctx->stream;
+    const int w = S->hist_width;
+    int64_t done = 0;
+    while (done < count) {      // the ring may wrap
+        const int64_t slot = (first + done) % KRY_HIST_CAP;
+        int64_t run = KRY_HIST_CAP - slot;
+        if (run > count - done) run = count - done;
+        KRY_CUDA(cudaMemcpyAsync(host + done * w, S->hist + slot * w, (size_t)run * w * sizeof(double),
+                                 cudaMemcpyDeviceToHost, st));
+        done += run;
+    }
+    KRY_CUDA(cudaStreamSynchronize(st));
+    return KRY_OK;
+}
+
+extern "C" int kry_solver_solution(kry_solver *S, double *x_host)
+{
+    KRY_REQUIRE(S && x_host, KRY_ERR_INVALID, "kry_solver_solution: NULL argument");
+    KRY_CUDA(cudaMemcpyAsync(x_host, solver_vec(S, "x"), (size_t)S->n * sizeof(double),
+                             cudaMemcpyDeviceToHost, S->ctx->stream));
+    KRY_CUDA(cudaStreamSynchronize(S->ctx->stream));
+    return KRY_OK;
+}
+
+// MINRES rotates its buffers; map the reference's names onto the rotation that
+// the device actually reached (trips executed, not trips enqueued).
+static double *solver_vec_logical(kry_solver *S, const char *name)
+{
+    if (S->method == KRY_MINRES) {
+        long long itn = 0;
+        cudaMemcpyAsync(&itn, &S->ds->n_iter, sizeof(itn), cudaMemcpyDeviceToHost, S->ctx->stream);
+        cudaStreamSynchronize(S->ctx->stream);
+        const char *R[3] = {"ra", "rb", "rc"}, *W[2] = {"wa", "wb"};
+        const int k = (int)(itn % 3), j = (int)(itn % 2);
+        if (!strcmp(name, "r2") || !strcmp(name, "y")) return solver_vec(S, R[k]);
+        if (!strcmp(name, "r1")) return solver_vec(S, R[(k + 2) % 3]);
+        if (!strcmp(name, "w")) return solver_vec(S, W[j]);
+        if (!strcmp(name, "w2")) return solver_vec(S, W[1 - j]);
+    }
+    return solver_vec(S, name);
+}
+
+extern "C" int kry_solver_get_vector(kry_solver *S, const char *name, double *host)
+{
+    KRY_REQUIRE(S && name && host, KRY_ERR_INVALID, "kry_solver_get_vector: NULL argument");
+    double *d = solver_vec_logical(S, name);
+    KRY_REQUIRE(d, KRY_ERR_INVALID, "kry_solver_get_vector: no vector named '%s'", name);
+    KRY_CUDA(cudaMemcpyAsync(host, d, (size_t)S->n * sizeof(double), cudaMemcpyDeviceToHost,
+                             S->ctx->stream));
+    KRY_CUDA(cudaStreamSynchronize(S->ctx->stream));
+    return KRY_OK;
+}
+
+extern "C" int kry_solver_set_vector(kry_solver *S, const char *name, const double *host)
+{
+    KRY_REQUIRE(S && name && host, KRY_ERR_INVALID, "kry_solver_set_vector: NULL argument");
+    double *d = solver_vec_logical(S, name);
+    KRY_REQUIRE(d, KRY_ERR_INVALID, "kry_solver_set_vector: no vector named '%s'", name);
+    KRY_CUDA(cudaMemcpyAsync(d, host, (size_t)S->n * sizeof(double), cudaMemcpyHostToDevice,
+                             S->ctx->stream));
+    KRY_CUDA(cudaStreamSynchronize(S->ctx->stream));
+    return KRY_OK;
+}
+
+struct ScalarName {
+    const char *name;
+    int         idx;
+};
+static const ScalarName kScalarNames[] = {
+    {"ry", S_RY}, {"pAp", S_PAP}, {"alpha", S_ALPHA}, {"beta", S_BETA}, {"rho", S_RHO},
+    {"rho_next", S_RHO_NEXT}, {"omega", S_OMEGA}, {"sigma", S_SIGMA}, {"theta", S_THETA},
+    {"eta", S_ETA}, {"k", S_K}, {"m", S_M}, {"alfa", M_ALFA}, {"mbeta", M_BETA}, {"oldb", M_OLDB},
+    {"beta1", M_BETA1}, {"dbar", M_DBAR}, {"epsln", M_EPSLN}, {"phibar", M_PHIBAR},
+    {"cs", M_CS}, {"sn", M_SN}, {"phi", M_PHI}, {"tnorm2", M_TNORM2}, {"ynorm2", M_YNORM2},
+    {"rhs1", M_RHS1}, {"rhs2", M_RHS2}, {"gmax", M_GMAX}, {"gmin", M_GMIN}};
+
+static int scalar_index(const char *name)
+{
+    for (size_t i = 0; i < sizeof(kScalarNames) / sizeof(kScalarNames[0]); ++i)
+        if (!strcmp(kScalarNames[i].name, name)) return kScalarNames[i].idx;
+    return -1;
+}
+
+extern "C" int kry_solver_get_scalar(kry_solver *S, const char *name, double *value)
+{
+    KRY_REQUIRE(S && name && value, KRY_ERR_INVALID, "kry_solver_get_scalar: NULL argument");
+    const int idx = scalar_index(name);
+    KRY_REQUIRE(idx >= 0, KRY_ERR_INVALID, "kry_solver_get_scalar: no scalar named '%s'", name);
+    KRY_CUDA(cudaMemcpyAsync(value, &S->ds->s[idx], sizeof(double), cudaMemcpyDeviceToHost,
+                             S->ctx->stream));
+    KRY_CUDA(cudaStreamSynchronize(S->ctx->stream));
+    return KRY_OK;
+}
+
+extern "C" int kry_solver_set_scalar(kry_solver *S, const char *name, double value)
+{
+    KRY_REQUIRE(S && name, KRY_ERR_INVALID, "kry_solver_set_scalar: NULL argument");
+    const int idx = scalar_index(name);
+    KRY_REQUIRE(idx >= 0, KRY_ERR_INVALID, "kry_solver_set_scalar: no scalar named '%s'", name);
+    KRY_CUDA(cudaMemcpyAsync(&S->ds->s[idx], &value, sizeof(double), cudaMemcpyHostToDevice,
+                             S->ctx->stream));
+    KRY_CUDA(cudaStreamSynchronize(S->ctx->stream));
+    return KRY_OK;
+}

@@ -1,0 +1,279 @@
+// spmv.cuh -- CSR SpMV kernels with fused row-local epilogue + inner products.
+//
+// Replaces the operator closure behind `op * x` (reference
+// pykrylov/linop/linop.py:362-369 -> :356-360 -> :271-298 -> :697-706) together
+// with the np.dot that follows it in every solver loop (cg/cg.py:115-117,
+// bicgstab/bicgstab.py:101-103,125-127, minres/minres.py:239-245).
+//
+// Parity contract: each row is summed sequentially in
+// storage order with an un-fused multiply and add,
+//     sum = 0;  sum = sum + (val[k] * x[col[k]])   for k in row,
+// which is bit-for-bit scipy's csr_matvec.  All kernels below keep that order;
+// they differ only in how the nnz stream reaches the SM.
+//
+//   spmv_row_kernel    one thread per row, direct loads (fallback for very long rows)
+//   spmv_stream_kernel one CTA per nnz tile: val/col are read fully coalesced,
+//                      products are staged in shared memory, then one thread per
+//                      row sums its (short) row from smem.  HBM sees only
+//                      contiguous 128-byte streams; the x gather hits L1/L2.
+//   spmv_tma_kernel    persistent CTAs; val/col tiles are fetched by the TMA unit
+//                      (cp.async.bulk + mbarrier, multi-stage ring) while the
+//                      previous tile is being reduced.
+//
+// Gather functor  : double operator()(int col)   -- x[col], possibly transformed
+// Epilogue functor: void operator()(int row, double Ax, double *acc) -- writes y
+//                   (and anything row-local) and accumulates fused dot terms.
+#pragma once
+
+#include "common.cuh"
+
+struct CsrView {
+    const int    *rowptr;
+    const int    *col;
+    const double *val;
+    const int    *rowblk;
+    int           nrows;
+    int           nblocks;
+};
+
+static inline CsrView csr_view(const CsrDev &m)
+{
+    CsrView v;
+    v.rowptr = m.rowptr; v.col = m.col; v.val = m.val; v.rowblk = m.rowblk;
+    v.nrows = (int)m.nrows; v.nblocks = m.nblocks;
+    return v;
+}
+
+#ifdef __CUDACC__
+
+struct GatherPlain {
+    const double *x;
+    __device__ void   init() {}
+    __device__ double operator()(int c) const { return __ldg(x + c); }
+};
+
+// x[c] * s with s read from device memory (MINRES: v = (1/beta) * y on the fly)
+struct GatherScaled {
+    const double *x;
+    const double *s_ptr;
+    double        s;
+    __device__ void   init() { s = *s_ptr; }
+    __device__ double operator()(int c) const { return __dmul_rn(s, __ldg(x + c)); }
+};
+
+// ------------------------------------------------------------ thread per row
+template <int ND, class Gather, class Epi, class Fin>
+__global__ void __launch_bounds__(256)
+spmv_row_kernel(CsrView A, Gather g, Epi epi, ReduceWs ws, Fin fin, const int *done)
+{
+    if (*done) return;
+    g.init();
+    epi.init();
+    double acc[ND > 0 ? ND : 1];
+#pragma unroll
+    for (int d = 0; d < (ND > 0 ? ND : 1); ++d) acc[d] = 0.0;
+    const int stride = gridDim.x * blockDim.x;
+    for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < A.nrows; row += stride) {
+        const int s = __ldg(A.rowptr + row), e = __ldg(A.rowptr + row + 1);
+        double sum = 0.0;
+        for (int k = s; k < e; ++k)
+            sum = __dadd_rn(sum, __dmul_rn(__ldg(A.val + k), g(__ldg(A.col + k))));
+        epi(row, sum, acc);
+    }
+    if constexpr (ND > 0) block_reduce_finalize<ND>(acc, ws, fin);
+}
+
+// ------------------------------------------------------- coalesced nnz stream
+// Dynamic smem: (tile_nnz + max_row) doubles of staged products.
+template <int ND, class Gather, class Epi, class Fin>
+__global__ void
+spmv_stream_kernel(CsrView A, Gather g, Epi epi, ReduceWs ws, Fin fin, const int *done)
+{
+    if (*done) return;
+    extern __shared__ double s_prod[];
+    g.init();
+    epi.init();
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int row_lo = __ldg(A.rowblk + blockIdx.x);
+    const int row_hi = __ldg(A.rowblk + blockIdx.x + 1);
+    const int k_lo = __ldg(A.rowptr + row_lo);
+    const int k_hi = __ldg(A.rowptr + row_hi);
+
+    // phase 1: stream val/col (coalesced), gather x, stage products.
+    // 4 independent element loads in flight per thread per trip.
+    int k = k_lo + tid;
+    for (; k + 3 * nt < k_hi; k += 4 * nt) {
+        const int    c0 = __ldg(A.col + k), c1 = __ldg(A.col + k + nt);
+        const int    c2 = __ldg(A.col + k + 2 * nt), c3 = __ldg(A.col + k + 3 * nt);
+        const double v0 = __ldg(A.val + k), v1 = __ldg(A.val + k + nt);
+        const double v2 = __ldg(A.val + k + 2 * nt), v3 = __ldg(A.val + k + 3 * nt);
+        const double x0 = g(c0), x1 = g(c1), x2 = g(c2), x3 = g(c3);
+        s_prod[k - k_lo]          = __dmul_rn(v0, x0);
+        s_prod[k - k_lo + nt]     = __dmul_rn(v1, x1);
+        s_prod[k - k_lo + 2 * nt] = __dmul_rn(v2, x2);
+        s_prod[k - k_lo + 3 * nt] = __dmul_rn(v3, x3);
+    }
+    for (; k < k_hi; k += nt) s_prod[k - k_lo] = __dmul_rn(__ldg(A.val + k), g(__ldg(A.col + k)));
+    __syncthreads();
+
+    // phase 2: one thread per row, sequential sum in storage order.
+    double acc[ND > 0 ? ND : 1];
+#pragma unroll
+    for (int d = 0; d < (ND > 0 ? ND : 1); ++d) acc[d] = 0.0;
+    for (int row = row_lo + tid; row < row_hi; row += nt) {
+        const int s = __ldg(A.rowptr + row) - k_lo, e = __ldg(A.rowptr + row + 1) - k_lo;
+        double sum = 0.0;
+        for (int j = s; j < e; ++j) sum = __dadd_rn(sum, s_prod[j]);
+        epi(row, sum, acc);
+    }
+    if constexpr (ND > 0) block_reduce_finalize<ND>(acc, ws, fin);
+}
+
+// --------------------------------------------------------- TMA bulk pipeline
+// Persistent CTAs walk the nnz tiles with stride gridDim.x.  One elected thread
+// drives the TMA unit: for every tile it issues two 1-D bulk copies
+// (cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes; SASS
+// UBLKCP) for the 16-byte aligned val and col windows of the tile into a
+// kStages-deep smem ring; all threads wait on the stage's mbarrier, turn the
+// staged (val, col) pairs into products in place, sum rows, run the epilogue,
+// and hand the stage back.  HBM latency of the streaming part is hidden behind
+// the reduction of the previous tile instead of behind occupancy.
+namespace tma {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, unsigned phase)
+{
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned phase)
+{
+    while (!mbar_try_wait(bar, phase)) {
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes,
+                                         uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+}  // namespace tma
+
+// smem per stage: cap doubles (val, overwritten by products) + cap ints (col),
+// cap = tile_nnz + max_row + 4 rounded up to a multiple of 4.
+template <int ND, int kStages, class Gather, class Epi, class Fin>
+__global__ void
+spmv_tma_kernel(CsrView A, int cap, Gather g, Epi epi, ReduceWs ws, Fin fin, const int *done)
+{
+    if (*done) return;
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    __shared__ __align__(8) uint64_t s_full[kStages];
+    double *s_val = reinterpret_cast<double *>(s_raw);                         // [kStages][cap]
+    int    *s_col = reinterpret_cast<int *>(s_raw + (size_t)kStages * cap * 8);  // [kStages][cap]
+
+    g.init();
+    epi.init();
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) tma::mbar_init(&s_full[s], 1);
+        tma::fence_barrier_init();
+    }
+    __syncthreads();
+
+    // issue(tile t into stage s): thread 0 only
+    auto issue = [&](int tile, int s) {
+        const int row_lo = __ldg(A.rowblk + tile), row_hi = __ldg(A.rowblk + tile + 1);
+        const int k_lo = __ldg(A.rowptr + row_lo), k_hi = __ldg(A.rowptr + row_hi);
+        const int a_lo = k_lo & ~3;                 // 16-byte aligned for both arrays
+        const int a_hi = (k_hi + 3) & ~3;           // arrays are padded by >= 4 entries
+        const unsigned n = (unsigned)(a_hi - a_lo);
+        if (n == 0) {                               // empty tile: complete the phase by hand
+            tma::mbar_expect_tx(&s_full[s], 0);
+            return;
+        }
+        tma::mbar_expect_tx(&s_full[s], n * 12u);
+        tma::bulk_g2s(s_val + (size_t)s * cap, A.val + a_lo, n * 8u, &s_full[s]);
+        tma::bulk_g2s(s_col + (size_t)s * cap, A.col + a_lo, n * 4u, &s_full[s]);
+    };
+
+    const int first = blockIdx.x, step = gridDim.x;
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            const int t = first + s * step;
+            if (t < A.nblocks) issue(t, s);
+        }
+    }
+
+    double acc[ND > 0 ? ND : 1];
+#pragma unroll
+    for (int d = 0; d < (ND > 0 ? ND : 1); ++d) acc[d] = 0.0;
+
+    int it = 0;
+    for (int tile = first; tile < A.nblocks; tile += step, ++it) {
+        const int      s     = it % kStages;
+        const unsigned phase = (unsigned)(it / kStages) & 1u;
+        const int row_lo = __ldg(A.rowblk + tile), row_hi = __ldg(A.rowblk + tile + 1);
+        const int k_lo = __ldg(A.rowptr + row_lo), k_hi = __ldg(A.rowptr + row_hi);
+        const int a_lo = k_lo & ~3;
+        double *pv = s_val + (size_t)s * cap;
+        int    *pc = s_col + (size_t)s * cap;
+
+        tma::mbar_wait(&s_full[s], phase);
+
+        // products in place (each thread touches only its own slots)
+        for (int j = (k_lo - a_lo) + tid; j < k_hi - a_lo; j += nt)
+            pv[j] = __dmul_rn(pv[j], g(pc[j]));
+        __syncthreads();
+
+        for (int row = row_lo + tid; row < row_hi; row += nt) {
+            const int rs = __ldg(A.rowptr + row) - a_lo, re = __ldg(A.rowptr + row + 1) - a_lo;
+            double sum = 0.0;
+            for (int j = rs; j < re; ++j) sum = __dadd_rn(sum, pv[j]);
+            epi(row, sum, acc);
+        }
+        tma::fence_proxy_async();        // my generic-proxy smem writes before the async-proxy refill
+        __syncthreads();                 // stage s fully consumed by every thread
+
+        if (tid == 0) {
+            const int nxt = tile + kStages * step;
+            if (nxt < A.nblocks) issue(nxt, s);
+        }
+    }
+    if constexpr (ND > 0) block_reduce_finalize<ND>(acc, ws, fin);
+}
+
+#endif  // __CUDACC__

@@ -1,0 +1,414 @@
+"""Thin object layer over the C ABI: Context, DeviceVector, DeviceCsr, DeviceSolver.
+
+Host code stays pure Python + NumPy; every array crossing this layer is copied
+into / out of HBM by libkrylov_b200 (the library never keeps a host pointer).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib as L
+from ._lib import call
+
+__all__ = ["Context", "DeviceVector", "DeviceCsr", "DeviceSolver", "default_context", "device_count"]
+
+
+def device_count():
+    n = C.c_int(0)
+    call("kry_device_count", C.byref(n))
+    return n.value
+
+
+def _f64(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context(object):
+    """One CUDA device + stream + reduction workspace (``kry_ctx``)."""
+
+    def __init__(self, device=None):
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+            n = device_count()
+            if n > 0:
+                device %= n
+        self._h = L.handle()
+        call("kry_ctx_create", int(device), C.byref(self._h))
+        self.device = int(device)
+        self.nranks, self.rank = 1, 0
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            L.lib.kry_ctx_destroy(self._h)
+            self._h = L.handle()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- misc
+    def sync(self):
+        call("kry_ctx_sync", self._h)
+
+    def props(self):
+        p = (C.c_int64 * 6)()
+        call("kry_ctx_props", self._h, p)
+        keys = ("sm_count", "total_bytes", "free_bytes", "cc", "l2_bytes", "smem_optin")
+        return dict(zip(keys, [int(v) for v in p]))
+
+    def timer_start(self):
+        call("kry_timer_start", self._h)
+
+    def timer_stop(self):
+        ms = C.c_double(0.0)
+        call("kry_timer_stop", self._h, C.byref(ms))
+        return ms.value
+
+    def flush_l2(self):
+        call("kry_flush_l2", self._h)
+
+    def launch_count(self):
+        n = C.c_int64(0)
+        call("kry_launch_count", self._h, C.byref(n))
+        return n.value
+
+    def scalars(self, first=0, count=L.KRY_NUM_SLOTS):
+        out = (C.c_double * count)()
+        call("kry_scalars_read", self._h, first, count, out)
+        return np.array(out[:count])
+
+    def set_scalars(self, first, values):
+        values = [float(v) for v in values]
+        buf = (C.c_double * len(values))(*values)
+        call("kry_scalars_write", self._h, first, len(values), buf)
+
+    # -- factories
+    def vector(self, n_or_array):
+        if np.isscalar(n_or_array):
+            return DeviceVector(self, int(n_or_array))
+        a = _f64(n_or_array)
+        v = DeviceVector(self, a.shape[0])
+        v.upload(a)
+        return v
+
+    # -- multi-GPU
+    def comm_init(self, nranks, rank, unique_id):
+        call("kry_comm_init", self._h, int(nranks), int(rank), C.c_char_p(unique_id))
+        self.nranks, self.rank = int(nranks), int(rank)
+
+    def barrier(self):
+        call("kry_comm_barrier", self._h)
+
+    def allreduce(self, values, op="sum"):
+        vals = [float(v) for v in np.atleast_1d(values)]
+        buf = (C.c_double * len(vals))(*vals)
+        call("kry_comm_allreduce_host", self._h, buf, len(vals), 1 if op == "max" else 0)
+        return np.array(buf[:len(vals)])
+
+    def allgather_bytes(self, payload):
+        payload = bytes(payload)
+        out = C.create_string_buffer(len(payload) * self.nranks)
+        call("kry_comm_allgather_host", self._h, C.c_char_p(payload), out, len(payload))
+        raw = out.raw
+        return [raw[i * len(payload):(i + 1) * len(payload)] for i in range(self.nranks)]
+
+
+_default = None
+
+
+def default_context():
+    """Process-wide context on cuda:LOCAL_RANK (created on first use)."""
+    global _default
+    if _default is None:
+        _default = Context()
+    return _default
+
+
+class DeviceVector(object):
+    """fp64 vector resident in HBM (``kry_vec``)."""
+
+    def __init__(self, ctx, n):
+        self.ctx = ctx
+        self.n = int(n)
+        self._h = L.handle()
+        call("kry_vec_create", ctx._h, self.n, C.byref(self._h))
+
+    def __del__(self):
+        try:
+            if self._h.value:
+                L.lib.kry_vec_destroy(self._h)
+                self._h = L.handle()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return self.n
+
+    def upload(self, a):
+        a = _f64(a)
+        call("kry_vec_upload", self._h, _ptr(a), a.shape[0])
+        return self
+
+    def download(self, out=None):
+        if out is None:
+            out = np.empty(self.n, dtype=np.float64)
+        call("kry_vec_download", self._h, _ptr(out), out.shape[0])
+        return out
+
+    def fill(self, value):
+        call("kry_vec_fill", self._h, float(value))
+        return self
+
+    def copy_from(self, other):
+        call("kry_vec_copy", self._h, other._h)
+        return self
+
+
+class DeviceCsr(object):
+    """CSR operator resident in HBM (``kry_csr``): int32 indices, fp64 values."""
+
+    def __init__(self, ctx, handle, symmetric):
+        self.ctx = ctx
+        self._h = handle
+        self.symmetric = bool(symmetric)
+        nr, nc, nz = C.c_int64(), C.c_int64(), C.c_int64()
+        call("kry_csr_shape", self._h, C.byref(nr), C.byref(nc), C.byref(nz))
+        self.shape = (nr.value, nc.value)
+        self.nnz = nz.value
+
+    def __del__(self):
+        try:
+            if self._h.value:
+                L.lib.kry_csr_destroy(self._h)
+                self._h = L.handle()
+        except Exception:
+            pass
+
+    # -- constructors
+    @classmethod
+    def from_arrays(cls, ctx, shape, indptr, indices, data, symmetric=False, build_transpose=False):
+        indptr = np.ascontiguousarray(indptr)
+        if indptr.dtype != np.int32:
+            if len(indptr) and int(indptr[-1]) >= 2 ** 31 - 2 ** 20:
+                raise L.KrylovDeviceError(L.KRY_ERR_UNSUPPORTED, "nnz exceeds the int32 index space")
+            indptr = indptr.astype(np.int32)
+        indices = np.ascontiguousarray(indices, dtype=np.int32)
+        data = _f64(data)
+        flags = (L.KRY_CSR_SYMMETRIC if symmetric else 0) | (L.KRY_CSR_BUILD_TRANSPOSE if build_transpose else 0)
+        h = L.handle()
+        call("kry_csr_create", ctx._h, int(shape[0]), int(shape[1]), int(data.shape[0]),
+             _ptr(indptr), _ptr(indices), _ptr(data), flags, C.byref(h))
+        return cls(ctx, h, symmetric)
+
+    @classmethod
+    def poisson1d(cls, ctx, n, row_begin=0, row_end=-1):
+        h = L.handle()
+        call("kry_csr_create_poisson1d", ctx._h, int(n), int(row_begin), int(row_end), 0, C.byref(h))
+        return cls(ctx, h, True)
+
+    @classmethod
+    def poisson2d(cls, ctx, g, row_begin=0, row_end=-1):
+        h = L.handle()
+        call("kry_csr_create_poisson2d", ctx._h, int(g), int(row_begin), int(row_end), 0, C.byref(h))
+        return cls(ctx, h, True)
+
+    @classmethod
+    def convdiff3d(cls, ctx, m, gamma=0.5, row_begin=0, row_end=-1, build_transpose=False):
+        h = L.handle()
+        flags = L.KRY_CSR_BUILD_TRANSPOSE if build_transpose else 0
+        call("kry_csr_create_convdiff3d", ctx._h, int(m), float(gamma), int(row_begin), int(row_end),
+             flags, C.byref(h))
+        return cls(ctx, h, False)
+
+    # -- queries
+    def download(self, transposed=False):
+        nr = self.shape[1] if (transposed and not self.symmetric) else self.shape[0]
+        indptr = np.empty(nr + 1, dtype=np.int32)
+        indices = np.empty(self.nnz, dtype=np.int32)
+        data = np.empty(self.nnz, dtype=np.float64)
+        call("kry_csr_download", self._h, int(bool(transposed)), _ptr(indptr), _ptr(indices), _ptr(data))
+        return indptr, indices, data
+
+    def diagonal(self):
+        d = np.empty(self.shape[0], dtype=np.float64)
+        call("kry_csr_diagonal", self._h, _ptr(d))
+        return d
+
+    def build_transpose(self):
+        call("kry_csr_build_transpose", self._h)
+
+    def set_kernel(self, kind=L.KRY_SPMV_AUTO, tile_nnz=0, threads=0):
+        call("kry_csr_set_kernel", self._h, int(kind), int(tile_nnz), int(threads))
+
+    def shard_finalize(self, n_global, row_begin):
+        call("kry_csr_shard_finalize", self._h, int(n_global), int(row_begin))
+        nr, nc, nz = C.c_int64(), C.c_int64(), C.c_int64()
+        call("kry_csr_shape", self._h, C.byref(nr), C.byref(nc), C.byref(nz))
+        self.shape = (nr.value, nc.value)
+
+    # -- products
+    def spmv(self, x, y, trans=False):
+        call("kry_spmv", self._h, int(bool(trans)), x._h, y._h)
+        return y
+
+    def spmv_dot(self, x, y, dot_with, slot0=0, trans=False):
+        n = len(dot_with)
+        arr = (L.handle * max(n, 1))(*[(w._h if w is not None else None) for w in dot_with])
+        call("kry_spmv_dot", self._h, int(bool(trans)), x._h, y._h, n, arr, int(slot0))
+        return y
+
+    def matvec(self, x, trans=False):
+        """Host array in, host array out (LinearOperator.__mul__ bridge)."""
+        nin = self.shape[0] if trans else self.shape[1]
+        nout = self.shape[1] if trans else self.shape[0]
+        x = _f64(x)
+        if x.shape != (nin,):
+            raise ValueError("input array size incompatible with operator dimensions")
+        xv = DeviceVector(self.ctx, nin).upload(x)
+        yv = DeviceVector(self.ctx, nout)
+        self.spmv(xv, yv, trans=trans)
+        return yv.download()
+
+
+def multi_axpy_dot(ctx, ops, dots=(), slot0=0):
+    """ops: list of dicts(z, u, w, a, b, a_slot, b_slot, a_neg, b_neg); dots: list of (u, w)."""
+    arr = (L.Axpby * max(len(ops), 1))()
+    for k, o in enumerate(ops):
+        arr[k].z = o["z"]._h
+        arr[k].u = o["u"]._h if o.get("u") is not None else None
+        arr[k].w = o["w"]._h if o.get("w") is not None else None
+        arr[k].a = float(o.get("a", 1.0))
+        arr[k].b = float(o.get("b", 1.0))
+        arr[k].a_slot = int(o.get("a_slot", -1))
+        arr[k].b_slot = int(o.get("b_slot", -1))
+        arr[k].a_neg = int(o.get("a_neg", 0))
+        arr[k].b_neg = int(o.get("b_neg", 0))
+    darr = (L.DotSpec * max(len(dots), 1))()
+    for k, (u, w) in enumerate(dots):
+        darr[k].u = u._h
+        darr[k].w = w._h
+    call("kry_multi_axpy_dot", ctx._h, len(ops), arr, len(dots), darr, int(slot0))
+
+
+METHODS = {"cg": L.KRY_CG, "bicgstab": L.KRY_BICGSTAB, "cgs": L.KRY_CGS, "tfqmr": L.KRY_TFQMR,
+           "minres": L.KRY_MINRES}
+
+
+class DeviceSolver(object):
+    """Device-resident Krylov iteration (``kry_solver``)."""
+
+    def __init__(self, ctx, method, A):
+        self.ctx = ctx
+        self.A = A
+        self.method = method
+        self.n = A.shape[0]
+        self._h = L.handle()
+        call("kry_solver_create", ctx._h, METHODS[method], A._h, C.byref(self._h))
+        self._hist_read = 0
+
+    def __del__(self):
+        try:
+            if self._h.value:
+                L.lib.kry_solver_destroy(self._h)
+                self._h = L.handle()
+        except Exception:
+            pass
+
+    def set_precon_diag(self, diag, mode=1):
+        if diag is None:
+            call("kry_solver_set_precon_diag", self._h, None, 0)
+        else:
+            d = _f64(diag)
+            if d.shape != (self.n,):
+                raise ValueError("preconditioner diagonal has the wrong size")
+            call("kry_solver_set_precon_diag", self._h, _ptr(d), int(mode))
+
+    @staticmethod
+    def params(abstol=1.0e-8, reltol=1.0e-6, matvec_max=0, check_curvature=True, guess_supplied=False,
+               shift=0.0, rtol=1.0e-12, etol=1.0e-6, window=5):
+        p = L.SolverParams()
+        p.abstol, p.reltol, p.matvec_max = float(abstol), float(reltol), int(matvec_max)
+        p.check_curvature, p.guess_supplied = int(bool(check_curvature)), int(bool(guess_supplied))
+        p.shift, p.rtol, p.etol, p.window = float(shift), float(rtol), float(etol), int(window)
+        return p
+
+    def setup(self, rhs, guess=None, **kw):
+        rhs = _f64(rhs)
+        if rhs.shape != (self.n,):
+            raise ValueError("right-hand side size incompatible with operator dimensions")
+        g = None
+        if guess is not None:
+            g = _f64(guess)
+            if g.shape != (self.n,):
+                raise ValueError("initial guess size incompatible with operator dimensions")
+        p = self.params(guess_supplied=guess is not None, **kw)
+        call("kry_solver_setup", self._h, _ptr(rhs), _ptr(g) if g is not None else None, C.byref(p))
+        self._hist_read = 0
+
+    def setup_dev(self, rhs_vec, guess_vec=None, **kw):
+        p = self.params(guess_supplied=guess_vec is not None, **kw)
+        call("kry_solver_setup_dev", self._h, rhs_vec._h, guess_vec._h if guess_vec is not None else None,
+             C.byref(p))
+        self._hist_read = 0
+
+    def iterate(self, n_iters):
+        call("kry_solver_iterate", self._h, int(n_iters))
+
+    def status(self):
+        s = L.SolverStatus()
+        call("kry_solver_status_read", self._h, C.byref(s))
+        return s
+
+    def drain_history(self, status=None):
+        """New per-iteration entries since the last drain, shape (k, width)."""
+        s = status if status is not None else self.status()
+        count = s.hist_count - self._hist_read
+        width = C.c_int32(0)
+        if count <= 0:
+            call("kry_solver_history", self._h, 0, 0, None, C.byref(width))
+            return np.empty((0, width.value))
+        buf = np.empty((count, 2), dtype=np.float64)
+        call("kry_solver_history", self._h, self._hist_read, count, _ptr(buf), C.byref(width))
+        self._hist_read = s.hist_count
+        return buf.reshape(-1)[:count * width.value].reshape(count, width.value)
+
+    def solution(self):
+        x = np.empty(self.n, dtype=np.float64)
+        call("kry_solver_solution", self._h, _ptr(x))
+        return x
+
+    def get_vector(self, name):
+        v = np.empty(self.n, dtype=np.float64)
+        call("kry_solver_get_vector", self._h, name.encode(), _ptr(v))
+        return v
+
+    def set_vector(self, name, a):
+        a = _f64(a)
+        if a.shape != (self.n,):
+            raise ValueError("vector size incompatible with solver dimensions")
+        call("kry_solver_set_vector", self._h, name.encode(), _ptr(a))
+
+    def get_scalar(self, name):
+        v = C.c_double(0.0)
+        call("kry_solver_get_scalar", self._h, name.encode(), C.byref(v))
+        return v.value
+
+    def set_scalar(self, name, value):
+        call("kry_solver_set_scalar", self._h, name.encode(), float(value))
+
+    def run(self, check_interval=64):
+        """Iterate until the device latches `done`; returns the final status."""
+        while True:
+            self.iterate(check_interval)
+            s = self.status()
+            if s.done:
+                return s
