@@ -20,7 +20,7 @@ from math import sqrt
 
 import numpy as np
 
-EPS = float(np.finfo(np.double).eps)          # tools/utils.py:7-9
+EPS = np.float64(np.finfo(np.double).eps)          # tools/utils.py:7-9
 
 
 class State(dict):
@@ -50,8 +50,8 @@ def cg_start(A, rhs, guess=None, precon=None, abstol=1.0e-8, reltol=1.0e-6,
         st.nMatvec += 1
     st.r = r
     y = _apply(precon, r)                                                   # cg.py:91-94
-    st.ry = float(np.dot(r, y))                                             # cg.py:99
-    st.residNorm0 = st.residNorm = float(np.abs(np.sqrt(st.ry)))            # cg.py:100
+    st.ry = np.float64(np.dot(r, y))                                             # cg.py:99
+    st.residNorm0 = st.residNorm = np.float64(np.abs(np.sqrt(st.ry)))            # cg.py:100
     st.residHistory = [st.residNorm0]
     st.threshold = max(abstol, reltol * st.residNorm0)                      # cg.py:102
     st.p = -r                                                               # cg.py:104
@@ -69,7 +69,7 @@ def cg_step(A, st):
     Ap = A(st.p)                                                            # cg.py:115
     st.nMatvec += 1
     st.Ap = Ap
-    pAp = float(np.dot(st.p, Ap))                                           # cg.py:117
+    pAp = np.float64(np.dot(st.p, Ap))                                           # cg.py:117
     st.pAp = pAp
     if st.check_curvature and pAp <= 0:                                     # cg.py:119-124
         st.infiniteDescent = st.p
@@ -80,13 +80,13 @@ def cg_step(A, st):
     st.x += alpha * st.p                                                    # cg.py:130
     st.r += alpha * Ap                                                      # cg.py:131
     y = _apply(st.precon, st.r)                                             # cg.py:137-140
-    ry_next = float(np.dot(st.r, y))                                        # cg.py:146
+    ry_next = np.float64(np.dot(st.r, y))                                        # cg.py:146
     beta = ry_next / st.ry                                                  # cg.py:149
     st.beta = beta
     st.p *= beta                                                            # cg.py:150
     st.p -= st.r                                                            # cg.py:151
     st.ry = ry_next
-    st.residNorm = float(np.abs(np.sqrt(st.ry)))                            # cg.py:154
+    st.residNorm = np.float64(np.abs(np.sqrt(st.ry)))                            # cg.py:154
     st.residHistory.append(st.residNorm)
     return st
 
@@ -114,8 +114,8 @@ def bicgstab_start(A, rhs, guess=None, precon=None, abstol=1.0e-8, reltol=1.0e-6
         st.nMatvec += 1
     st.r0 = r0
     st.rho = st.alpha = st.omega = 1.0                                      # bicgstab.py:67
-    st.rho_next = float(np.dot(r0, r0))                                     # bicgstab.py:68
-    st.residNorm = st.residNorm0 = float(np.abs(np.sqrt(st.rho_next)))
+    st.rho_next = np.float64(np.dot(r0, r0))                                     # bicgstab.py:68
+    st.residNorm = st.residNorm0 = np.float64(np.abs(np.sqrt(st.rho_next)))
     st.threshold = max(abstol, reltol * st.residNorm0)
     st.finished = bool(st.residNorm <= st.threshold or st.nMatvec >= st.matvec_max)
     st.residHistory = [st.residNorm0]
@@ -138,11 +138,11 @@ def bicgstab_step(A, st):
     q = _apply(st.precon, p)
     st.v = A(q)                                                             # :101
     st.nMatvec += 1
-    st.r0v = float(np.dot(st.r0, st.v))
+    st.r0v = np.float64(np.dot(st.r0, st.v))
     st.alpha = st.rho / st.r0v                                              # :103
     s = st.r - st.alpha * st.v                                              # :104
     st.s = s
-    st.residNorm = float(np.linalg.norm(s))                                 # :107
+    st.residNorm = np.float64(np.linalg.norm(s))                                 # :107
     st.residHistory.append(st.residNorm)
     if st.residNorm <= st.threshold:                                        # :110-113
         st.x += st.alpha * q
@@ -155,14 +155,14 @@ def bicgstab_step(A, st):
     t = A(z)                                                                # :125
     st.nMatvec += 1
     st.t = t
-    st.ts, st.tt, st.r0t = float(np.dot(t, s)), float(np.dot(t, t)), float(np.dot(st.r0, t))
+    st.ts, st.tt, st.r0t = np.float64(np.dot(t, s)), np.float64(np.dot(t, t)), np.float64(np.dot(st.r0, t))
     st.omega = st.ts / st.tt                                                # :126
     st.rho_next = -st.omega * st.r0t                                        # :127
     st.r = s - st.omega * t                                                 # :130
     z *= st.omega                                                           # :135 (aliases s)
     st.x += z                                                               # :136
     st.x += st.alpha * q                                                    # :137
-    st.residNorm = float(np.linalg.norm(st.r))                              # :139
+    st.residNorm = np.float64(np.linalg.norm(st.r))                              # :139
     st.residHistory.append(st.residNorm)
     if st.residNorm <= st.threshold or st.nMatvec >= st.matvec_max:         # :142
         st.finished = True
@@ -190,8 +190,8 @@ def cgs_start(A, rhs, guess=None, precon=None, abstol=1.0e-8, reltol=1.0e-6,
     if guess is not None:
         r0 = rhs - A(st.x)                       # cgs.py:59-60 -- NOT counted in nMatvec
     st.r0 = r0
-    st.rho = float(np.dot(r0, r0))                                          # :62
-    st.residNorm = st.residNorm0 = float(np.abs(np.sqrt(st.rho)))
+    st.rho = np.float64(np.dot(r0, r0))                                          # :62
+    st.residNorm = st.residNorm0 = np.float64(np.abs(np.sqrt(st.rho)))
     st.threshold = max(abstol, reltol * st.residNorm0)
     st.finished = bool(st.residNorm <= st.threshold or st.nMatvec >= st.matvec_max)
     st.residHistory = [st.residNorm0]
@@ -207,7 +207,7 @@ def cgs_step(A, st):
     y = _apply(st.precon, st.p)
     v = A(y)                                                                # :84
     st.nMatvec += 1
-    st.sigma = float(np.dot(st.r0, v))                                      # :85
+    st.sigma = np.float64(np.dot(st.r0, v))                                      # :85
     alpha = st.rho / st.sigma                                               # :86
     st.alpha = alpha
     q = st.u - alpha * v                                                    # :87
@@ -216,12 +216,12 @@ def cgs_step(A, st):
     Az = A(z)                                                               # :96
     st.nMatvec += 1
     st.r -= alpha * Az                                                      # :97
-    st.residNorm = float(np.linalg.norm(st.r))                              # :100
+    st.residNorm = np.float64(np.linalg.norm(st.r))                              # :100
     st.residHistory.append(st.residNorm)
     if st.residNorm <= st.threshold or st.nMatvec >= st.matvec_max:         # :102-104
         st.finished = True
         return st
-    rho_next = float(np.dot(st.r0, st.r))                                   # :106
+    rho_next = np.float64(np.dot(st.r0, st.r))                                   # :106
     beta = rho_next / st.rho
     st.beta = beta
     st.rho = rho_next
@@ -255,8 +255,8 @@ def tfqmr_start(A, rhs, guess=None, precon=None, abstol=1.0e-8, reltol=1.0e-6,
     if guess is not None:
         r0 = rhs - A(st.x)                       # tfqmr.py:58-59 -- NOT counted
     st.r0 = r0
-    st.rho = float(np.dot(r0, r0))                                          # :61
-    st.residNorm = st.residNorm0 = float(np.abs(np.sqrt(st.rho)))
+    st.rho = np.float64(np.dot(r0, r0))                                          # :61
+    st.residNorm = st.residNorm0 = np.float64(np.abs(np.sqrt(st.rho)))
     st.threshold = max(abstol, reltol * st.residNorm0)
     st.finished = bool(st.residNorm <= st.threshold or st.nMatvec >= st.matvec_max)
     st.residHistory = [st.residNorm0]
@@ -280,7 +280,7 @@ def _tfqmr_half(st, alpha):
     st.w -= alpha * st.u
     st.d *= st.theta * st.theta * st.eta / alpha
     st.d += st.z
-    st.theta = float(np.linalg.norm(st.w)) / st.residNorm
+    st.theta = np.float64(np.linalg.norm(st.w)) / st.residNorm
     c = 1.0 / np.sqrt(1 + st.theta * st.theta)
     st.residNorm *= st.theta * c
     st.eta = c * c * alpha
@@ -290,12 +290,12 @@ def _tfqmr_half(st, alpha):
 def tfqmr_step(A, st):
     """One pass of the body of tfqmr.py:85-153."""
     st.k += 1
-    st.sigma = float(np.dot(st.r0, st.v))                                   # :88
+    st.sigma = np.float64(np.dot(st.r0, st.v))                                   # :88
     alpha = st.rho / st.sigma
     st.alpha = alpha
     _tfqmr_half(st, alpha)                                                  # :92-99
     st.m = 2.0 * st.k - 1.0
-    st.residHistory.append(float(st.residNorm))
+    st.residHistory.append(np.float64(st.residNorm))
     if st.residNorm * np.sqrt(st.m + 1) < st.threshold or st.nMatvec >= st.matvec_max:
         st.finished = True
         return st
@@ -305,11 +305,11 @@ def tfqmr_step(A, st):
     st.u = A(st.z)                                                          # :114
     st.nMatvec += 1
     _tfqmr_half(st, alpha)                                                  # :116-123
-    st.residHistory.append(float(st.residNorm))
+    st.residHistory.append(np.float64(st.residNorm))
     if st.residNorm * np.sqrt(st.m + 1) < st.threshold or st.nMatvec >= st.matvec_max:
         st.finished = True
         return st
-    rho_next = float(np.dot(st.r0, st.w))                                   # :128
+    rho_next = np.float64(np.dot(st.r0, st.w))                                   # :128
     beta = rho_next / st.rho
     st.beta = beta
     st.rho = rho_next
@@ -355,7 +355,7 @@ def minres_start(A, b, precon=None, shift=0.0, itnlim=None, rtol=1.0e-12,
     st.done = False
     st.r1 = b
     st.y = b.copy() if precon is None else precon(b)                        # :161-165
-    beta1 = float(np.dot(b, st.y))                                          # :166
+    beta1 = np.float64(np.dot(b, st.y))                                          # :166
     if beta1 < 0:                                                           # :170-173
         st.istop = 9
         st.done = True
@@ -394,7 +394,7 @@ def minres_step(A, st):
     y -= st.shift * v                                                       # :240
     if itn >= 2:
         y = y - (st.beta / st.oldb) * st.r1                                 # :243
-    alfa = float(np.dot(v, y))                                              # :245
+    alfa = np.float64(np.dot(v, y))                                              # :245
     st.alfa = alfa
     y = (-alfa / st.beta) * st.r2 + y                                       # :246
     st.r1 = st.r2.copy()                                                    # :247-248
@@ -403,7 +403,7 @@ def minres_step(A, st):
         y = st.precon(st.r2)
     st.y = y
     st.oldb = st.beta                                                       # :250
-    beta = float(np.dot(st.r2, y))                                          # :251
+    beta = np.float64(np.dot(st.r2, y))                                          # :251
     if beta < 0:                                                            # :252-254
         st.istop = 6
         st.broke = True
@@ -438,7 +438,7 @@ def minres_step(A, st):
     st.xNrgNorm2 += phi * phi                                               # :303-310
     st.dErr[itn % st.window] = phi
     if itn > st.window:
-        st.trncDirErr = float(np.linalg.norm(st.dErr))
+        st.trncDirErr = np.float64(np.linalg.norm(st.dErr))
         xNrgNorm = sqrt(st.xNrgNorm2)
         st.dir_errors_window.append(st.trncDirErr / xNrgNorm)
         if st.trncDirErr < st.etol * xNrgNorm:

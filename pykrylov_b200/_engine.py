@@ -1,0 +1,120 @@
+"""Glue between the solver classes (reference API) and the device-resident iterations.
+
+``resolve`` decides whether a (operator, preconditioner) pair can iterate entirely
+on the GPU: the operator must be a :class:`CsrLinearOperator` and the
+preconditioner absent or diagonal.  Anything else is a closure the device cannot
+see; those go through the host-callback bridge (vectors stay in HBM, each
+operator application crosses PCIe) -- never through a NumPy re-implementation of
+the loop.
+"""
+import numpy as np
+
+from .device import DeviceSolver, DeviceVector, default_context, multi_axpy_dot
+
+
+class DevicePlan(object):
+    def __init__(self, csr, precon_diag, precon_mode):
+        self.csr = csr
+        self.precon_diag = precon_diag
+        self.precon_mode = precon_mode
+
+
+def _diag_precon(precon, n):
+    """(diag, mode) for preconditioners the device can apply itself, else None."""
+    if precon is None:
+        return None, 0
+    from .linop import DiagonalOperator
+    if isinstance(precon, DiagonalOperator):
+        d = np.asarray(precon.diag)
+        if d.dtype == np.float64 and d.shape == (n,):
+            return d, 1                      # y = d .* r   (linop.py:473-503)
+        return None
+    d = getattr(precon, "diag", None)
+    if d is not None and not hasattr(precon, "device_csr") and callable(precon):
+        d = np.asarray(d)
+        if d.dtype == np.float64 and d.shape == (n,):
+            return d, 2                      # y = r ./ d   (examples/bmark.py:14-22)
+    return None
+
+
+def resolve(op, precon, n):
+    csr = getattr(op, "device_csr", None)
+    if csr is None or csr.shape != (n, n):
+        return None
+    pd = _diag_precon(precon, n)
+    if pd is None:
+        return None
+    return DevicePlan(csr, pd[0], pd[1])
+
+
+def check_real(op, rhs):
+    rtype = np.result_type(op.dtype, rhs.dtype)
+    if np.issubdtype(rtype, np.complexfloating):
+        raise TypeError("the device engine iterates in real fp64; complex systems are not supported")
+    return np.result_type(rtype, np.float64) if not np.issubdtype(rtype, np.floating) else rtype
+
+
+def make_solver(method, plan, context=None):
+    ctx = context or plan.csr.ctx
+    S = DeviceSolver(ctx, method, plan.csr)
+    S.set_precon_diag(plan.precon_diag, plan.precon_mode)
+    return S
+
+
+def drive(S, check_interval, on_chunk=None):
+    """Enqueue `check_interval` iterations at a time until the device latches done.
+    One small D2H (status block + new history entries) per chunk."""
+    st = S.status()
+    if on_chunk is not None:
+        on_chunk(st, S.drain_history(st))
+    while not st.done:
+        S.iterate(check_interval)
+        st = S.status()
+        if on_chunk is not None:
+            on_chunk(st, S.drain_history(st))
+    return st
+
+
+# ------------------------------------------------------------------ bridge
+class HostBridge(object):
+    """Vectors live in HBM; an opaque Python operator is applied by copying its
+    argument to the host and its result back."""
+
+    def __init__(self, n, context=None):
+        self.ctx = context or default_context()
+        self.n = n
+
+    def vec(self, init=None):
+        v = DeviceVector(self.ctx, self.n)
+        if init is None:
+            v.fill(0.0)
+        else:
+            v.upload(np.asarray(init, dtype=np.float64))
+        return v
+
+    def apply(self, op, x_vec, out_vec):
+        """out = op * x through the host (counts as one operator product)."""
+        y = op * x_vec.download()
+        out_vec.upload(np.asarray(y, dtype=np.float64))
+        return out_vec
+
+    def apply_precon(self, precon, x_vec, out_vec):
+        out_vec.upload(np.asarray(precon * x_vec.download(), dtype=np.float64))
+        return out_vec
+
+    def fused(self, ops, dots=()):
+        """kry_multi_axpy_dot + read back the dot results."""
+        multi_axpy_dot(self.ctx, ops, dots, slot0=0)
+        if dots:
+            return self.ctx.scalars(0, len(dots))
+        return ()
+
+
+def require_plan(method, op, precon, n):
+    plan = resolve(op, precon, n)
+    if plan is None:
+        raise NotImplementedError(
+            "%s currently iterates only on device operators (CsrLinearOperator / "
+            "PysparseLinearOperator / CoordLinearOperator / linop_from_scipy) with no or a "
+            "diagonal preconditioner; closure-defined operators are bridged for CG only" % method)
+    return plan

@@ -13,9 +13,10 @@ int kry_halo_exchange(kry_csr *M, double *x_dev);    // comm.cu; no-op unless sh
 template <class K>
 static inline int set_max_smem(K kernel, kry_ctx *c, size_t bytes)
 {
+    (void)c;
     if (bytes <= 48 * 1024) return KRY_OK;
-    KRY_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)c->smem_optin));
+    // the opt-in limit counts static + dynamic smem, so ask for exactly what is used
+    KRY_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     return KRY_OK;
 }
 
@@ -42,7 +43,7 @@ int spmv_launch(kry_csr *M, bool trans, Gather g, Epi epi, Fin fin, const int *d
     int kind = M->kind == KRY_SPMV_AUTO ? KRY_SPMV_STREAM : M->kind;
     const int tile = M->tile_nnz ? M->tile_nnz : KRY_DEFAULT_TILE;
     const int threads = M->threads ? M->threads : KRY_DEFAULT_THREADS;
-    const size_t budget = (size_t)c->smem_optin - 1024;
+    const size_t budget = (size_t)c->smem_optin - 2048;   // static smem of the reduction + barriers
     size_t smem = 0;
     int grid = 1, cap = 0;
 

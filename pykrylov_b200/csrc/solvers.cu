@@ -7,6 +7,7 @@
 // inner products), and the scalar step that follows an inner product runs in
 // the last CTA of the same launch.  Reference line numbers are relative to
 // /root/reference/pykrylov/.
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -958,6 +959,7 @@ struct MinFinQR {
         // energy norm / truncated direct error, :303-310
         v[M_XNRG2] += phi * phi;
         const int window = s->window;
+        double direrr = nan("");
         s->derr[itn % window] = phi;
         if (itn > window) {
             double ss = 0.0;           // np.linalg.norm(dErr): sqrt of the ordered sum of squares
@@ -965,6 +967,7 @@ struct MinFinQR {
             const double trnc = sqrt(ss);
             v[M_TRNC] = trnc;
             const double xnrg = sqrt(v[M_XNRG2]);
+            direrr = trnc / xnrg;                                            // :308
             if (trnc < s->etol * xnrg) s->istop = 10;
         }
         v[M_GMAX] = fmax(v[M_GMAX], gamma);                                  // :314-319
@@ -984,7 +987,7 @@ struct MinFinQR {
         v[M_TEST1] = test1;
         v[M_TEST2] = test2;
         s->resid = rnorm;
-        hist_push(s, hist, 1, rnorm, 0.0);                                   // :336
+        hist_push(s, hist, 2, rnorm, direrr);                                // :336, :308
         const double Acond = v[M_GMAX] / v[M_GMIN];                          // :344
         v[M_ACOND] = Acond;
         if (s->istop == 0) {                                                 // :349-361
@@ -1168,7 +1171,7 @@ extern "C" int kry_solver_create(kry_ctx *c, kry_method method, kry_csr *A, kry_
     S->n = n;
     S->ncap = A->halo.active ? A->A.ncols : n;
     S->sharded = A->halo.active && c->nranks > 1;
-    S->hist_width = (method == KRY_CG) ? 2 : 1;
+    S->hist_width = (method == KRY_CG || method == KRY_MINRES) ? 2 : 1;
     auto pad = [](int64_t v) { return (v + 31) & ~(int64_t)31; };
     int64_t total = 0;
     for (int i = 0; i < nv; ++i) total += pad(specs[i].gathered ? S->ncap : n);
@@ -1467,24 +1470,60 @@ static int scalar_index(const char *name)
     return -1;
 }
 
+// Address of a named scalar inside the device block.  Besides the recurrence
+// scalars this covers the counters and the MINRES error window so that the
+// single-step parity tests can transplant a complete state.
+static int scalar_locate(kry_solver *S, const char *name, void **addr, int *kind)
+{
+    *kind = 0;                                    // 0: double, 1: long long, 2: int
+    const int idx = scalar_index(name);
+    if (idx >= 0) { *addr = &S->ds->s[idx]; return KRY_OK; }
+    if (!strcmp(name, "resid")) { *addr = &S->ds->resid; return KRY_OK; }
+    if (!strcmp(name, "resid0")) { *addr = &S->ds->resid0; return KRY_OK; }
+    if (!strcmp(name, "threshold")) { *addr = &S->ds->threshold; return KRY_OK; }
+    if (!strcmp(name, "xnrg2")) { *addr = &S->ds->s[M_XNRG2]; return KRY_OK; }
+    if (!strcmp(name, "n_iter")) { *addr = &S->ds->n_iter; *kind = 1; return KRY_OK; }
+    if (!strcmp(name, "n_matvec")) { *addr = &S->ds->n_matvec; *kind = 1; return KRY_OK; }
+    if (!strcmp(name, "istop")) { *addr = &S->ds->istop; *kind = 2; return KRY_OK; }
+    if (!strcmp(name, "done")) { *addr = &S->ds->done; *kind = 2; return KRY_OK; }
+    if (!strncmp(name, "derr", 4)) {
+        const int k = atoi(name + 4);
+        if (k >= 0 && k < 16) { *addr = &S->ds->derr[k]; return KRY_OK; }
+    }
+    kry_set_error("no scalar named '%s'", name);
+    return KRY_ERR_INVALID;
+}
+
 extern "C" int kry_solver_get_scalar(kry_solver *S, const char *name, double *value)
 {
     KRY_REQUIRE(S && name && value, KRY_ERR_INVALID, "kry_solver_get_scalar: NULL argument");
-    const int idx = scalar_index(name);
-    KRY_REQUIRE(idx >= 0, KRY_ERR_INVALID, "kry_solver_get_scalar: no scalar named '%s'", name);
-    KRY_CUDA(cudaMemcpyAsync(value, &S->ds->s[idx], sizeof(double), cudaMemcpyDeviceToHost,
-                             S->ctx->stream));
+    void *addr = nullptr;
+    int kind = 0;
+    KRY_TRY(scalar_locate(S, name, &addr, &kind));
+    double d = 0.0;
+    long long ll = 0;
+    int i = 0;
+    void *dst = kind == 0 ? (void *)&d : (kind == 1 ? (void *)&ll : (void *)&i);
+    const size_t bytes = kind == 0 ? sizeof(d) : (kind == 1 ? sizeof(ll) : sizeof(i));
+    KRY_CUDA(cudaMemcpyAsync(dst, addr, bytes, cudaMemcpyDeviceToHost, S->ctx->stream));
     KRY_CUDA(cudaStreamSynchronize(S->ctx->stream));
+    *value = kind == 0 ? d : (kind == 1 ? (double)ll : (double)i);
     return KRY_OK;
 }
 
 extern "C" int kry_solver_set_scalar(kry_solver *S, const char *name, double value)
 {
     KRY_REQUIRE(S && name, KRY_ERR_INVALID, "kry_solver_set_scalar: NULL argument");
-    const int idx = scalar_index(name);
-    KRY_REQUIRE(idx >= 0, KRY_ERR_INVALID, "kry_solver_set_scalar: no scalar named '%s'", name);
-    KRY_CUDA(cudaMemcpyAsync(&S->ds->s[idx], &value, sizeof(double), cudaMemcpyHostToDevice,
-                             S->ctx->stream));
+    void *addr = nullptr;
+    int kind = 0;
+    KRY_TRY(scalar_locate(S, name, &addr, &kind));
+    double d = value;
+    long long ll = (long long)value;
+    int i = (int)value;
+    const void *src = kind == 0 ? (void *)&d : (kind == 1 ? (void *)&ll : (void *)&i);
+    const size_t bytes = kind == 0 ? sizeof(d) : (kind == 1 ? sizeof(ll) : sizeof(i));
+    KRY_CUDA(cudaMemcpyAsync(addr, src, bytes, cudaMemcpyHostToDevice, S->ctx->stream));
     KRY_CUDA(cudaStreamSynchronize(S->ctx->stream));
+    if (!strcmp(name, "n_iter")) S->rot = ll;      // keep the MINRES buffer rotation in step
     return KRY_OK;
 }

@@ -1,0 +1,53 @@
+"""TFQMR, device-resident (reference: pykrylov/tfqmr/tfqmr.py:7-160).
+
+The loop of tfqmr.py:85-153 runs on the GPU; ``residNorm`` is the quasi-residual
+tau and the stopping test is ``tau * sqrt(m+1) < threshold`` as in the reference
+(tfqmr.py:101-105,123-127).  The initial-residual product of a supplied guess is
+not counted in ``nMatvec`` (tfqmr.py:58-59).
+"""
+from ..generic import KrylovMethod
+from .. import _engine
+
+__docformat__ = "restructuredtext"
+
+
+class TFQMR(KrylovMethod):
+    """Transpose-free QMR for unsymmetric ``A x = b`` (2 operator products,
+    4 inner products, 10 AXPYs per iteration; never uses A^T)."""
+
+    def __init__(self, op, **kwargs):
+        KrylovMethod.__init__(self, op, **kwargs)
+        self.name = "Transpose-Free Quasi-Minimum Residual"
+        self.acronym = "TFQMR"
+        self.prefix = self.acronym + ": "
+
+    def solve(self, rhs, **kwargs):
+        """Keywords (tfqmr.py:44-47): ``guess`` (default 0), ``matvec_max`` (2n)."""
+        n = rhs.shape[0]
+        result_type = _engine.check_real(self.op, rhs)
+        guess = kwargs.get("guess", None)
+        matvec_max = kwargs.get("matvec_max", 2 * n)
+        plan = _engine.require_plan(self.acronym, self.op, self.precon, n)
+        S = _engine.make_solver("tfqmr", plan, self.context)
+        S.setup(rhs, guess=guess, abstol=self.abstol, reltol=self.reltol, matvec_max=matvec_max)
+        state = {"first": True}
+
+        def replay(st, hist):
+            for (resid,) in hist:
+                if state["first"]:
+                    state["first"] = False
+                    self.residNorm0 = resid
+                    self.logger.info("Initial residual = %8.2e" % resid)
+                    self.logger.info("Threshold = %8.2e" % st.threshold)
+
+        st = _engine.drive(S, self.check_interval, replay)
+        if st.n_iter == 0 and st.hist_count <= 1:
+            # the reference raises NameError here (`m` is unbound when the initial
+            # guess already satisfies the test, tfqmr.py:156); report non-convergence
+            self.converged = False
+        else:
+            self.converged = bool(st.converged)
+        self.nMatvec = int(st.n_matvec)
+        self.bestSolution = self.x = S.solution().astype(result_type, copy=False)
+        self.residNorm = st.resid_norm
+        self.op._nMatvec += self.nMatvec + (1 if guess is not None else 0)
