@@ -1,0 +1,691 @@
+"""GPU parity tests (run with `-m gpu` on a B200): every CUDA path is called through
+the C ABI (ctypes) and compared with the oracle on identical, seeded inputs.
+
+Bars (BASELINE.json north_star):
+  * integer / indexing work and the SpMV row sums: BIT-EXACT;
+  * floating point per iteration from an identical state: relative <= 1e-12;
+  * final residual: agreement <= 1e-8.
+"""
+import os
+import zlib
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import mtx
+from oracle import krylov_ref as kr
+from oracle.csr_ref import CsrRef, load_mtx
+
+pytestmark = pytest.mark.gpu
+
+RTOL_STEP = 1.0e-12      # per-iteration floating point bar
+RTOL_FINAL = 1.0e-8      # final residual bar
+
+
+def L():
+    from pykrylov_b200 import _lib
+    return _lib
+
+
+def dev():
+    from pykrylov_b200 import device
+    return device
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    scale = np.max(np.abs(b)) if b.size else 0.0
+    if scale == 0.0:
+        return float(np.max(np.abs(a))) if a.size else 0.0
+    return float(np.max(np.abs(a - b)) / scale)
+
+
+def srel(a, b):
+    return abs(a - b) / abs(b) if b != 0 else abs(a)
+
+
+def upload(ctx, M, symmetric=False, transpose=False):
+    return dev().DeviceCsr.from_arrays(ctx, M.shape, M.indptr, M.indices, M.data,
+                                       symmetric=symmetric, build_transpose=transpose)
+
+
+def fixtures():
+    rng = np.random.default_rng(7)
+    mats = {"1138bus": load_mtx(mtx("1138bus")), "jpwh_991": load_mtx(mtx("jpwh_991")),
+            "GD97_b": load_mtx(mtx("GD97_b"))}
+    ip, ix, dv = kr.poisson2d_csr(123)
+    mats["poisson2d_123"] = CsrRef((123 * 123, 123 * 123), ip, ix, dv)
+    ip, ix, dv = kr.convdiff3d_csr(21)
+    mats["convdiff3d_21"] = CsrRef((21 ** 3, 21 ** 3), ip, ix, dv)
+    R = sp.random(3000, 2500, density=0.004, random_state=2, format="csr")
+    R.sort_indices()
+    mats["random_rect"] = CsrRef.from_scipy(R)
+    # ragged: empty rows, one very long row (forces the thread-per-row fallback), unsorted columns
+    n = 6000
+    rows = [np.array([], dtype=np.int64)] * n
+    rows = list(rows)
+    rows[5] = rng.permutation(n)[:5000]
+    rows[17] = np.array([3, 1, 2])
+    rows[n - 1] = np.array([0, n - 1])
+    for i in range(100, 400):
+        rows[i] = rng.integers(0, n, size=rng.integers(0, 9))
+    indptr = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int32)
+    indices = np.concatenate(rows).astype(np.int32)
+    mats["ragged"] = CsrRef((n, n), indptr, indices, rng.standard_normal(len(indices)))
+    mats["empty"] = CsrRef((50, 40), np.zeros(51, np.int32), np.zeros(0, np.int32), np.zeros(0))
+    return mats
+
+
+KERNELS = [("row", 1, 0, 0), ("stream", 2, 4096, 256), ("stream_small", 2, 512, 64),
+           ("tma", 3, 2048, 256), ("tma_small", 3, 256, 128)]
+
+
+# ============================================================== integer work
+@pytest.mark.parametrize("name", ["1138bus", "jpwh_991", "GD97_b"])
+def test_device_csr_equals_scipy_and_golden(ctx, name, golden):
+    from pykrylov_b200.mmio import read_mtx
+    shape, ip, ix, dv, sym = read_mtx(mtx(name))
+    A = dev().DeviceCsr.from_arrays(ctx, shape, ip, ix, dv, symmetric=sym, build_transpose=True)
+    p, i, d = A.download()
+    g = golden["csr/" + name]
+    assert zlib.crc32(p.tobytes()) == g["indptr_crc"] and zlib.crc32(i.tobytes()) == g["indices_crc"]
+    assert zlib.crc32(d.tobytes()) == g["data_crc"]
+    M = load_mtx(mtx(name))
+    T = CsrRef.from_scipy(M.to_scipy().T.tocsr())
+    tp, ti, td = A.download(transposed=True)
+    assert np.array_equal(tp, T.indptr) and np.array_equal(ti, T.indices) and np.array_equal(td, T.data)
+    assert np.array_equal(A.diagonal(), M.to_scipy().diagonal())
+
+
+def test_device_transpose_of_unsymmetric_is_bit_exact(ctx):
+    for name in ("jpwh_991", "random_rect", "ragged", "convdiff3d_21"):
+        M = fixtures()[name]
+        A = upload(ctx, M, transpose=True)
+        tp, ti, td = A.download(transposed=True)
+        S = M.to_scipy()
+        # stable counting sort: inside a row of A^T the original row order is kept
+        coo_r = np.repeat(np.arange(M.shape[0]), np.diff(M.indptr))
+        order = np.argsort(M.indices, kind="stable")
+        assert np.array_equal(ti, coo_r[order].astype(np.int32)) and np.array_equal(td, M.data[order])
+        assert np.array_equal(tp, np.concatenate([[0], np.cumsum(np.bincount(M.indices, minlength=M.shape[1]))]))
+        del S
+
+
+def test_device_gallery_equals_oracle_generators(ctx):
+    D = dev().DeviceCsr
+    for g in (1, 2, 7, 64):
+        p, i, d = D.poisson2d(ctx, g).download()
+        rp, ri, rd = kr.poisson2d_csr(g)
+        assert np.array_equal(p, rp) and np.array_equal(i, ri) and np.array_equal(d, rd)
+    g = 40                                               # a row shard keeps global column ids
+    p, i, d = D.poisson2d(ctx, g, 500, 1100).download()
+    rp, ri, rd = kr.poisson2d_csr(g, 500, 1100)
+    assert np.array_equal(p, rp) and np.array_equal(i, ri) and np.array_equal(d, rd)
+    for m in (1, 3, 9):
+        p, i, d = D.convdiff3d(ctx, m, 0.5).download()
+        rp, ri, rd = kr.convdiff3d_csr(m, 0.5)
+        assert np.array_equal(p, rp) and np.array_equal(i, ri) and np.array_equal(d, rd)
+    p, i, d = D.poisson1d(ctx, 11).download()
+    assert list(p[:3]) == [0, 2, 5] and list(d[:5]) == [2, -1, -1, 2, -1] and len(d) == 31
+
+
+# ===================================================================== SpMV
+@pytest.mark.parametrize("kname,kind,tile,threads", KERNELS)
+def test_spmv_bit_exact_all_fixtures(ctx, kname, kind, tile, threads):
+    rng = np.random.default_rng(0)
+    for name, M in fixtures().items():
+        A = upload(ctx, M, transpose=True)
+        A.set_kernel(kind, tile, threads)
+        x = rng.standard_normal(M.shape[1])
+        xt = rng.standard_normal(M.shape[0])
+        assert np.array_equal(A.matvec(x), M.matvec(x)), (name, kname)
+        assert np.array_equal(A.matvec(xt, trans=True), M.rmatvec(xt)), (name, kname, "T")
+
+
+@pytest.mark.parametrize("kname,kind,tile,threads", KERNELS)
+def test_spmv_fused_dots(ctx, kname, kind, tile, threads):
+    rng = np.random.default_rng(1)
+    for name in ("jpwh_991", "poisson2d_123", "ragged"):
+        M = fixtures()[name]
+        A = upload(ctx, M)
+        A.set_kernel(kind, tile, threads)
+        x = rng.standard_normal(M.shape[1])
+        w1, w2 = rng.standard_normal(M.shape[0]), rng.standard_normal(M.shape[0])
+        xv, yv = ctx.vector(x), ctx.vector(M.shape[0])
+        A.spmv_dot(xv, yv, [ctx.vector(w1), None, ctx.vector(w2)], slot0=5)
+        y = M.matvec(x)
+        assert np.array_equal(yv.download(), y)
+        got = ctx.scalars(5, 3)
+        for g_, ref in zip(got, (np.dot(w1, y), np.dot(y, y), np.dot(w2, y))):
+            assert abs(g_ - ref) <= 1e-13 * np.sqrt(np.dot(y, y) * max(np.dot(w1, w1), np.dot(y, y)))
+
+
+def test_spmv_shape_errors_are_valueerror(ctx):
+    M = fixtures()["random_rect"]
+    A = upload(ctx, M)
+    with pytest.raises(ValueError):
+        A.matvec(np.ones(M.shape[1] + 1))
+    with pytest.raises(ValueError):
+        A.spmv(ctx.vector(M.shape[1]), ctx.vector(M.shape[0] + 2))
+    with pytest.raises(L().KrylovDeviceError):
+        A.matvec(np.ones(M.shape[0]), trans=True)           # transpose was not built
+    with pytest.raises(L().KrylovDeviceError):
+        dev().DeviceCsr.from_arrays(ctx, (2, 2), [0, 1, 3], [0, 1], [1.0, 1.0])   # rowptr[-1] != nnz
+
+
+# =============================================================== multi-AXPY
+def test_multi_axpy_dot_matches_numpy(ctx):
+    rng = np.random.default_rng(3)
+    n = 100003
+    a, b, c = (rng.standard_normal(n) for _ in range(3))
+    va, vb, vc = ctx.vector(a), ctx.vector(b), ctx.vector(c)
+    ctx.set_scalars(10, [0.37, -1.25])
+    ops = [dict(z=va, u=va, w=vb, a=1.0, b=0.37),                     # a += 0.37 b      (immediate)
+           dict(z=vc, u=vc, w=va, a_slot=11, b=1.0, b_slot=10, b_neg=1),  # c = -1.25 c - 0.37 a (slots)
+           dict(z=vb, u=vb, a=2.0)]                                   # b *= 2
+    dev().multi_axpy_dot(ctx, ops, [(va, vc), (vb, vb)], slot0=20)
+    a2 = a + 0.37 * b
+    c2 = -1.25 * c + (-0.37) * a2
+    b2 = 2.0 * b
+    assert np.array_equal(va.download(), a2) and np.array_equal(vc.download(), c2)
+    assert np.array_equal(vb.download(), b2)
+    got = ctx.scalars(20, 2)
+    assert srel(got[0], np.dot(a2, c2)) <= 1e-12 and srel(got[1], np.dot(b2, b2)) <= 1e-13
+    with pytest.raises(ValueError):
+        dev().multi_axpy_dot(ctx, [dict(z=va, u=ctx.vector(5), a=1.0)])
+
+
+def test_reduction_is_deterministic(ctx):
+    M = fixtures()["poisson2d_123"]
+    A = upload(ctx, M)
+    x = np.random.default_rng(5).standard_normal(M.shape[1])
+    xv, yv = ctx.vector(x), ctx.vector(M.shape[0])
+    seen = set()
+    for _ in range(5):
+        A.spmv_dot(xv, yv, [xv, None], slot0=0)
+        seen.add(tuple(ctx.scalars(0, 2)))
+    assert len(seen) == 1
+
+
+# ==================================================== single-step solver parity
+def cg_case(name):
+    M = fixtures()[name]
+    n = M.shape[0]
+    rng = np.random.default_rng(21)
+    return M, M.matvec(np.ones(n)), rng.standard_normal(n)
+
+
+@pytest.mark.parametrize("name,precon", [("1138bus", 0), ("poisson2d_123", 0), ("1138bus", 1), ("1138bus", 2)])
+def test_cg_single_step_from_identical_state(ctx, name, precon):
+    M, rhs, guess = cg_case(name)
+    n = M.shape[0]
+    d = np.abs(M.to_scipy().diagonal())
+    pvec = None if precon == 0 else (1.0 / d if precon == 1 else d)
+    pfun = None if precon == 0 else ((lambda r: pvec * r) if precon == 1 else (lambda r: r / pvec))
+    A = upload(ctx, M, symmetric=True)
+    st = kr.cg_start(M, rhs, guess=guess.copy(), precon=pfun, matvec_max=10 ** 6)
+    S = dev().DeviceSolver(ctx, "cg", A)
+    S.set_precon_diag(pvec, precon)
+    S.setup(rhs, guess=guess, matvec_max=10 ** 6)
+    d0 = S.status()
+    assert srel(d0.resid_norm0, st.residNorm0) <= RTOL_STEP and d0.n_matvec == 1
+    assert rel(S.get_vector("r"), st.r) <= RTOL_STEP and np.array_equal(S.get_vector("p"), -S.get_vector("r"))
+    for k in range(12):
+        for _ in range(3 if k else 0):
+            kr.cg_step(M, st)
+        # transplant the oracle state, then advance both by exactly one iteration
+        S.set_vector("x", st.x); S.set_vector("r", st.r); S.set_vector("p", st.p)
+        S.set_scalar("ry", float(st.ry))
+        kr.cg_step(M, st)
+        S.iterate(1)
+        assert np.array_equal(S.get_vector("Ap"), st.Ap)           # SpMV: bit-exact
+        assert srel(S.get_scalar("pAp"), st.pAp) <= RTOL_STEP
+        assert srel(S.get_scalar("alpha"), st.alpha) <= RTOL_STEP
+        assert srel(S.get_scalar("beta"), st.beta) <= RTOL_STEP
+        assert srel(S.get_scalar("ry"), st.ry) <= RTOL_STEP
+        assert srel(S.status().resid_norm, st.residNorm) <= RTOL_STEP
+        for v in ("x", "r", "p"):
+            assert rel(S.get_vector(v), st[v]) <= RTOL_STEP, (k, v)
+
+
+def nonsym_case():
+    M = fixtures()["jpwh_991"]
+    n = M.shape[0]
+    rng = np.random.default_rng(22)
+    return M, M.matvec(rng.standard_normal(n)), rng.standard_normal(n)
+
+
+@pytest.mark.parametrize("precon", [0, 2])
+def test_bicgstab_single_step_from_identical_state(ctx, precon):
+    M, rhs, guess = nonsym_case()
+    d = np.maximum(np.abs(M.to_scipy().diagonal()), 1.0)
+    pfun = None if precon == 0 else (lambda r: r / d)
+    A = upload(ctx, M)
+    st = kr.bicgstab_start(M, rhs, guess=guess.copy(), precon=pfun, matvec_max=10 ** 6)
+    S = dev().DeviceSolver(ctx, "bicgstab", A)
+    S.set_precon_diag(None if precon == 0 else d, precon)
+    S.setup(rhs, guess=guess, matvec_max=10 ** 6)
+    assert srel(S.status().resid_norm0, st.residNorm0) <= RTOL_STEP
+    assert rel(S.get_vector("r0"), st.r0) <= RTOL_STEP
+    for k in range(10):
+        for _ in range(2 if k else 0):
+            kr.bicgstab_step(M, st)
+        # device boundary state already holds the direction of the coming trip
+        beta = st.rho_next / st.rho * st.alpha / st.omega
+        p_new = st.p * beta
+        p_new -= beta * st.omega * st.v
+        p_new += st.r
+        S.set_vector("x", st.x); S.set_vector("r", st.r); S.set_vector("r0", st.r0)
+        S.set_vector("p", p_new); S.set_vector("v", st.v)
+        if precon:
+            S.set_vector("q", p_new / d)
+        S.set_scalar("rho", float(st.rho_next))
+        kr.bicgstab_step(M, st)
+        S.iterate(1)
+        assert np.array_equal(S.get_vector("v"), st.v) and np.array_equal(S.get_vector("t"), st.t)
+        assert srel(S.get_scalar("alpha"), st.alpha) <= RTOL_STEP
+        assert srel(S.get_scalar("omega"), st.omega) <= RTOL_STEP
+        assert srel(S.get_scalar("rho"), st.rho_next) <= 1e-11     # -omega*(r0.t): one cancellation
+        assert srel(S.status().resid_norm, st.residNorm) <= RTOL_STEP
+        for v in ("x", "r"):
+            assert rel(S.get_vector(v), st[v]) <= RTOL_STEP, (k, v)
+
+
+@pytest.mark.parametrize("precon", [0, 2])
+def test_cgs_single_step_from_identical_state(ctx, precon):
+    M, rhs, guess = nonsym_case()
+    d = np.maximum(np.abs(M.to_scipy().diagonal()), 1.0)
+    pfun = None if precon == 0 else (lambda r: r / d)
+    A = upload(ctx, M)
+    st = kr.cgs_start(M, rhs, guess=guess.copy(), precon=pfun, matvec_max=10 ** 6)
+    S = dev().DeviceSolver(ctx, "cgs", A)
+    S.set_precon_diag(None if precon == 0 else d, precon)
+    S.setup(rhs, guess=guess, matvec_max=10 ** 6)
+    assert S.status().n_matvec == 0                                # cgs.py:59-60: not counted
+    for k in range(10):
+        for _ in range(2 if k else 0):
+            kr.cgs_step(M, st)
+        for v in ("x", "r", "r0", "u", "p"):
+            S.set_vector(v, st[v])
+        if precon:
+            S.set_vector("y", st.p / d)
+        S.set_scalar("rho", float(st.rho))
+        kr.cgs_step(M, st)
+        S.iterate(1)
+        assert srel(S.get_scalar("alpha"), st.alpha) <= RTOL_STEP
+        assert srel(S.get_scalar("beta"), st.beta) <= 1e-11
+        assert srel(S.get_scalar("rho"), st.rho) <= 1e-11
+        assert srel(S.status().resid_norm, st.residNorm) <= RTOL_STEP
+        for v in ("x", "r", "u", "p"):
+            assert rel(S.get_vector(v), st[v]) <= 1e-11, (k, v)
+
+
+@pytest.mark.parametrize("precon", [0, 2])
+def test_tfqmr_single_step_from_identical_state(ctx, precon):
+    M, rhs, guess = nonsym_case()
+    d = np.maximum(np.abs(M.to_scipy().diagonal()), 1.0)
+    pfun = None if precon == 0 else (lambda r: r / d)
+    A = upload(ctx, M)
+    st = kr.tfqmr_start(M, rhs, guess=guess.copy(), precon=pfun, matvec_max=10 ** 6)
+    S = dev().DeviceSolver(ctx, "tfqmr", A)
+    S.set_precon_diag(None if precon == 0 else d, precon)
+    S.setup(rhs, guess=guess, matvec_max=10 ** 6)
+    assert S.status().n_matvec == 1 and np.array_equal(S.get_vector("u"), S.get_vector("v"))
+    for k in range(10):
+        for _ in range(2 if k else 0):
+            kr.tfqmr_step(M, st)
+        for v in ("x", "r0", "y", "w", "d", "u", "v"):
+            S.set_vector(v, st[v])
+        if precon:
+            S.set_vector("z", st.z)
+        S.set_scalar("rho", float(st.rho)); S.set_scalar("theta", float(st.theta))
+        S.set_scalar("eta", float(st.eta)); S.set_scalar("resid", float(st.residNorm))
+        S.set_scalar("k", float(st.k + 1))
+        S.set_scalar("alpha", float(st.rho / np.dot(st.r0, st.v)))
+        kr.tfqmr_step(M, st)
+        S.iterate(1)
+        assert srel(S.get_scalar("theta"), st.theta) <= RTOL_STEP
+        assert srel(S.get_scalar("eta"), st.eta) <= RTOL_STEP
+        assert srel(S.get_scalar("rho"), st.rho) <= 1e-11
+        assert srel(S.status().resid_norm, st.residNorm) <= RTOL_STEP
+        for v in ("x", "y", "w", "d", "u", "v"):
+            assert rel(S.get_vector(v), st[v]) <= 1e-11, (k, v)
+
+
+def minres_case():
+    M = fixtures()["jpwh_991"]
+    S0 = M.to_scipy()
+    Sm = CsrRef.from_scipy((S0 + S0.T) * 0.5)
+    return Sm, Sm.matvec(np.ones(Sm.shape[0]))
+
+
+@pytest.mark.parametrize("shift", [0.0, 0.5])
+def test_minres_single_step_from_identical_state(ctx, shift):
+    M, rhs = minres_case()
+    A = upload(ctx, M, symmetric=True)
+    st = kr.minres_start(M, rhs, shift=shift)
+    S = dev().DeviceSolver(ctx, "minres", A)
+    S.setup(rhs, matvec_max=10 ** 6, shift=shift, rtol=1e-12, etol=1e-6, window=5)
+    assert srel(S.status().resid_norm0, st.beta1) <= RTOL_STEP
+    names = dict(mbeta="beta", oldb="oldb", dbar="dbar", epsln="epsln", phibar="phibar", cs="cs", sn="sn",
+                 tnorm2="tnorm2", ynorm2="ynorm2", rhs1="rhs1", rhs2="rhs2", gmax="gmax", gmin="gmin",
+                 beta1="beta1", xnrg2="xNrgNorm2")
+    for k in range(12):
+        for _ in range(3 if k else 0):
+            kr.minres_step(M, st)
+        S.set_scalar("n_iter", st.itn); S.set_scalar("n_matvec", st.itn)
+        S.set_vector("r2", st.r2); S.set_vector("r1", st.r1 if st.itn else st.r2)
+        S.set_vector("w", st.w); S.set_vector("w2", st.w2); S.set_vector("x", st.x)
+        for dname, oname in names.items():
+            S.set_scalar(dname, float(st[oname]))
+        for j in range(5):
+            S.set_scalar("derr%d" % j, float(st.dErr[j]))
+        kr.minres_step(M, st)
+        S.iterate(1)
+        ds = S.status()
+        assert ds.n_iter == st.itn and ds.istop == st.istop
+        assert srel(S.get_scalar("alfa"), st.alfa) <= RTOL_STEP
+        assert srel(S.get_scalar("mbeta"), st.beta) <= RTOL_STEP
+        for dname in ("phibar", "cs", "sn", "tnorm2", "ynorm2", "rhs1", "gmax", "gmin", "dbar", "epsln"):
+            assert srel(S.get_scalar(dname), float(st[names.get(dname, dname)])) <= 1e-11, dname
+        assert srel(ds.resid_norm, st.rnorm) <= RTOL_STEP
+        assert srel(ds.aux[0], st.Anorm) <= RTOL_STEP and srel(ds.aux[3], st.Arnorm) <= 1e-11
+        for v in ("x", "r2", "r1", "w"):
+            assert rel(S.get_vector(v), st[v]) <= 1e-11, (k, v)
+
+
+# ================================================= trajectories and known answers
+def test_cg_trajectory_poisson2d(ctx, golden):
+    g = 100
+    ip, ix, dv = kr.poisson2d_csr(g)
+    M = CsrRef((g * g, g * g), ip, ix, dv)
+    rhs = M.matvec(np.ones(g * g))
+    ref = kr.cg_solve(M, rhs)
+    A = dev().DeviceCsr.poisson2d(ctx, g)
+    S = dev().DeviceSolver(ctx, "cg", A)
+    S.setup(rhs, matvec_max=2 * g * g)
+    st = S.run(7)
+    hist = S.drain_history(st)[:, 0]
+    rec = golden["cg/poisson2d_csr/100"]
+    assert st.n_matvec == ref.nMatvec == rec["nMatvec"] == 160
+    assert rel(hist[:20], ref.residHistory[:20]) <= RTOL_STEP
+    assert np.max(np.abs(hist - np.array(ref.residHistory)) / np.array(ref.residHistory)) <= 1e-10
+    assert srel(st.resid_norm0, rec["residNorm0"]) <= 1e-14
+    # final residual: true residuals of both solutions agree to 1e-8 (relative to |b|)
+    x = S.solution()
+    nb = np.linalg.norm(rhs)
+    assert abs(np.linalg.norm(rhs - M.matvec(x)) - np.linalg.norm(rhs - M.matvec(ref.x))) / nb <= RTOL_FINAL
+    assert rel(x, ref.x) <= 1e-10
+
+
+def test_public_api_known_answers(ctx, golden):
+    """The reference's own CG tests (pykrylov/cg/tests/test_diagdom.py) through the
+    public classes, on device operators."""
+    from pykrylov_b200.cg import CG
+    from pykrylov_b200.gallery import poisson1d_operator, poisson2d_operator
+    from pykrylov_b200.tools import machine_epsilon
+    from math import sin, pi
+    for n in (10, 20, 100, 1000, 5000):
+        A = poisson1d_operator(n, context=ctx)
+        e = np.ones(n)
+        rhs = A * e
+        cg = CG(A, matvec_max=2 * n, outputStream=None)           # ctor kwargs ignored like the reference
+        cg.solve(rhs)
+        cond = (4.0 * sin((n - 1) * pi / 2.0 / n) ** 2) / (4.0 * sin(pi / 2.0 / n) ** 2)
+        assert cg.nMatvec == n // 2 and cg.converged
+        assert np.allclose(e, cg.bestSolution, rtol=cond * machine_epsilon())
+        assert A.nMatvec == 1 + cg.nMatvec
+    for g, nmv in ((10, 15), (20, 33), (100, 160), (500, 756)):
+        A = poisson2d_operator(g, context=ctx)
+        e = np.ones(g * g)
+        cg = CG(A)
+        cg.solve(A * e)
+        assert cg.nMatvec == nmv and cg.converged
+        if g <= 100:
+            rec = golden["cg/poisson2d_csr/%d" % g]
+            assert srel(cg.residNorm0, rec["residNorm0"]) <= 1e-14
+            assert len(cg.residHistory) == nmv + 1
+            assert rel(cg.residHistory[:25], rec["residHistory"]) <= 1e-11
+        assert np.linalg.norm(e - cg.bestSolution) / g <= 1e-5
+
+
+def test_bmark_through_pysparse_shim(ctx, golden):
+    """examples/bmark.py:34-54, unchanged apart from print()."""
+    from pykrylov.linop import PysparseLinearOperator
+    from pykrylov.cgs import CGS
+    from pykrylov.tfqmr import TFQMR
+    from pykrylov.bicgstab import BiCGSTAB
+    from pysparse import spmatrix
+    from pysparse.sparse.pysparseMatrix import PysparseMatrix as spm
+    AA = spmatrix.ll_mat_from_mtx(mtx("jpwh_991"))
+    A = spm(matrix=AA)
+    op = PysparseLinearOperator(A)
+    n = A.shape[0]
+    e = np.ones(n)
+    rhs = A * e
+    assert np.array_equal(rhs, load_mtx(mtx("jpwh_991")).matvec(e))
+    for KSolver in [CGS, TFQMR, BiCGSTAB]:
+        ks = KSolver(op, reltol=1.0e-8)
+        ks.solve(rhs, guess=1 + np.arange(n, dtype=op.dtype), matvec_max=2 * n)
+        err = np.linalg.norm(ks.bestSolution - e) / np.sqrt(n)
+        rec = golden["%s/jpwh_991/reltol1e-08" % ks.acronym]
+        assert ks.converged and abs(ks.nMatvec - rec["nMatvec"]) <= 4      # doc table: 82/84/84
+        assert srel(ks.residNorm0, rec["residNorm0"]) <= 1e-13
+        assert ks.residNorm <= 1e-8 * ks.residNorm0 and err <= 1e-5
+        assert ks.residHistory == []
+
+
+def test_short_runs_reproduce_doc_tables(ctx, golden):
+    """doc/source/{cgs,bicgstab}.rst:50-52 (reltol 1e-5): identical counts and digits."""
+    from pykrylov_b200.linop import csr_operator
+    from pykrylov_b200.cgs import CGS
+    from pykrylov_b200.bicgstab import BiCGSTAB
+    M = load_mtx(mtx("jpwh_991"))
+    n = M.shape[0]
+    op = csr_operator(M.shape, M.indptr, M.indices, M.data, context=ctx)
+    e = np.ones(n)
+    for K, nmv, res, err in ((CGS, 64, "4.72e-03", "1.47e-04"), (BiCGSTAB, 57, "5.18e-02", "3.35e-03")):
+        ks = K(op, reltol=1.0e-5)
+        ks.solve(M.matvec(e), guess=1 + np.arange(n, dtype=float), matvec_max=2 * n)
+        assert ks.nMatvec == nmv and "%8.2e" % ks.residNorm == res
+        assert "%8.2e" % (np.linalg.norm(ks.bestSolution - e) / np.sqrt(n)) == err
+
+
+def test_minres_public_api(ctx, golden, capsys):
+    from pykrylov_b200.linop import csr_operator
+    from pykrylov_b200.minres import Minres
+    M, rhs = minres_case()
+    op = csr_operator(M.shape, M.indptr, M.indices, M.data, symmetric=True, context=ctx)
+    mr = Minres(op)
+    mr.solve(rhs, show=False)
+    g = golden["MINRES/sym_jpwh_991"]
+    assert mr.istop == 10 and abs(mr.itn - g["itn"]) <= 2 and mr.converged and mr.nMatvec == mr.itn
+    assert srel(mr.residNorm0, g["residNorm0"]) <= 1e-14
+    assert rel(mr.residHistory[:15], g["residHistory"][:15]) <= 1e-9
+    assert srel(mr.Acond, g["Acond"]) <= 1e-6 and np.linalg.norm(mr.x - 1) / np.sqrt(len(rhs)) <= 1e-5
+    assert len(mr.dir_errors_window) == mr.itn - 5
+    # nonsymmetric operator: the default symmetry check stops at 0 iterations, istop 7
+    N = load_mtx(mtx("jpwh_991"))
+    nop = csr_operator(N.shape, N.indptr, N.indices, N.data, context=ctx)
+    mr = Minres(nop)
+    mr.solve(N.matvec(np.ones(N.shape[0])), show=False)
+    g = golden["MINRES/jpwh_991_nonsym"]
+    assert (mr.istop, mr.itn) == (g["istop"], g["itn"]) and not mr.converged
+    mr = Minres(op)
+    mr.solve(rhs)                                                   # show=True prints the banner
+    out = capsys.readouterr().out
+    assert "Enter minres." in out and "istop   =   10" in out
+
+
+# ================================================================ edge cases
+def test_cg_edge_cases(ctx):
+    from pykrylov_b200.linop import csr_operator
+    from pykrylov_b200.cg import CG
+    # zero right-hand side: converged at entry, x = 0, no product
+    ip, ix, dv = kr.poisson2d_csr(5)
+    op = csr_operator((25, 25), ip, ix, dv, symmetric=True, context=ctx)
+    cg = CG(op)
+    cg.solve(np.zeros(25))
+    assert cg.nMatvec == 0 and cg.converged and cg.residNorm == 0.0 and np.array_equal(cg.x, np.zeros(25))
+    assert cg.residHistory == [0.0]
+    # 1 x 1 system
+    one = csr_operator((1, 1), [0, 1], [0], [4.0], symmetric=True, context=ctx)
+    cg = CG(one)
+    cg.solve(np.array([2.0]))
+    assert cg.nMatvec == 1 and np.array_equal(cg.x, [0.5])
+    # matvec_max stops the loop exactly like cg.py:113
+    cg = CG(op)
+    cg.solve(op * np.ones(25), matvec_max=3)
+    assert cg.nMatvec == 3 and not cg.converged and len(cg.residHistory) == 4
+    # indefinite operator: curvature test (cg.py:119-124)
+    ind = csr_operator((2, 2), [0, 1, 2], [0, 1], [1.0, -1.0], symmetric=True, context=ctx)
+    cg = CG(ind)
+    cg.solve(np.array([1.0, 2.0]))
+    ref = kr.cg_solve(CsrRef((2, 2), [0, 1, 2], [0, 1], [1.0, -1.0]), np.array([1.0, 2.0]))
+    assert not cg.definite and not ref.definite and cg.nMatvec == ref.nMatvec
+    assert np.array_equal(cg.infiniteDescent, ref.infiniteDescent) and np.array_equal(cg.x, ref.x)
+    cg = CG(ind)
+    cg.solve(np.array([1.0, 2.0]), check_curvature=False, matvec_max=4)
+    ref = kr.cg_solve(CsrRef((2, 2), [0, 1, 2], [0, 1], [1.0, -1.0]), np.array([1.0, 2.0]),
+                      check_curvature=False, matvec_max=4)
+    assert cg.nMatvec == ref.nMatvec and np.allclose(cg.x, ref.x, rtol=1e-12, equal_nan=True)
+    # check_symmetric on a nonsymmetric operator: logs and returns None without solving
+    N = load_mtx(mtx("jpwh_991"))
+    nop = csr_operator(N.shape, N.indptr, N.indices, N.data, context=ctx)
+    cg = CG(nop)
+    assert cg.solve(np.ones(991), check_symmetric=True) is None and cg.bestSolution is None
+    # wrong-size right-hand side
+    with pytest.raises(ValueError):
+        CG(op).solve(np.ones(24))
+    # store_iterates / store_resids keep per-iteration copies
+    cg = CG(op)
+    cg.solve(op * np.ones(25), store_iterates=True, store_resids=True)
+    assert len(cg.iterates) == cg.nMatvec + 1 and len(cg.resids) == cg.nMatvec + 1
+
+
+def test_cg_jacobi_precon_reproduces_reference_quirk(ctx, golden):
+    """cg.py:104,150-151 build p from r, not from the preconditioned residual; with a
+    Jacobi preconditioner on 1138bus the reference therefore stalls until matvec_max."""
+    from pykrylov_b200.linop import csr_operator, DiagonalOperator
+    from pykrylov_b200.cg import CG
+    M = load_mtx(mtx("1138bus"))
+    op = csr_operator(M.shape, M.indptr, M.indices, M.data, symmetric=True, context=ctx)
+    cg = CG(op, precon=DiagonalOperator(1.0 / M.to_scipy().diagonal()))
+    cg.solve(M.matvec(np.ones(M.shape[0])))
+    rec = golden["cg/1138bus/jacobi"]
+    assert cg.nMatvec == rec["nMatvec"] and cg.converged == rec["converged"]
+    assert srel(cg.residNorm0, rec["residNorm0"]) <= 1e-13
+    assert rel(cg.residHistory[:10], rec["residHistory"][:10]) <= 1e-10
+
+
+def test_bicgstab_breakdown_runs_to_matvec_max_like_reference(ctx):
+    """rhs = A*ones with a zero guess is an exact breakdown on jpwh_991 (rho' = 0):
+    the reference keeps iterating on NaNs until matvec_max; so must the device."""
+    from pykrylov_b200.linop import csr_operator
+    from pykrylov_b200.bicgstab import BiCGSTAB
+    M = load_mtx(mtx("jpwh_991"))
+    n = M.shape[0]
+    op = csr_operator(M.shape, M.indptr, M.indices, M.data, context=ctx)
+    ks = BiCGSTAB(op, reltol=1e-8)
+    ks.solve(M.matvec(np.ones(n)), matvec_max=2 * n)
+    with np.errstate(all="ignore"):
+        ref = kr.bicgstab_solve(M, M.matvec(np.ones(n)), reltol=1e-8, matvec_max=2 * n)
+    if np.isnan(ks.residNorm):
+        assert ks.nMatvec == ref.nMatvec == 2 * n and not ks.converged
+    else:                       # a different summation order may dodge the exact zero
+        assert ks.converged
+
+
+def test_closure_operator_goes_through_host_bridge(ctx):
+    """The reference's own test operator: LinearOperator(n, n, lambda x: Poisson1dMatvec(x))."""
+    from pykrylov_b200.linop import LinearOperator
+    from pykrylov_b200.gallery import Poisson1dMatvec, Poisson2dMatvec
+    from pykrylov_b200.cg import CG
+    n = 100
+    A = LinearOperator(n, n, lambda x: Poisson1dMatvec(x), symmetric=True)
+    e = np.ones(n)
+    cg = CG(A, context=ctx)
+    cg.solve(A * e)
+    assert cg.nMatvec == 50 and np.allclose(cg.bestSolution, e, rtol=1e-10)
+    ref = kr.cg_solve(kr.poisson1d_matvec, kr.poisson1d_matvec(e))
+    assert rel(cg.residHistory[:30], ref.residHistory[:30]) <= 1e-9
+    A2 = LinearOperator(400, 400, lambda x: Poisson2dMatvec(x), symmetric=True)
+    cg = CG(A2, context=ctx)
+    cg.solve(A2 * np.ones(400))
+    assert cg.nMatvec == 33 and cg.converged
+
+
+# ===================================== full-size, size-independent properties
+@pytest.fixture(scope="module")
+def big(ctx):
+    g = 3162                                       # BASELINE.json config 2: N = 9 998 244
+    A = dev().DeviceCsr.poisson2d(ctx, g)
+    return g, A
+
+
+def test_fullsize_row_sums_are_exact(ctx, big):
+    g, A = big
+    n = g * g
+    assert A.shape == (n, n) and A.nnz == 5 * n - 4 * g
+    ones, y = dev().DeviceVector(ctx, n).fill(1.0), dev().DeviceVector(ctx, n)
+    for kind, tile, thr in ((1, 0, 0), (2, 4096, 256), (3, 2048, 256)):
+        A.set_kernel(kind, tile, thr)
+        A.spmv_dot(ones, y, [ones, None], slot0=0)
+        s = ctx.scalars(0, 2)
+        # A*1 is 0 in the interior, 1 on edges, 2 in corners: sums are exact integers
+        assert s[0] == 4.0 * g and s[1] == 4.0 * g + 8.0
+    A.set_kernel(0, 0, 0)
+
+
+def test_fullsize_kernels_agree_bitwise_and_operator_is_symmetric(ctx, big):
+    g, A = big
+    n = g * g
+    rng = np.random.default_rng(9)
+    x, w = ctx.vector(rng.standard_normal(n)), ctx.vector(rng.standard_normal(n))
+    y1, y2, z = (dev().DeviceVector(ctx, n) for _ in range(3))
+    A.set_kernel(1, 0, 0)
+    A.spmv_dot(x, y1, [w], slot0=0)
+    w_Ax = ctx.scalars(0, 1)[0]
+    for kind, tile, thr in ((2, 4096, 256), (3, 2048, 512)):
+        A.set_kernel(kind, tile, thr)
+        A.spmv(x, y2)
+        dev().multi_axpy_dot(ctx, [dict(z=z, u=y1, w=y2, a=1.0, b=-1.0)], [(z, z)], slot0=1)
+        assert ctx.scalars(1, 1)[0] == 0.0                         # bit-identical vectors
+    A.set_kernel(0, 0, 0)
+    A.spmv_dot(w, y2, [x], slot0=2)
+    x_Aw = ctx.scalars(2, 1)[0]
+    assert srel(w_Ax, x_Aw) <= 1e-11                               # symmetry, reduction-order noise only
+    # linearity: A(2x - 3w) == 2Ax - 3Aw up to rounding of the combination
+    dev().multi_axpy_dot(ctx, [dict(z=z, u=x, w=w, a=2.0, b=-3.0)])
+    y3 = dev().DeviceVector(ctx, n)
+    A.spmv(z, y3)
+    dev().multi_axpy_dot(ctx, [dict(z=z, u=y1, w=y2, a=2.0, b=-3.0), dict(z=z, u=z, w=y3, a=1.0, b=-1.0)],
+                         [(z, z), (y3, y3)], slot0=3)
+    s = ctx.scalars(3, 2)
+    assert np.sqrt(s[0] / s[1]) <= 1e-14
+
+
+def test_fullsize_cg_residual_recurrence_is_consistent(ctx, big):
+    g, A = big
+    n = g * g
+    ones = dev().DeviceVector(ctx, n).fill(1.0)
+    rhs = dev().DeviceVector(ctx, n)
+    A.spmv(ones, rhs)
+    S = dev().DeviceSolver(ctx, "cg", A)
+    runs = []
+    for _ in range(2):
+        S.setup_dev(rhs, abstol=0.0, reltol=0.0, matvec_max=60)
+        st = S.run(16)
+        runs.append((st.resid_norm, st.n_matvec, st.n_iter))
+    assert runs[0] == runs[1] and runs[0][1] == 60                 # deterministic, exactly K iterations
+    # recurrence residual r = A x - b versus the explicitly recomputed one
+    x = ctx.vector(S.solution())
+    Ax, r = dev().DeviceVector(ctx, n), ctx.vector(S.get_vector("r"))
+    A.spmv(x, Ax)
+    z = dev().DeviceVector(ctx, n)
+    dev().multi_axpy_dot(ctx, [dict(z=z, u=Ax, w=rhs, a=1.0, b=-1.0), dict(z=z, u=z, w=r, a=1.0, b=-1.0)],
+                         [(z, z), (r, r), (rhs, rhs)], slot0=0)
+    s = ctx.scalars(0, 3)
+    assert np.sqrt(s[0] / s[2]) <= RTOL_FINAL                      # |(Ax-b) - r| / |b|
+    assert srel(np.sqrt(s[1]), runs[0][0]) <= 1e-12

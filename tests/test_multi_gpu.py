@@ -1,0 +1,184 @@
+"""N>1 path.  CPU part: world_size-2 processes over gloo exercise the host-side logic
+(row partition, unique-id rendezvous, and the boundary-set / [local | halo] remap
+algorithm that csrc/comm.cu implements) against the oracle SpMV.  GPU part (marked
+gpu, needs >= 2 devices): the real NCCL path against the oracle."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle import krylov_ref as kr
+from oracle.csr_ref import CsrRef
+from pykrylov_b200.comm import row_partition
+
+
+def test_row_partition():
+    assert row_partition(10, 3) == [(0, 4), (4, 7), (7, 10)]
+    assert row_partition(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]
+    for n, p in ((10 ** 8, 8), (9998244, 4), (7, 7)):
+        b = row_partition(n, p)
+        assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(p - 1))
+        assert max(e - s for s, e in b) - min(e - s for s, e in b) <= 1
+
+
+def halo_plan(indices, lo, hi, ranges, gather):
+    """NumPy statement of kry_csr_shard_finalize (csrc/comm.cu): need list -> boundary
+    sets -> remap to [local | owner*max_send + position]. `gather(obj)` all-gathers."""
+    me = [i for i, r in enumerate(ranges) if r == (lo, hi)][0]
+    need = np.unique(indices[(indices < lo) | (indices >= hi)])
+    all_need = gather(need)
+    send = np.unique(np.concatenate([a[(a >= lo) & (a < hi)] for q, a in enumerate(all_need) if q != me]
+                                    + [np.zeros(0, np.int64)])).astype(np.int64)
+    all_send = gather(send)
+    max_send = max(len(s) for s in all_send)
+    n_local = hi - lo
+    remap = np.empty(len(need), dtype=np.int64)
+    for i, c in enumerate(need):
+        owner = [q for q, (a, b) in enumerate(ranges) if a <= c < b][0]
+        remap[i] = n_local + owner * max_send + np.searchsorted(all_send[owner], c)
+    local = indices.copy().astype(np.int64)
+    inside = (indices >= lo) & (indices < hi)
+    local[inside] -= lo
+    local[~inside] = remap[np.searchsorted(need, indices[~inside])]
+    return local, send - lo, max_send
+
+
+WORKER = textwrap.dedent("""
+    import os, sys, pickle
+    import numpy as np
+    import torch.distributed as dist
+    sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests"))
+    from oracle import krylov_ref as kr
+    from oracle.csr_ref import CsrRef
+    from pykrylov_b200.comm import env_world, row_partition, exchange_unique_id
+    from test_multi_gpu import halo_plan
+
+    rank, world, local = env_world()
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    def gather(obj):
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+
+    # 1. unique-id rendezvous (file based, as used for the NCCL id)
+    uid = exchange_unique_id(rank, world, lambda: bytes(range(128)), tag="pytest_%%s" %% os.environ["MASTER_PORT"])
+    assert uid == bytes(range(128))
+
+    # 2. sharded SpMV == global SpMV, 5-point Laplacian and an irregular matrix
+    for case in ("poisson", "random"):
+        if case == "poisson":
+            g = 13; n = g * g
+            ranges = row_partition(n, world); lo, hi = ranges[rank]
+            ip, ix, dv = kr.poisson2d_csr(g, lo, hi)
+            fip, fix, fdv = kr.poisson2d_csr(g)
+        else:
+            import scipy.sparse as sp
+            n = 97
+            R = sp.random(n, n, density=0.08, random_state=4, format="csr"); R.sort_indices()
+            ranges = row_partition(n, world); lo, hi = ranges[rank]
+            sub = R[lo:hi].tocsr(); sub.sort_indices()
+            ip, ix, dv = sub.indptr, sub.indices, sub.data
+            fip, fix, fdv = R.indptr, R.indices, R.data
+        local_cols, send_idx, max_send = halo_plan(np.asarray(ix, dtype=np.int64), lo, hi, ranges, gather)
+        x = np.random.default_rng(0).standard_normal(n)
+        x_local = x[lo:hi]
+        packed = np.zeros(max_send); packed[:len(send_idx)] = x_local[send_idx]
+        halo = np.concatenate(gather(packed))
+        x_ext = np.concatenate([x_local, halo])
+        y_local = CsrRef((hi - lo, len(x_ext)), ip, local_cols, dv).matvec(x_ext)
+        y_ref = CsrRef((n, n), fip, fix, fdv).matvec(x)[lo:hi]
+        assert np.array_equal(y_local, y_ref), case            # same row order -> bit-exact
+        if case == "poisson":
+            assert max_send == g                               # one grid line per neighbour
+        # 3. all-reduced inner product == global one (to rounding)
+        part = np.array([np.dot(x_local, y_local)])
+        tot = sum(float(p[0]) for p in gather(part))
+        assert abs(tot - np.dot(x, CsrRef((n, n), fip, fix, fdv).matvec(x))) <= 1e-12 * abs(tot)
+    dist.barrier()
+    dist.destroy_process_group()
+    print("rank %%d ok" %% rank)
+""")
+
+
+def test_two_process_sharding_logic_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % dict(root=ROOT))
+    port = 29000 + (os.getpid() % 2000)
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", LOCAL_RANK=str(rank),
+                   MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for rank, (p, out) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, out
+        assert "rank %d ok" % rank in out
+
+
+GPU_WORKER = textwrap.dedent("""
+    import os, sys
+    import numpy as np
+    sys.path.insert(0, %(root)r)
+    from oracle import krylov_ref as kr
+    from oracle.csr_ref import CsrRef
+    from pykrylov_b200.comm import init_from_env, row_partition
+    from pykrylov_b200.device import DeviceCsr, DeviceSolver, DeviceVector
+
+    ctx, rank, world = init_from_env()
+    g = 200; n = g * g
+    lo, hi = row_partition(n, world)[rank]
+    A = DeviceCsr.poisson2d(ctx, g, lo, hi)
+    A.shard_finalize(n, lo)
+    ip, ix, dv = kr.poisson2d_csr(g)
+    M = CsrRef((n, n), ip, ix, dv)
+    x = np.random.default_rng(1).standard_normal(n)
+    # sharded SpMV (+ fused, all-reduced dot) is bit-exact per row: the setup kernel of a
+    # guess-started CG computes r = A x - b through the halo exchange
+    S = DeviceSolver(ctx, "cg", A)
+    rhs = M.matvec(np.ones(n))
+    S.setup(rhs[lo:hi], guess=x[lo:hi], matvec_max=10 ** 6)
+    r_ref = -rhs + M.matvec(x)
+    assert np.array_equal(S.get_vector("r"), r_ref[lo:hi])
+    st0 = S.status()
+    assert abs(st0.resid_norm0 - np.linalg.norm(r_ref)) <= 1e-12 * np.linalg.norm(r_ref)
+    # full solve from a zero guess: same iteration count and history as the 1-process oracle
+    S.setup(rhs[lo:hi], matvec_max=2 * n)
+    st = S.run(16)
+    ref = kr.cg_solve(M, rhs)
+    hist = S.drain_history(st)[:, 0]
+    assert st.n_matvec == ref.nMatvec, (st.n_matvec, ref.nMatvec)
+    k = len(ref.residHistory)
+    assert np.max(np.abs(hist[:k] - np.array(ref.residHistory)) / np.array(ref.residHistory)) <= 1e-9
+    assert np.max(np.abs(S.solution() - ref.x[lo:hi])) <= 1e-9
+    # every rank holds bitwise identical scalars (NCCL all-reduce)
+    vals = ctx.allgather_bytes(np.array([st.resid_norm]).tobytes())
+    assert len(set(vals)) == 1
+    ctx.barrier()
+    print("rank %%d ok nmv=%%d" %% (rank, st.n_matvec))
+""")
+
+
+@pytest.mark.gpu
+def test_two_gpu_sharded_cg_nccl(tmp_path):
+    from pykrylov_b200.device import device_count
+    if device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    script = tmp_path / "gpu_worker.py"
+    script.write_text(GPU_WORKER % dict(root=ROOT))
+    port = 31000 + (os.getpid() % 2000)
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", LOCAL_RANK=str(rank),
+                   MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), TORCHELASTIC_RUN_ID="pytest")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for rank, (p, out) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, out
+        assert "rank %d ok" % rank in out
