@@ -5,6 +5,7 @@ into / out of HBM by libkrylov_b200 (the library never keeps a host pointer).
 """
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -42,10 +43,18 @@ class Context(object):
         call("kry_ctx_create", int(device), C.byref(self._h))
         self.device = int(device)
         self.nranks, self.rank = 1, 0
+        self._children = weakref.WeakSet()     # vectors / operators / solvers living on this context
 
     # -- lifetime
+    def _adopt(self, obj):
+        self._children.add(obj)
+
     def close(self):
+        """Destroy the context after every object that still lives on it."""
         if getattr(self, "_h", None) is not None and self._h.value:
+            order = {"DeviceSolver": 0, "DeviceCsr": 1, "DeviceVector": 2}
+            for obj in sorted(list(self._children), key=lambda o: order.get(type(o).__name__, 3)):
+                obj._release()
             L.lib.kry_ctx_destroy(self._h)
             self._h = L.handle()
 
@@ -141,12 +150,16 @@ class DeviceVector(object):
         self.n = int(n)
         self._h = L.handle()
         call("kry_vec_create", ctx._h, self.n, C.byref(self._h))
+        ctx._adopt(self)
+
+    def _release(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            L.lib.kry_vec_destroy(self._h)
+            self._h = L.handle()
 
     def __del__(self):
         try:
-            if self._h.value:
-                L.lib.kry_vec_destroy(self._h)
-                self._h = L.handle()
+            self._release()
         except Exception:
             pass
 
@@ -184,12 +197,16 @@ class DeviceCsr(object):
         call("kry_csr_shape", self._h, C.byref(nr), C.byref(nc), C.byref(nz))
         self.shape = (nr.value, nc.value)
         self.nnz = nz.value
+        ctx._adopt(self)
+
+    def _release(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            L.lib.kry_csr_destroy(self._h)
+            self._h = L.handle()
 
     def __del__(self):
         try:
-            if self._h.value:
-                L.lib.kry_csr_destroy(self._h)
-                self._h = L.handle()
+            self._release()
         except Exception:
             pass
 
@@ -314,12 +331,16 @@ class DeviceSolver(object):
         self._h = L.handle()
         call("kry_solver_create", ctx._h, METHODS[method], A._h, C.byref(self._h))
         self._hist_read = 0
+        ctx._adopt(self)
+
+    def _release(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            L.lib.kry_solver_destroy(self._h)
+            self._h = L.handle()
 
     def __del__(self):
         try:
-            if self._h.value:
-                L.lib.kry_solver_destroy(self._h)
-                self._h = L.handle()
+            self._release()
         except Exception:
             pass
 

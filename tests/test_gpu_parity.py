@@ -281,10 +281,19 @@ def test_bicgstab_single_step_from_identical_state(ctx, precon):
         if precon:
             S.set_vector("q", p_new / d)
         S.set_scalar("rho", float(st.rho_next))
+        r_scale = np.max(np.abs(st.r))
         kr.bicgstab_step(M, st)
         S.iterate(1)
-        assert np.array_equal(S.get_vector("v"), st.v) and np.array_equal(S.get_vector("t"), st.t)
-        assert srel(S.get_scalar("alpha"), st.alpha) <= RTOL_STEP
+        assert np.array_equal(S.get_vector("v"), st.v)             # SpMV of identical input: bit-exact
+        if st.finished:
+            break
+        alpha_err = srel(S.get_scalar("alpha"), st.alpha)
+        # s = r - alpha v cancels: its relative error is alpha's (a dot product, accurate to
+        # its own conditioning) amplified by |r|/|s|; t = A M s inherits it
+        amp = max(1.0, r_scale / np.max(np.abs(st.s / st.omega)))
+        assert rel(S.get_vector("t"), st.t) <= (RTOL_STEP + 4 * alpha_err) * amp
+        alpha_err = srel(S.get_scalar("alpha"), st.alpha)
+        assert alpha_err <= RTOL_STEP
         assert srel(S.get_scalar("omega"), st.omega) <= RTOL_STEP
         assert srel(S.get_scalar("rho"), st.rho_next) <= 1e-11     # -omega*(r0.t): one cancellation
         assert srel(S.status().resid_norm, st.residNorm) <= RTOL_STEP
@@ -314,6 +323,9 @@ def test_cgs_single_step_from_identical_state(ctx, precon):
         kr.cgs_step(M, st)
         S.iterate(1)
         assert srel(S.get_scalar("alpha"), st.alpha) <= RTOL_STEP
+        if st.finished:                      # beta / u / p are not formed on the last trip
+            assert rel(S.get_vector("x"), st.x) <= 1e-11 and S.status().done
+            break
         assert srel(S.get_scalar("beta"), st.beta) <= 1e-11
         assert srel(S.get_scalar("rho"), st.rho) <= 1e-11
         assert srel(S.status().resid_norm, st.residNorm) <= RTOL_STEP
@@ -345,6 +357,9 @@ def test_tfqmr_single_step_from_identical_state(ctx, precon):
         S.set_scalar("alpha", float(st.rho / np.dot(st.r0, st.v)))
         kr.tfqmr_step(M, st)
         S.iterate(1)
+        if st.finished:
+            assert rel(S.get_vector("x"), st.x) <= 1e-11 and S.status().done
+            break
         assert srel(S.get_scalar("theta"), st.theta) <= RTOL_STEP
         assert srel(S.get_scalar("eta"), st.eta) <= RTOL_STEP
         assert srel(S.get_scalar("rho"), st.rho) <= 1e-11
@@ -371,9 +386,10 @@ def test_minres_single_step_from_identical_state(ctx, shift):
     names = dict(mbeta="beta", oldb="oldb", dbar="dbar", epsln="epsln", phibar="phibar", cs="cs", sn="sn",
                  tnorm2="tnorm2", ynorm2="ynorm2", rhs1="rhs1", rhs2="rhs2", gmax="gmax", gmin="gmin",
                  beta1="beta1", xnrg2="xNrgNorm2")
-    for k in range(12):
+    for k in range(8):
         for _ in range(3 if k else 0):
             kr.minres_step(M, st)
+        assert st.istop == 0
         S.set_scalar("n_iter", st.itn); S.set_scalar("n_matvec", st.itn)
         S.set_vector("r2", st.r2); S.set_vector("r1", st.r1 if st.itn else st.r2)
         S.set_vector("w", st.w); S.set_vector("w2", st.w2); S.set_vector("x", st.x)
