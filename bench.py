@@ -1,0 +1,383 @@
+#!/usr/bin/env python3
+"""bench.py -- the headline benchmark of BASELINE.json on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU arm
+
+A *step* is one pass of the hot path: one CG iteration (fused SpMV+dot, fused
+2xAXPY+dot, AYPX) on the 5-point Laplacian.
+
+  N = 1 : BASELINE.json configs[1] -- CG fp64, 5-pt Poisson, grid 3162^2 (N = 9 998 244).
+  N > 1 : BASELINE.json configs[4] -- the row-sharded 10^8-row operator (grid 10000^2),
+          1-D row blocks, packed-halo ncclAllGather + ncclAllReduce of the scalars
+          (strong scaling: the total problem is fixed for every N >= 2; rank 0 also
+          times the same operator on one GPU so the speed-up is in the same line).
+
+`value` is CG iterations/s with everything resident in HBM (CUDA events, max over
+ranks); `e2e` is the same metric through the public pykrylov-style API
+(CG(op).solve(rhs) with host buffers: H2D of rhs, per-check status reads, D2H of x
+inside the timed region).  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+G_CONFIG2 = 3162          # grid of configs[1]
+G_CONFIG5 = 10000         # grid of configs[4]
+METRIC = "cg_iters_per_s"
+UNIT = "iters/s"
+
+
+def spmv_bytes(n, nnz):
+    """Algorithmic bytes of one CSR SpMV."""
+    return 12 * nnz + 4 * (n + 1) + 16 * n
+
+
+def cg_iter_bytes(n, nnz):
+    return spmv_bytes(n, nnz) + 72 * n
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.QUERY,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.lines:
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(smax)) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------- our arm
+def build_problem(ctx, g, rank, world):
+    """Local rows of the g x g 5-point Laplacian, generated in HBM; rhs = A * ones."""
+    from pykrylov_b200.comm import row_partition
+    from pykrylov_b200.device import DeviceCsr, DeviceVector
+    n = g * g
+    lo, hi = row_partition(n, world)[rank]
+    A = DeviceCsr.poisson2d(ctx, g, lo, hi)
+    if world > 1:
+        A.shard_finalize(n, lo)
+    ones = A.input_vector()
+    ones.fill(1.0)
+    rhs = DeviceVector(ctx, hi - lo)
+    A.spmv(ones, rhs)
+    return A, rhs, n, lo, hi
+
+
+def time_device_resident(ctx, A, rhs, steps, warmup, profile=True):
+    """K iterations, inputs resident, CUDA events on the launching stream."""
+    from pykrylov_b200.device import DeviceSolver
+    S = DeviceSolver(ctx, "cg", A)
+    S.setup_dev(rhs, abstol=0.0, reltol=0.0, matvec_max=10 ** 12)
+    S.iterate(warmup)
+    ctx.sync()
+    if profile:
+        ctx.prof_enable(steps)
+    if ctx.nranks > 1:
+        ctx.barrier()
+    ctx.sync()
+    l0 = ctx.launch_count()
+    ctx.timer_start()
+    S.iterate(steps)
+    ms = ctx.timer_stop()                     # synchronises
+    launches = ctx.launch_count() - l0
+    if ctx.nranks > 1:
+        ctx.barrier()
+        ms = float(ctx.allreduce([ms], op="max")[0])
+    prof = ctx.prof_read() if profile else (0, 0.0)
+    if profile:
+        ctx.prof_enable(0)
+    st = S.status()
+    assert st.n_iter == warmup + steps and not st.done, "timed region did not run exactly K iterations"
+    return ms, launches, prof, S, st
+
+
+def time_e2e(ctx, op, rhs_host, steps, warmup_calls=1):
+    """Public API, host buffers: CG(op).solve(rhs) -- H2D, K iterations with a status
+    read per check interval, D2H of the solution, all inside the timed region."""
+    from pykrylov_b200.cg import CG
+    interval = 25
+    for _ in range(warmup_calls):
+        CG(op, abstol=0.0, reltol=0.0, check_interval=interval).solve(rhs_host, matvec_max=min(steps, 10))
+    ctx.sync()
+    if ctx.nranks > 1:
+        ctx.barrier()
+    t0 = time.perf_counter()
+    cg = CG(op, abstol=0.0, reltol=0.0, check_interval=interval)
+    cg.solve(rhs_host, matvec_max=steps)
+    ctx.sync()
+    dt = time.perf_counter() - t0
+    if ctx.nranks > 1:
+        dt = float(ctx.allreduce([dt], op="max")[0])
+    assert cg.nMatvec == steps
+    n_loc = rhs_host.shape[0]
+    checks = (steps + interval - 1) // interval + 1
+    d2h = 8 * n_loc + checks * 232 + (steps + 1) * 16       # x + status blocks + history
+    return dt, 8 * n_loc / steps, d2h / steps, float(cg.residNorm)
+
+
+def cpu_baseline(g, budget_s=20.0):
+    """The reference's CPU path on the host cores, bounded sample of the same workload."""
+    n = g * g
+    t0 = time.perf_counter()
+    res = run_reference_cg(g, max_steps=10 ** 9, warmup=1, budget_s=budget_s)
+    res["wall_s_including_setup"] = time.perf_counter() - t0
+    res["rows"] = n
+    return res
+
+
+def run_reference_cg(g, max_steps, warmup, budget_s):
+    """CG of the reference (oracle/_ref if present, else the oracle port) on the
+    g x g Laplacian with the scipy-CSR stand-in operator; returns iterations/s."""
+    import scipy.sparse as sp
+    from oracle import krylov_ref as kr
+    n = g * g
+    ip, ix, dv = kr.poisson2d_csr(g)
+    M = sp.csr_matrix((dv, ix, ip), shape=(n, n))
+    rhs = M @ np.ones(n)
+    kind = "port"
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    CG = LinearOperator = None
+    if os.path.isdir(os.path.join(ref_dir, "refpykrylov")):
+        try:
+            sys.path.insert(0, ref_dir)
+            from refpykrylov.cg import CG
+            from refpykrylov.linop import LinearOperator
+            kind = "reference"
+        except Exception:
+            kind = "port"
+    # one calibration iteration to size the sample
+    t0 = time.perf_counter()
+    y = M @ rhs
+    float(np.dot(rhs, y))
+    t_cal = max(time.perf_counter() - t0, 1e-3) * 2.4       # SpMV is ~42% of an iteration
+    steps = int(max(3, min(max_steps, budget_s / t_cal)))
+    if kind == "reference":
+        op = LinearOperator(n, n, lambda v: M @ v, symmetric=True)
+        CG(op, abstol=0.0, reltol=0.0).solve(rhs, matvec_max=warmup)
+        t0 = time.perf_counter()
+        cg = CG(op, abstol=0.0, reltol=0.0)
+        cg.solve(rhs, matvec_max=steps)
+        dt = time.perf_counter() - t0
+        done = cg.nMatvec
+    else:
+        kr.cg_solve(lambda v: M @ v, rhs, abstol=0.0, reltol=0.0, matvec_max=warmup)
+        t0 = time.perf_counter()
+        st = kr.cg_solve(lambda v: M @ v, rhs, abstol=0.0, reltol=0.0, matvec_max=steps)
+        dt = time.perf_counter() - t0
+        done = st.nMatvec
+    try:
+        from threadpoolctl import threadpool_info
+        threads = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        threads = os.cpu_count() or 1
+    return {"value": done / dt, "unit": UNIT, "cores": int(threads), "kind": kind, "steps": int(done),
+            "ms_per_step": 1e3 * dt / done,
+            "sample": "%d CG iterations of pykrylov CG.solve (%s) on the full %dx%d 5-pt Laplacian, "
+                      "scipy-CSR operator; SpMV and AXPYs single-threaded, np.dot on %d OpenBLAS threads "
+                      "(host has %d logical cores)" % (done, kind, g, g, threads, os.cpu_count() or 0)}
+
+
+def load_traffic():
+    """ncu-measured DRAM bytes per launch of the dominant kernel (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "spmv_dot_traffic.json")) as fh:
+            return json.load(fh)
+    except Exception:
+        return None
+
+
+def main_ours(args):
+    from pykrylov_b200.comm import init_from_env
+    from pykrylov_b200.linop import CsrLinearOperator
+    ctx, rank, world = init_from_env()
+    if world != args.gpus and rank == 0:
+        print("warning: --gpus %d but WORLD_SIZE=%d" % (args.gpus, world), file=sys.stderr)
+    g = args.grid or (G_CONFIG2 if world == 1 else G_CONFIG5)
+    A, rhs, n, lo, hi = build_problem(ctx, g, rank, world)
+    nnz_total = 5 * n - 4 * g
+    sampler = ClockSampler(ctx.device)
+    if rank == 0:
+        sampler.start()
+    ms, launches, prof, S, st = time_device_resident(ctx, A, rhs, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    value = args.steps / (ms / 1e3)
+
+    # roofline of the dominant kernel (fused SpMV+dot), from per-launch CUDA events
+    peak, peak_src = measured_peak()
+    n_loc, nnz_loc = hi - lo, A.nnz
+    k1_ms = prof[1] / max(prof[0], 1)
+    achieved = spmv_bytes(n_loc, nnz_loc) / (k1_ms * 1e-3) / 1e9 if prof[0] else None
+    traffic = load_traffic()
+    roofline = {"bound": "hbm", "kernel": "spmv_row_kernel<1,GatherPlain,CgEpiAp,CgFinAp> (fused CSR SpMV + p.Ap)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None,
+                "traffic": (traffic or {}).get("dram_bytes_per_launch") if world == 1 and g == G_CONFIG2 else None,
+                "algorithmic_bytes_per_launch": spmv_bytes(n_loc, nnz_loc),
+                "avg_launch_ms": k1_ms, "launches_timed": prof[0], "peak_source": peak_src,
+                "step_achieved_GBs": cg_iter_bytes(n_loc, nnz_loc) * args.steps / (ms * 1e-3) / 1e9,
+                "kernel_share_of_step": (prof[1] / ms) if prof[0] else None}
+
+    # end to end through the public API with host buffers
+    rhs_host = ctx.pinned_array(n_loc)
+    rhs.download(rhs_host)
+    op = CsrLinearOperator(A)
+    e2e_dt, h2d, d2h, _ = time_e2e(ctx, op, rhs_host, args.steps)
+    e2e = {"value": args.steps / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "api": "pykrylov_b200.cg.CG(op, abstol=0, reltol=0).solve(rhs_host_pinned, matvec_max=K)",
+           "wall_ms": 1e3 * e2e_dt}
+
+    extra = {}
+    if world > 1 and not args.no_single:
+        # same 10^8-row operator on ONE GPU (rank 0), for the speed-up claim
+        ctx.barrier()
+        if rank == 0:
+            from pykrylov_b200.device import Context
+            solo = Context(ctx.device)
+            A1, rhs1, _, _, _ = build_problem(solo, g, 0, 1)
+            ms1, _, _, _, _ = time_device_resident(solo, A1, rhs1, max(10, args.steps // 4), 3, profile=False)
+            one = max(10, args.steps // 4) / (ms1 / 1e3)
+            extra["one_gpu_same_workload"] = {"value": one, "unit": UNIT}
+            extra["speedup_vs_one_gpu"] = value / one
+            solo.close()
+        ctx.barrier()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(g)
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+               "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic",
+               "config": {"workload": ("BASELINE.json configs[1]: CG fp64, 5-pt Poisson Laplacian (gallery), "
+                                       "grid %d^2" % g) if world == 1 else
+                                      ("BASELINE.json configs[4]: CG fp64, row-sharded 5-pt Laplacian grid %d^2, "
+                                       "%d row blocks, packed-halo ncclAllGather + ncclAllReduce(scalars)" % (g, world)),
+                          "rows": n, "nnz": nnz_total, "rows_per_gpu": n_loc,
+                          "operator": "CSR int32/fp64 generated on device (kry_csr_create_poisson2d)",
+                          "rhs": "A*ones", "stopping": "abstol=reltol=0 so exactly K iterations run",
+                          "l2": "inputs larger than L2: %.2f GB touched per iteration per GPU vs 126 MB L2"
+                                % (cg_iter_bytes(n_loc, nnz_loc) / 1e9),
+                          "algorithmic_bytes_per_step_per_gpu": cg_iter_bytes(n_loc, nnz_loc)},
+               "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+               "cpu_baseline": cpu, "resid_norm_after_timed_region": st.resid_norm}
+        out.update(extra)
+        print(json.dumps(out))
+    if world > 1:
+        ctx.barrier()
+
+
+# ---------------------------------------------------------- reference arm
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    g_full = args.grid or (G_CONFIG2 if world == 1 else G_CONFIG5)
+    # bounded sample: the config-2 grid is run in full; the 10^8-row config is sampled on the
+    # 10^7-row grid and scaled by the row ratio (a CG iteration is linear in the rows)
+    g_run = min(g_full, G_CONFIG2)
+    budget = 120.0
+    res = run_reference_cg(g_run, max_steps=args.steps, warmup=min(args.warmup, 2), budget_s=budget)
+    scale = (g_run * g_run) / float(g_full * g_full)
+    value = res["value"] * scale
+    sample = res["sample"]
+    if g_run != g_full:
+        sample += "; scaled by rows %d/%d to the %dx%d workload" % (g_run * g_run, g_full * g_full, g_full, g_full)
+    n = g_full * g_full
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+           "steps": res["steps"], "warmup": min(args.warmup, 2), "ms_per_step": 1e3 / value,
+           "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic",
+           "config": {"workload": ("BASELINE.json configs[1]: CG fp64, 5-pt Poisson Laplacian (gallery), "
+                                   "grid %d^2" % g_full) if world == 1 else
+                                  ("BASELINE.json configs[4]: CG fp64, 5-pt Laplacian grid %d^2" % g_full),
+                      "rows": n, "nnz": 5 * n - 4 * g_full},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": res["cores"], "kind": res["kind"],
+                            "sample": sample},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", type=int, default=0, help="override the Laplacian grid size (debugging)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-single", action="store_true", help="skip the 1-GPU same-workload leg (N>1)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        main_reference(args)
+    else:
+        main_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -66,6 +66,13 @@ int kry_timer_stop(kry_ctx *ctx, double *elapsed_ms); /* synchronises           
 int kry_flush_l2(kry_ctx *ctx);
 /* Number of kernels this library has launched on this context so far.               */
 int kry_launch_count(kry_ctx *ctx, int64_t *count);
+/* Per-kernel device timing of the dominant kernel (the fused SpMV+dot of the solver
+ * loops): when enabled, every such launch is bracketed by a CUDA event pair on the
+ * context's stream (up to max_samples launches; 0 disables).  kry_prof_read
+ * synchronises and returns the number of completed samples and their summed
+ * duration -- this is what bench.py's roofline.achieved is computed from.          */
+int kry_prof_enable(kry_ctx *ctx, int max_samples);
+int kry_prof_read(kry_ctx *ctx, int64_t *samples, double *total_ms);
 
 /* Pinned host staging memory (for the end-to-end H2D/D2H legs). */
 int kry_host_alloc(int64_t bytes, void **out);
@@ -73,6 +80,9 @@ int kry_host_free(void *p);
 
 /* ---------------------------------------------------------------- vectors */
 int kry_vec_create(kry_ctx *ctx, int64_t n, kry_vec **out);
+/* Same with spare capacity behind the n logical entries: the input vector of a
+ * row-sharded operator carries the gathered halo there (kry_csr_shape's ncols). */
+int kry_vec_create_cap(kry_ctx *ctx, int64_t n, int64_t capacity, kry_vec **out);
 int kry_vec_destroy(kry_vec *v);
 int kry_vec_size(const kry_vec *v, int64_t *n);
 int kry_vec_upload(kry_vec *v, const double *host, int64_t n);

@@ -39,7 +39,7 @@ def _diag_precon(precon, n):
 
 def resolve(op, precon, n):
     csr = getattr(op, "device_csr", None)
-    if csr is None or csr.shape != (n, n):
+    if csr is None or csr.shape[0] != n or (not csr.sharded and csr.shape[1] != n):
         return None
     pd = _diag_precon(precon, n)
     if pd is None:

@@ -73,6 +73,9 @@ struct kry_ctx {
     void        *flush_buf;
     size_t       flush_bytes;
     int64_t      launches;
+    // optional per-launch timing of the dominant kernel (kry_prof_*)
+    cudaEvent_t *prof_ev;      // 2 * prof_cap events
+    int          prof_cap, prof_n;
     // multi-GPU
     void        *nccl;         // ncclComm_t
     int          nranks, rank;

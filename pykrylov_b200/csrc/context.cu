@@ -120,6 +120,8 @@ extern "C" int kry_ctx_destroy(kry_ctx *c)
     cudaFree(c->counter);
     cudaFree(c->never_done);
     if (c->flush_buf) cudaFree(c->flush_buf);
+    for (int i = 0; i < 2 * c->prof_cap; ++i) cudaEventDestroy(c->prof_ev[i]);
+    delete[] c->prof_ev;
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);
@@ -197,6 +199,39 @@ extern "C" int kry_launch_count(kry_ctx *c, int64_t *count)
     return KRY_OK;
 }
 
+extern "C" int kry_prof_enable(kry_ctx *c, int max_samples)
+{
+    KRY_REQUIRE(c && max_samples >= 0 && max_samples <= (1 << 20), KRY_ERR_INVALID,
+                "kry_prof_enable: bad argument");
+    KRY_CUDA(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < 2 * c->prof_cap; ++i) cudaEventDestroy(c->prof_ev[i]);
+    delete[] c->prof_ev;
+    c->prof_ev = nullptr;
+    c->prof_cap = c->prof_n = 0;
+    if (max_samples == 0) return KRY_OK;
+    c->prof_ev = new (std::nothrow) cudaEvent_t[2 * (size_t)max_samples];
+    KRY_REQUIRE(c->prof_ev, KRY_ERR_NOMEM, "kry_prof_enable: host allocation failed");
+    for (int i = 0; i < 2 * max_samples; ++i) KRY_CUDA(cudaEventCreate(&c->prof_ev[i]));
+    c->prof_cap = max_samples;
+    return KRY_OK;
+}
+
+extern "C" int kry_prof_read(kry_ctx *c, int64_t *samples, double *total_ms)
+{
+    KRY_REQUIRE(c && samples && total_ms, KRY_ERR_INVALID, "kry_prof_read: NULL argument");
+    KRY_CUDA(cudaStreamSynchronize(c->stream));
+    double tot = 0.0;
+    for (int i = 0; i < c->prof_n; ++i) {
+        float ms = 0.f;
+        KRY_CUDA(cudaEventElapsedTime(&ms, c->prof_ev[2 * i], c->prof_ev[2 * i + 1]));
+        tot += ms;
+    }
+    *samples = c->prof_n;
+    *total_ms = tot;
+    c->prof_n = 0;
+    return KRY_OK;
+}
+
 extern "C" int kry_host_alloc(int64_t bytes, void **out)
 {
     KRY_REQUIRE(out && bytes >= 0, KRY_ERR_INVALID, "kry_host_alloc: bad argument");
@@ -213,16 +248,21 @@ extern "C" int kry_host_free(void *p)
 // ----------------------------------------------------------------- vectors
 extern "C" int kry_vec_create(kry_ctx *c, int64_t n, kry_vec **out)
 {
-    KRY_REQUIRE(c && out && n >= 0, KRY_ERR_INVALID, "kry_vec_create: bad argument");
+    return kry_vec_create_cap(c, n, n, out);
+}
+
+extern "C" int kry_vec_create_cap(kry_ctx *c, int64_t n, int64_t cap, kry_vec **out)
+{
+    KRY_REQUIRE(c && out && n >= 0 && cap >= n, KRY_ERR_INVALID, "kry_vec_create: bad argument");
     *out = nullptr;
     KRY_CUDA(cudaSetDevice(c->device));
     kry_vec *v = new (std::nothrow) kry_vec();
     KRY_REQUIRE(v, KRY_ERR_NOMEM, "kry_vec_create: host allocation failed");
     v->ctx = c;
     v->n = n;
-    v->cap = n;
+    v->cap = cap;
     v->owned = true;
-    int rc = kry_alloc((void **)&v->d, (size_t)(n + 4) * sizeof(double));
+    int rc = kry_alloc((void **)&v->d, (size_t)(cap + 4) * sizeof(double));
     if (rc != KRY_OK) {
         delete v;
         return rc;

@@ -75,6 +75,8 @@ int spmv_launch(kry_csr *M, bool trans, Gather g, Epi epi, Fin fin, const int *d
     ReduceWs ws = kry_ws(c);
     ws.defer = defer;
     const CsrView A = csr_view(*m);
+    const bool prof = ND > 0 && c->prof_ev && c->prof_n < c->prof_cap;
+    if (prof) KRY_CUDA(cudaEventRecord(c->prof_ev[2 * c->prof_n], c->stream));
 
     if (kind == KRY_SPMV_ROW) {
         spmv_row_kernel<ND, Gather, Epi, Fin><<<grid, 256, 0, c->stream>>>(A, g, epi, ws, fin, done);
@@ -86,6 +88,10 @@ int spmv_launch(kry_csr *M, bool trans, Gather g, Epi epi, Fin fin, const int *d
         auto k = spmv_tma_kernel<ND, KRY_TMA_STAGES, Gather, Epi, Fin>;
         KRY_TRY(set_max_smem(k, c, smem));
         k<<<grid, threads, smem, c->stream>>>(A, cap, g, epi, ws, fin, done);
+    }
+    if (prof) {
+        KRY_CUDA(cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], c->stream));
+        c->prof_n++;
     }
     c->launches++;
     KRY_CUDA(cudaGetLastError());

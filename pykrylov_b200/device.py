@@ -90,6 +90,25 @@ class Context(object):
         call("kry_launch_count", self._h, C.byref(n))
         return n.value
 
+    def prof_enable(self, max_samples):
+        call("kry_prof_enable", self._h, int(max_samples))
+
+    def prof_read(self):
+        """(samples, total_ms) of the fused SpMV+dot launches since the last read."""
+        n, ms = C.c_int64(0), C.c_double(0.0)
+        call("kry_prof_read", self._h, C.byref(n), C.byref(ms))
+        return n.value, ms.value
+
+    def pinned_array(self, n):
+        """fp64 NumPy array backed by page-locked host memory (DMA-able staging)."""
+        p = C.c_void_p()
+        call("kry_host_alloc", int(n) * 8, C.byref(p))
+        buf = (C.c_double * int(n)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=np.float64, count=int(n))
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append((p, buf))
+        return arr
+
     def scalars(self, first=0, count=L.KRY_NUM_SLOTS):
         out = (C.c_double * count)()
         call("kry_scalars_read", self._h, first, count, out)
@@ -145,11 +164,12 @@ def default_context():
 class DeviceVector(object):
     """fp64 vector resident in HBM (``kry_vec``)."""
 
-    def __init__(self, ctx, n):
+    def __init__(self, ctx, n, capacity=None):
         self.ctx = ctx
         self.n = int(n)
+        self.capacity = self.n if capacity is None else int(capacity)
         self._h = L.handle()
-        call("kry_vec_create", ctx._h, self.n, C.byref(self._h))
+        call("kry_vec_create_cap", ctx._h, self.n, self.capacity, C.byref(self._h))
         ctx._adopt(self)
 
     def _release(self):
@@ -197,6 +217,8 @@ class DeviceCsr(object):
         call("kry_csr_shape", self._h, C.byref(nr), C.byref(nc), C.byref(nz))
         self.shape = (nr.value, nc.value)
         self.nnz = nz.value
+        self.sharded = False          # set by shard_finalize(): columns address [local | halo]
+        self.n_global = nr.value
         ctx._adopt(self)
 
     def _release(self):
@@ -271,6 +293,16 @@ class DeviceCsr(object):
         nr, nc, nz = C.c_int64(), C.c_int64(), C.c_int64()
         call("kry_csr_shape", self._h, C.byref(nr), C.byref(nc), C.byref(nz))
         self.shape = (nr.value, nc.value)
+        self.sharded = True
+        self.n_global = int(n_global)
+
+    def input_vector(self, init=None):
+        """A vector usable as SpMV input (a shard's input carries the halo tail)."""
+        n = self.shape[0] if self.sharded else self.shape[1]
+        v = DeviceVector(self.ctx, n, capacity=self.shape[1])
+        if init is not None:
+            v.upload(init)
+        return v
 
     # -- products
     def spmv(self, x, y, trans=False):
@@ -285,12 +317,12 @@ class DeviceCsr(object):
 
     def matvec(self, x, trans=False):
         """Host array in, host array out (LinearOperator.__mul__ bridge)."""
-        nin = self.shape[0] if trans else self.shape[1]
+        nin = self.shape[0] if (trans or self.sharded) else self.shape[1]
         nout = self.shape[1] if trans else self.shape[0]
         x = _f64(x)
         if x.shape != (nin,):
             raise ValueError("input array size incompatible with operator dimensions")
-        xv = DeviceVector(self.ctx, nin).upload(x)
+        xv = DeviceVector(self.ctx, nin, capacity=max(nin, self.shape[1])).upload(x)
         yv = DeviceVector(self.ctx, nout)
         self.spmv(xv, yv, trans=trans)
         return yv.download()

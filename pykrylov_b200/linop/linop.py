@@ -407,6 +407,8 @@ class CsrLinearOperator(LinearOperator):
     def __init__(self, device_csr, **kwargs):
         self.device_csr = device_csr
         nrow, ncol = device_csr.shape
+        if getattr(device_csr, "sharded", False):
+            ncol = nrow                       # SPMD view: local slice in, local slice out
         _drop(kwargs, "symmetric", "matvec", "matvec_transp", "dtype")
 
         def matvec(x):
