@@ -132,6 +132,8 @@ int kry_csr_create_convdiff3d(kry_ctx *ctx, int64_t m, double gamma,
 #define KRY_SPMV_ROW     1   /* one thread per row, direct global loads              */
 #define KRY_SPMV_STREAM  2   /* coalesced nnz stream staged in smem, row-sum pass    */
 #define KRY_SPMV_TMA     3   /* persistent CTAs, cp.async.bulk (TMA) multi-stage     */
+#define KRY_SPMV_ROWB8   4   /* one thread per row, loads batched 8 entries at a time */
+#define KRY_SPMV_ROWB4   5   /* one thread per row, loads batched 4 entries at a time */
 int kry_csr_set_kernel(kry_csr *A, int kind, int tile_nnz, int threads);
 
 /* ------------------------------------------------------- hot-path kernels */

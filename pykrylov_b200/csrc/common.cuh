@@ -215,7 +215,7 @@ __global__ void finalize_kernel(Fin fin, const double *sums, const int *done)
 
 // Generic fused vector pass: body(i, acc) over all elements + reduction + finalize.
 template <int ND, class Body, class Fin>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)      // <= 40 registers; the grid is sized to one resident wave
 vec_pass_kernel(int64_t n, Body body, ReduceWs ws, Fin fin, const int *done)
 {
     static_assert(ND >= 1 && ND <= KRY_MAX_DOTS, "1..KRY_MAX_DOTS fused inner products");
@@ -224,21 +224,22 @@ vec_pass_kernel(int64_t n, Body body, ReduceWs ws, Fin fin, const int *done)
     double acc[ND];
 #pragma unroll
     for (int d = 0; d < ND; ++d) acc[d] = 0.0;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    // n < 2^31 - 2^20 (check_sizes) and stride < 2^20: 32-bit indices cannot overflow
+    const int stride = (int)(gridDim.x * blockDim.x), nn = (int)n;
+    for (int i = (int)(blockIdx.x * blockDim.x + threadIdx.x); i < nn; i += stride)
         body(i, acc);
     block_reduce_finalize<ND>(acc, ws, fin);
 }
 
 // Same without inner products (pure element-wise update).
 template <class Body>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 vec_map_kernel(int64_t n, Body body, const int *done)
 {
     if (*done) return;
     body.init();
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    const int stride = (int)(gridDim.x * blockDim.x), nn = (int)n;
+    for (int i = (int)(blockIdx.x * blockDim.x + threadIdx.x); i < nn; i += stride)
         body(i);
 }
 

@@ -119,7 +119,7 @@ struct MultiAxpyBody {
             if (op[k].b_slot >= 0) op[k].b = op[k].b_neg ? -slots[op[k].b_slot] : slots[op[k].b_slot];
         }
     }
-    __device__ void update(int64_t i) const
+    __device__ void update(int i) const
     {
         for (int k = 0; k < n_ops; ++k) {
             const AxpbyDev &o = op[k];
@@ -135,13 +135,13 @@ struct MultiAxpyBody {
             o.z[i] = r;
         }
     }
-    __device__ void operator()(int64_t i, double *acc) const
+    __device__ void operator()(int i, double *acc) const
     {
         update(i);
 #pragma unroll
         for (int d = 0; d < ND; ++d) acc[d] = __dadd_rn(acc[d], __dmul_rn(du[d][i], dw[d][i]));
     }
-    __device__ void operator()(int64_t i) const { update(i); }
+    __device__ void operator()(int i) const { update(i); }
 };
 
 template <int ND>

@@ -47,7 +47,7 @@ struct CgFinAp {
 };
 
 // precon_mode: 0 none, 1 y = d .* r (DiagonalOperator), 2 y = r ./ d (bmark.py DiagonalPrec)
-__device__ __forceinline__ double apply_diag(const double *d, int mode, int64_t i, double r)
+__device__ __forceinline__ double apply_diag(const double *d, int mode, int i, double r)
 {
     if (mode == 1) return __dmul_rn(d[i], r);
     if (mode == 2) return __ddiv_rn(r, d[i]);
@@ -61,7 +61,7 @@ struct CgUpdateBody {
     DevScalars   *s;
     double        alpha;
     __device__ void init() { alpha = s->s[S_ALPHA]; }
-    __device__ void operator()(int64_t i, double *acc) const
+    __device__ void operator()(int i, double *acc) const
     {
         x[i] = __dadd_rn(x[i], __dmul_rn(alpha, p[i]));              // cg.py:130
         const double rn = __dadd_rn(r[i], __dmul_rn(alpha, Ap[i]));  // cg.py:131
@@ -93,7 +93,7 @@ struct CgDirBody {
     DevScalars   *s;
     double        beta;
     __device__ void init() { beta = s->s[S_BETA]; }
-    __device__ void operator()(int64_t i) const
+    __device__ void operator()(int i) const
     {
         p[i] = __dsub_rn(__dmul_rn(beta, p[i]), r[i]);               // cg.py:150-151
     }
@@ -120,7 +120,7 @@ struct CgSetupBody {              // zero initial guess
     const double *rhs, *pd;
     int           pmode;
     __device__ void init() {}
-    __device__ void operator()(int64_t i, double *acc) const
+    __device__ void operator()(int i, double *acc) const
     {
         const double rn = -rhs[i];
         r[i] = rn;
@@ -207,7 +207,7 @@ struct BcgBodyS {
     DevScalars   *s;
     double        alpha;
     __device__ void init() { alpha = s->s[S_ALPHA]; }
-    __device__ void operator()(int64_t i, double *acc) const
+    __device__ void operator()(int i, double *acc) const
     {
         const double si = __dsub_rn(r[i], __dmul_rn(alpha, v[i]));   // :104
         sv[i] = si;
@@ -278,7 +278,7 @@ struct BcgBodyX {
         bo = __dmul_rn(beta, omega);
         half = s->skip_half;
     }
-    __device__ void operator()(int64_t i, double *acc) const
+    __device__ void operator()(int i, double *acc) const
     {
         const double qi = pmode ? q[i] : p[i];
         if (half) {
@@ -340,7 +340,7 @@ struct R0SetupBody {     // zero guess: r0 = rhs
     double       *r0, *a, *b;
     const double *rhs;
     __device__ void init() {}
-    __device__ void operator()(int64_t i, double *acc) const
+    __device__ void operator()(int i, double *acc) const
     {
         const double v = rhs[i];
         r0[i] = v;
@@ -379,7 +379,7 @@ struct DiagApplyBody {   // q = M p
     const double *p, *pd;
     int           pmode;
     __device__ void init() {}
-    __device__ void operator()(int64_t i) const { q[i] = apply_diag(pd, pmode, i, p[i]); }
+    __device__ void operator()(int i) const { q[i] = apply_diag(pd, pmode, i, p[i]); }
 };
 
 static int bicgstab_setup(kry_solver *S, int guess)
@@ -456,7 +456,7 @@ struct CgsBodyQ {
     DevScalars   *s;
     double        alpha;
     __device__ void init() { alpha = s->s[S_ALPHA]; }
-    __device__ void operator()(int64_t i) const
+    __device__ void operator()(int i) const
     {
         const double qi = __dsub_rn(u[i], __dmul_rn(alpha, v[i]));           // :87
         q[i] = qi;
@@ -508,7 +508,7 @@ struct CgsBodyP {
     DevScalars   *s;
     double        beta;
     __device__ void init() { beta = s->s[S_BETA]; }
-    __device__ void operator()(int64_t i) const
+    __device__ void operator()(int i) const
     {
         const double ui = __dadd_rn(r[i], __dmul_rn(beta, q[i]));            // :109
         u[i] = ui;
@@ -592,7 +592,7 @@ struct TfqBodyW {             // w -= alpha u ; |w|^2
     DevScalars   *s;
     double        alpha;
     __device__ void init() { alpha = s->s[S_ALPHA]; }
-    __device__ void operator()(int64_t i, double *acc) const
+    __device__ void operator()(int i, double *acc) const
     {
         const double wi = __dsub_rn(w[i], __dmul_rn(alpha, u[i]));           // :92 / :116
         w[i] = wi;
@@ -640,7 +640,7 @@ struct TfqBodyD1 {            // d = coef d + z ; x += eta d ; then (if continui
         alpha = s->s[S_ALPHA];
         stop = s->skip_half;
     }
-    __device__ void operator()(int64_t i, double *acc) const
+    __device__ void operator()(int i, double *acc) const
     {
         const double zi = pmode ? z[i] : y[i];
         const double di = __dadd_rn(__dmul_rn(d[i], coef), zi);              // :93-94
@@ -702,7 +702,7 @@ struct TfqBodyD2 {            // d = coef d + z ; x += eta d ; rho' = r0.w
         coef = s->s[S_DCOEF];
         eta = s->s[S_ETA];
     }
-    __device__ void operator()(int64_t i, double *acc) const
+    __device__ void operator()(int i, double *acc) const
     {
         const double zi = pmode ? z[i] : y[i];
         const double di = __dadd_rn(__dmul_rn(d[i], coef), zi);              // :117-118
@@ -734,7 +734,7 @@ struct TfqBodyYV {            // y = beta y + w ; v = beta (beta v + u) ; z = M 
     DevScalars   *s;
     double        beta;
     __device__ void init() { beta = s->s[S_BETA]; }
-    __device__ void operator()(int64_t i) const
+    __device__ void operator()(int i) const
     {
         const double yi = __dadd_rn(__dmul_rn(y[i], beta), w[i]);            // :133-134
         y[i] = yi;
@@ -898,7 +898,7 @@ struct MinBodyR2 {            // y = (-alfa/beta) r2 + y' ; beta'^2 = r2new . (M
     DevScalars   *s;
     double        c;
     __device__ void init() { c = s->s[M_C_R2]; }
-    __device__ void operator()(int64_t i, double *acc) const
+    __device__ void operator()(int i, double *acc) const
     {
         const double yi = __dadd_rn(__dmul_rn(c, r2[i]), yn[i]);             // :246
         yn[i] = yi;                                                          // :248 (new r2)
@@ -1018,7 +1018,7 @@ struct MinBodyW {             // w = (v - oldeps w1 - delta w2) * denom ; x += p
         denom = s->s[M_DENOM];
         phi = s->s[M_PHI];
     }
-    __device__ void operator()(int64_t i, double *acc) const
+    __device__ void operator()(int i, double *acc) const
     {
         const double vi = __dmul_rn(inv, yold[i]);                           // :237
         double wi = __dsub_rn(vi, __dmul_rn(oldeps, wnew[i]));               // :296 (wnew holds w1)
@@ -1045,7 +1045,7 @@ struct MinSetupBody {         // y = M b ; beta1^2 = b.y   (minres.py:160-166)
     const double *b, *pd;
     int           pmode;
     __device__ void init() {}
-    __device__ void operator()(int64_t i, double *acc) const
+    __device__ void operator()(int i, double *acc) const
     {
         const double yi = apply_diag(pd, pmode, i, b[i]);
         y[i] = yi;

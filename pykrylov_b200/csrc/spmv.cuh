@@ -83,6 +83,46 @@ spmv_row_kernel(CsrView A, Gather g, Epi epi, ReduceWs ws, Fin fin, const int *d
     if constexpr (ND > 0) block_reduce_finalize<ND>(acc, ws, fin);
 }
 
+// -------------------------------------------- thread per row, batched loads
+// Same mapping as spmv_row_kernel, but the loads of a row are issued in three
+// waves of independent requests -- all (col,val) pairs of a CHUNK, then all x
+// gathers, then the (sequential, order-preserving) sum -- instead of one
+// dependent col -> x chain per entry.  More bytes in flight per warp for a
+// latency-bound kernel, at the price of registers.
+template <int ND, int CHUNK, class Gather, class Epi, class Fin>
+__global__ void __launch_bounds__(256)
+spmv_rowb_kernel(CsrView A, Gather g, Epi epi, ReduceWs ws, Fin fin, const int *done)
+{
+    if (*done) return;
+    g.init();
+    epi.init();
+    double acc[ND > 0 ? ND : 1];
+#pragma unroll
+    for (int d = 0; d < (ND > 0 ? ND : 1); ++d) acc[d] = 0.0;
+    const int stride = gridDim.x * blockDim.x;
+    for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < A.nrows; row += stride) {
+        const int s = __ldg(A.rowptr + row), e = __ldg(A.rowptr + row + 1);
+        double sum = 0.0;
+        for (int k = s; k < e; k += CHUNK) {
+            int    c[CHUNK];
+            double v[CHUNK], xv[CHUNK];
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j) {
+                const bool on = k + j < e;
+                c[j] = on ? __ldg(A.col + k + j) : 0;
+                v[j] = on ? __ldg(A.val + k + j) : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j) xv[j] = (k + j < e) ? g(c[j]) : 0.0;
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j)
+                if (k + j < e) sum = __dadd_rn(sum, __dmul_rn(v[j], xv[j]));
+        }
+        epi(row, sum, acc);
+    }
+    if constexpr (ND > 0) block_reduce_finalize<ND>(acc, ws, fin);
+}
+
 // ------------------------------------------------------- coalesced nnz stream
 // Dynamic smem: (tile_nnz + max_row) doubles of staged products.
 template <int ND, class Gather, class Epi, class Fin>

@@ -290,15 +290,16 @@ def test_bicgstab_single_step_from_identical_state(ctx, precon):
         alpha_err = srel(S.get_scalar("alpha"), st.alpha)
         # s = r - alpha v cancels: its relative error is alpha's (a dot product, accurate to
         # its own conditioning) amplified by |r|/|s|; t = A M s inherits it
-        amp = max(1.0, r_scale / np.max(np.abs(st.s / st.omega)))
-        assert rel(S.get_vector("t"), st.t) <= (RTOL_STEP + 4 * alpha_err) * amp
-        alpha_err = srel(S.get_scalar("alpha"), st.alpha)
+        s_vec = st.s if precon else st.s / st.omega                # (z *= omega aliases s, :135)
+        amp = max(1.0, r_scale / np.max(np.abs(s_vec)))
+        tol = (RTOL_STEP + 4 * alpha_err) * amp
         assert alpha_err <= RTOL_STEP
-        assert srel(S.get_scalar("omega"), st.omega) <= RTOL_STEP
-        assert srel(S.get_scalar("rho"), st.rho_next) <= 1e-11     # -omega*(r0.t): one cancellation
-        assert srel(S.status().resid_norm, st.residNorm) <= RTOL_STEP
-        for v in ("x", "r"):
-            assert rel(S.get_vector(v), st[v]) <= RTOL_STEP, (k, v)
+        assert rel(S.get_vector("t"), st.t) <= tol
+        assert srel(S.get_scalar("omega"), st.omega) <= tol
+        assert srel(S.get_scalar("rho"), st.rho_next) <= 10 * tol  # -omega*(r0.t): one more cancellation
+        assert srel(S.status().resid_norm, st.residNorm) <= tol
+        assert rel(S.get_vector("x"), st.x) <= RTOL_STEP           # x is not formed by cancellation
+        assert rel(S.get_vector("r"), st.r) / max(1.0, np.max(np.abs(s_vec)) / np.max(np.abs(st.r))) <= tol, k
 
 
 @pytest.mark.parametrize("precon", [0, 2])
