@@ -17,6 +17,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <type_traits>
+
 #include "../../include/krylov_b200.h"
 
 // ---------------------------------------------------------------- errors
@@ -191,6 +193,22 @@ __device__ __forceinline__ void block_reduce_finalize(double (&acc)[ND], const R
     }
 }
 
+// Bodies that also provide pair(i2[, acc]) -- elements 2*i2 and 2*i2+1 through one
+// 16-byte access per vector -- are run in that form by the vector kernels.
+template <class B, class = void>
+struct has_pair : std::false_type {};
+template <class B>
+struct has_pair<B, std::void_t<decltype(B::kPair)>> : std::true_type {};
+
+__device__ __forceinline__ double2 ld2(const double *p, int i2)
+{
+    return reinterpret_cast<const double2 *>(p)[i2];
+}
+__device__ __forceinline__ void st2(double *p, int i2, double2 v)
+{
+    reinterpret_cast<double2 *>(p)[i2] = v;
+}
+
 struct NoFin {
     __device__ void operator()(const double *) const {}
 };
@@ -226,8 +244,15 @@ vec_pass_kernel(int64_t n, Body body, ReduceWs ws, Fin fin, const int *done)
     for (int d = 0; d < ND; ++d) acc[d] = 0.0;
     // n < 2^31 - 2^20 (check_sizes) and stride < 2^20: 32-bit indices cannot overflow
     const int stride = (int)(gridDim.x * blockDim.x), nn = (int)n;
-    for (int i = (int)(blockIdx.x * blockDim.x + threadIdx.x); i < nn; i += stride)
-        body(i, acc);
+    const int t0 = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if constexpr (has_pair<Body>::value) {
+        // 16-byte (double2) accesses: two consecutive elements per thread per trip
+        const int half = nn >> 1;
+        for (int i = t0; i < half; i += stride) body.pair(i, acc);
+        if ((nn & 1) && t0 == 0) body(nn - 1, acc);
+    } else {
+        for (int i = t0; i < nn; i += stride) body(i, acc);
+    }
     block_reduce_finalize<ND>(acc, ws, fin);
 }
 
@@ -239,8 +264,14 @@ vec_map_kernel(int64_t n, Body body, const int *done)
     if (*done) return;
     body.init();
     const int stride = (int)(gridDim.x * blockDim.x), nn = (int)n;
-    for (int i = (int)(blockIdx.x * blockDim.x + threadIdx.x); i < nn; i += stride)
-        body(i);
+    const int t0 = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if constexpr (has_pair<Body>::value) {
+        const int half = nn >> 1;
+        for (int i = t0; i < half; i += stride) body.pair(i);
+        if ((nn & 1) && t0 == 0) body(nn - 1);
+    } else {
+        for (int i = t0; i < nn; i += stride) body(i);
+    }
 }
 
 #endif  // __CUDACC__

@@ -112,27 +112,35 @@ struct MultiAxpyBody {
     int           n_ops;
     const double *du[ND > 0 ? ND : 1], *dw[ND > 0 ? ND : 1];
     const double *slots;
+    double        ca[4], cb[4];      // resolved coefficients (registers: all loops are unrolled)
     __device__ void init()
     {
-        for (int k = 0; k < n_ops; ++k) {
-            if (op[k].a_slot >= 0) op[k].a = op[k].a_neg ? -slots[op[k].a_slot] : slots[op[k].a_slot];
-            if (op[k].b_slot >= 0) op[k].b = op[k].b_neg ? -slots[op[k].b_slot] : slots[op[k].b_slot];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            ca[k] = op[k].a;
+            cb[k] = op[k].b;
+            if (k < n_ops) {
+                if (op[k].a_slot >= 0) ca[k] = op[k].a_neg ? -slots[op[k].a_slot] : slots[op[k].a_slot];
+                if (op[k].b_slot >= 0) cb[k] = op[k].b_neg ? -slots[op[k].b_slot] : slots[op[k].b_slot];
+            }
         }
     }
     __device__ void update(int i) const
     {
-        for (int k = 0; k < n_ops; ++k) {
-            const AxpbyDev &o = op[k];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k >= n_ops) break;
+            const double *u = op[k].u, *w = op[k].w;
             double r;
-            if (o.u && o.w)
-                r = __dadd_rn(__dmul_rn(o.a, o.u[i]), __dmul_rn(o.b, o.w[i]));
-            else if (o.u)
-                r = __dmul_rn(o.a, o.u[i]);
-            else if (o.w)
-                r = __dmul_rn(o.b, o.w[i]);
+            if (u && w)
+                r = __dadd_rn(__dmul_rn(ca[k], u[i]), __dmul_rn(cb[k], w[i]));
+            else if (u)
+                r = __dmul_rn(ca[k], u[i]);
+            else if (w)
+                r = __dmul_rn(cb[k], w[i]);
             else
                 r = 0.0;
-            o.z[i] = r;
+            op[k].z[i] = r;
         }
     }
     __device__ void operator()(int i, double *acc) const

@@ -69,6 +69,21 @@ struct CgUpdateBody {
         const double y = apply_diag(pd, pmode, i, rn);               // cg.py:137-140
         acc[0] = __dadd_rn(acc[0], __dmul_rn(rn, y));                // cg.py:146
     }
+    static constexpr bool kPair = true;
+    __device__ void pair(int i2, double *acc) const
+    {
+        double2 xv = ld2(x, i2), rv = ld2(r, i2);
+        const double2 pv = ld2(p, i2), av = ld2(Ap, i2);
+        xv.x = __dadd_rn(xv.x, __dmul_rn(alpha, pv.x));
+        xv.y = __dadd_rn(xv.y, __dmul_rn(alpha, pv.y));
+        rv.x = __dadd_rn(rv.x, __dmul_rn(alpha, av.x));
+        rv.y = __dadd_rn(rv.y, __dmul_rn(alpha, av.y));
+        st2(x, i2, xv);
+        st2(r, i2, rv);
+        const double y0 = apply_diag(pd, pmode, 2 * i2, rv.x), y1 = apply_diag(pd, pmode, 2 * i2 + 1, rv.y);
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(rv.x, y0));
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(rv.y, y1));
+    }
 };
 
 struct CgFinRy {
@@ -96,6 +111,15 @@ struct CgDirBody {
     __device__ void operator()(int i) const
     {
         p[i] = __dsub_rn(__dmul_rn(beta, p[i]), r[i]);               // cg.py:150-151
+    }
+    static constexpr bool kPair = true;
+    __device__ void pair(int i2) const
+    {
+        double2 pv = ld2(p, i2);
+        const double2 rv = ld2(r, i2);
+        pv.x = __dsub_rn(__dmul_rn(beta, pv.x), rv.x);
+        pv.y = __dsub_rn(__dmul_rn(beta, pv.y), rv.y);
+        st2(p, i2, pv);
     }
 };
 
