@@ -74,6 +74,10 @@ int kry_launch_count(kry_ctx *ctx, int64_t *count);
 int kry_prof_enable(kry_ctx *ctx, int max_samples);
 int kry_prof_read(kry_ctx *ctx, int64_t *samples, double *total_ms);
 
+/* Engine options (A/B switches for measurement). */
+#define KRY_OPT_L2_HINTS 1   /* L2 eviction-priority hints in the CG kernels (default 1) */
+int kry_ctx_set_option(kry_ctx *ctx, int option, int value);
+
 /* Pinned host staging memory (for the end-to-end H2D/D2H legs). */
 int kry_host_alloc(int64_t bytes, void **out);
 int kry_host_free(void *p);

@@ -75,6 +75,7 @@ struct kry_ctx {
     void        *flush_buf;
     size_t       flush_bytes;
     int64_t      launches;
+    int          l2_hints;     // 1: CG kernels use L2 eviction-priority hints (default)
     // optional per-launch timing of the dominant kernel (kry_prof_*)
     cudaEvent_t *prof_ev;      // 2 * prof_cap events
     int          prof_cap, prof_n;
@@ -207,6 +208,54 @@ __device__ __forceinline__ double2 ld2(const double *p, int i2)
 __device__ __forceinline__ void st2(double *p, int i2, double2 v)
 {
     reinterpret_cast<double2 *>(p)[i2] = v;
+}
+
+// L2 eviction-priority hints (createpolicy + ld/st .L2::cache_hint).  The three CG
+// launches hand 80 MB vectors to each other (Ap: K1->K2, r: K2->K3, p: K3->K1); marking
+// the producer's stores evict_last and the pure streams (CSR arrays, x) evict_first lets
+// part of that traffic be served from the 126 MB L2 instead of HBM.
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ double ldnc_hint(const double *a, uint64_t pol)
+{
+    double d;
+    asm("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(d) : "l"(a), "l"(pol));
+    return d;
+}
+__device__ __forceinline__ int ldnc_hint(const int *a, uint64_t pol)
+{
+    int d;
+    asm("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(d) : "l"(a), "l"(pol));
+    return d;
+}
+__device__ __forceinline__ double2 ld2_hint(const double *a, int i2, uint64_t pol)
+{
+    double2 d;
+    asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;"
+                 : "=d"(d.x), "=d"(d.y)
+                 : "l"(reinterpret_cast<const double2 *>(a) + i2), "l"(pol));
+    return d;
+}
+__device__ __forceinline__ void st2_hint(double *a, int i2, double2 v, uint64_t pol)
+{
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(
+                     reinterpret_cast<double2 *>(a) + i2),
+                 "d"(v.x), "d"(v.y), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void st_hint(double *a, double v, uint64_t pol)
+{
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(a), "d"(v), "l"(pol) : "memory");
 }
 
 struct NoFin {

@@ -66,6 +66,7 @@ extern "C" int kry_ctx_create(int device, kry_ctx **out)
     c->l2_bytes = prop.l2CacheSize;
     c->smem_optin = (int64_t)prop.sharedMemPerBlockOptin;
     c->nranks = 1;
+    c->l2_hints = 1;
     KRY_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     KRY_CUDA(cudaEventCreate(&c->ev0));
     KRY_CUDA(cudaEventCreate(&c->ev1));
@@ -196,6 +197,14 @@ extern "C" int kry_launch_count(kry_ctx *c, int64_t *count)
 {
     KRY_REQUIRE(c && count, KRY_ERR_INVALID, "kry_launch_count: NULL argument");
     *count = c->launches;
+    return KRY_OK;
+}
+
+extern "C" int kry_ctx_set_option(kry_ctx *c, int option, int value)
+{
+    KRY_REQUIRE(c, KRY_ERR_INVALID, "kry_ctx_set_option: NULL context");
+    KRY_REQUIRE(option == KRY_OPT_L2_HINTS, KRY_ERR_INVALID, "kry_ctx_set_option: unknown option %d", option);
+    c->l2_hints = value;
     return KRY_OK;
 }
 

@@ -89,7 +89,8 @@ int spmv_launch(kry_csr *M, bool trans, Gather g, Epi epi, Fin fin, const int *d
     KRY_TRY(kry_ctx_ensure_partials(c, grid));
     ReduceWs ws = kry_ws(c);
     ws.defer = defer;
-    const CsrView A = csr_view(*m);
+    CsrView A = csr_view(*m);
+    A.hints = (c->l2_hints & 2) ? 1 : 0;     // bit 1: evict_first on the CSR streams (measured harmful)
     const bool prof = ND > 0 && c->prof_ev && c->prof_n < c->prof_cap;
     if (prof) KRY_CUDA(cudaEventRecord(c->prof_ev[2 * c->prof_n], c->stream));
 

@@ -22,10 +22,13 @@
 struct CgEpiAp {
     double       *Ap;
     const double *p;
-    __device__ void init() {}
+    int           hints;
+    uint64_t      el;
+    __device__ void init() { el = l2_policy_evict_last(); }
     __device__ void operator()(int row, double ax, double *acc) const
     {
-        Ap[row] = ax;
+        if (hints) st_hint(Ap + row, ax, el);                        // K2 reads it next: keep in L2
+        else Ap[row] = ax;
         acc[0] = __dadd_rn(acc[0], __dmul_rn(p[row], ax));          // cg.py:117
     }
 };
@@ -60,7 +63,14 @@ struct CgUpdateBody {
     int           pmode;
     DevScalars   *s;
     double        alpha;
-    __device__ void init() { alpha = s->s[S_ALPHA]; }
+    int           hints;
+    uint64_t      ef, el;
+    __device__ void init()
+    {
+        alpha = s->s[S_ALPHA];
+        ef = l2_policy_evict_first();
+        el = l2_policy_evict_last();
+    }
     __device__ void operator()(int i, double *acc) const
     {
         x[i] = __dadd_rn(x[i], __dmul_rn(alpha, p[i]));              // cg.py:130
@@ -72,14 +82,26 @@ struct CgUpdateBody {
     static constexpr bool kPair = true;
     __device__ void pair(int i2, double *acc) const
     {
-        double2 xv = ld2(x, i2), rv = ld2(r, i2);
-        const double2 pv = ld2(p, i2), av = ld2(Ap, i2);
+        double2 xv, rv, pv, av;
+        if (hints) {
+            // x, r(old), Ap are dead after this pass: evict_first; p is re-read by K3
+            xv = ld2_hint(x, i2, ef); rv = ld2_hint(r, i2, ef);
+            pv = ld2_hint(p, i2, el); av = ld2_hint(Ap, i2, ef);
+        } else {
+            xv = ld2(x, i2); rv = ld2(r, i2);
+            pv = ld2(p, i2); av = ld2(Ap, i2);
+        }
         xv.x = __dadd_rn(xv.x, __dmul_rn(alpha, pv.x));
         xv.y = __dadd_rn(xv.y, __dmul_rn(alpha, pv.y));
         rv.x = __dadd_rn(rv.x, __dmul_rn(alpha, av.x));
         rv.y = __dadd_rn(rv.y, __dmul_rn(alpha, av.y));
-        st2(x, i2, xv);
-        st2(r, i2, rv);
+        if (hints) {
+            st2_hint(x, i2, xv, ef);
+            st2_hint(r, i2, rv, el);                                 // K3 reads r next
+        } else {
+            st2(x, i2, xv);
+            st2(r, i2, rv);
+        }
         const double y0 = apply_diag(pd, pmode, 2 * i2, rv.x), y1 = apply_diag(pd, pmode, 2 * i2 + 1, rv.y);
         acc[0] = __dadd_rn(acc[0], __dmul_rn(rv.x, y0));
         acc[0] = __dadd_rn(acc[0], __dmul_rn(rv.y, y1));
@@ -107,7 +129,14 @@ struct CgDirBody {
     const double *r;
     DevScalars   *s;
     double        beta;
-    __device__ void init() { beta = s->s[S_BETA]; }
+    int           hints;
+    uint64_t      ef, el;
+    __device__ void init()
+    {
+        beta = s->s[S_BETA];
+        ef = l2_policy_evict_first();
+        el = l2_policy_evict_last();
+    }
     __device__ void operator()(int i) const
     {
         p[i] = __dsub_rn(__dmul_rn(beta, p[i]), r[i]);               // cg.py:150-151
@@ -115,11 +144,18 @@ struct CgDirBody {
     static constexpr bool kPair = true;
     __device__ void pair(int i2) const
     {
-        double2 pv = ld2(p, i2);
-        const double2 rv = ld2(r, i2);
+        double2 pv, rv;
+        if (hints) {
+            pv = ld2_hint(p, i2, ef);
+            rv = ld2_hint(r, i2, ef);
+        } else {
+            pv = ld2(p, i2);
+            rv = ld2(r, i2);
+        }
         pv.x = __dsub_rn(__dmul_rn(beta, pv.x), rv.x);
         pv.y = __dsub_rn(__dmul_rn(beta, pv.y), rv.y);
-        st2(p, i2, pv);
+        if (hints) st2_hint(p, i2, pv, el);                          // gathered by the next K1
+        else st2(p, i2, pv);
     }
 };
 
@@ -188,10 +224,12 @@ static int cg_iterate(kry_solver *S)
     double *x = solver_vec(S, "x"), *r = solver_vec(S, "r"), *p = solver_vec(S, "p");
     double *Ap = solver_vec(S, "Ap");
     const int *done = &S->ds->done;
-    KRY_TRY((solver_spmv<1>(S, GatherPlain{p}, CgEpiAp{Ap, p}, CgFinAp{S->ds}, done, p)));
-    CgUpdateBody ub{x, r, p, Ap, S->dinv, S->precon_mode, S->ds, 0.0};
+    // option bits: 1 = vector kernels, 4 = Ap store of the SpMV epilogue (2 = CSR streams, launch.cuh)
+    const int opt = S->ctx->l2_hints;
+    KRY_TRY((solver_spmv<1>(S, GatherPlain{p}, CgEpiAp{Ap, p, (opt & 4) ? 1 : 0, 0}, CgFinAp{S->ds}, done, p)));
+    CgUpdateBody ub{x, r, p, Ap, S->dinv, S->precon_mode, S->ds, 0.0, opt & 1, 0, 0};
     KRY_TRY((solver_pass<1>(S, ub, CgFinRy{S->ds, S->hist}, done)));
-    CgDirBody db{p, r, S->ds, 0.0};
+    CgDirBody db{p, r, S->ds, 0.0, opt & 1, 0, 0};
     return vec_map_launch(S->ctx, S->n, db, done);
 }
 

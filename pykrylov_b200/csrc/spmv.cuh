@@ -34,13 +34,14 @@ struct CsrView {
     const int    *rowblk;
     int           nrows;
     int           nblocks;
+    int           hints;      // L2 evict_first on the CSR streams (row kernel)
 };
 
 static inline CsrView csr_view(const CsrDev &m)
 {
     CsrView v;
     v.rowptr = m.rowptr; v.col = m.col; v.val = m.val; v.rowblk = m.rowblk;
-    v.nrows = (int)m.nrows; v.nblocks = m.nblocks;
+    v.nrows = (int)m.nrows; v.nblocks = m.nblocks; v.hints = 0;
     return v;
 }
 
@@ -73,12 +74,24 @@ spmv_row_kernel(CsrView A, Gather g, Epi epi, ReduceWs ws, Fin fin, const int *d
 #pragma unroll
     for (int d = 0; d < (ND > 0 ? ND : 1); ++d) acc[d] = 0.0;
     const int stride = gridDim.x * blockDim.x;
-    for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < A.nrows; row += stride) {
-        const int s = __ldg(A.rowptr + row), e = __ldg(A.rowptr + row + 1);
-        double sum = 0.0;
-        for (int k = s; k < e; ++k)
-            sum = __dadd_rn(sum, __dmul_rn(__ldg(A.val + k), g(__ldg(A.col + k))));
-        epi(row, sum, acc);
+    if (A.hints) {
+        // CSR arrays are pure streams: evict_first in L2 (still L1-cached for the row walk)
+        const uint64_t ef = l2_policy_evict_first();
+        for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < A.nrows; row += stride) {
+            const int s = ldnc_hint(A.rowptr + row, ef), e = ldnc_hint(A.rowptr + row + 1, ef);
+            double sum = 0.0;
+            for (int k = s; k < e; ++k)
+                sum = __dadd_rn(sum, __dmul_rn(ldnc_hint(A.val + k, ef), g(ldnc_hint(A.col + k, ef))));
+            epi(row, sum, acc);
+        }
+    } else {
+        for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < A.nrows; row += stride) {
+            const int s = __ldg(A.rowptr + row), e = __ldg(A.rowptr + row + 1);
+            double sum = 0.0;
+            for (int k = s; k < e; ++k)
+                sum = __dadd_rn(sum, __dmul_rn(__ldg(A.val + k), g(__ldg(A.col + k))));
+            epi(row, sum, acc);
+        }
     }
     if constexpr (ND > 0) block_reduce_finalize<ND>(acc, ws, fin);
 }

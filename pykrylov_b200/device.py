@@ -90,6 +90,9 @@ class Context(object):
         call("kry_launch_count", self._h, C.byref(n))
         return n.value
 
+    def set_option(self, option, value):
+        call("kry_ctx_set_option", self._h, int(option), int(value))
+
     def prof_enable(self, max_samples):
         call("kry_prof_enable", self._h, int(max_samples))
 
