@@ -76,6 +76,7 @@ int kry_prof_read(kry_ctx *ctx, int64_t *samples, double *total_ms);
 
 /* Engine options (A/B switches for measurement). */
 #define KRY_OPT_L2_HINTS 1   /* L2 eviction-priority hints in the CG kernels (default 1) */
+#define KRY_OPT_GRAPHS   2   /* replay the solver loops as CUDA graphs of 12 iterations (default 1) */
 int kry_ctx_set_option(kry_ctx *ctx, int option, int value);
 
 /* Pinned host staging memory (for the end-to-end H2D/D2H legs). */

@@ -75,7 +75,8 @@ struct kry_ctx {
     void        *flush_buf;
     size_t       flush_bytes;
     int64_t      launches;
-    int          l2_hints;     // 1: CG kernels use L2 eviction-priority hints (default)
+    int          l2_hints;     // bit 0: CG vector kernels use L2 eviction-priority hints (default 1)
+    int          use_graphs;   // 1: solver loops replay CUDA graphs of 12 iterations (default)
     // optional per-launch timing of the dominant kernel (kry_prof_*)
     cudaEvent_t *prof_ev;      // 2 * prof_cap events
     int          prof_cap, prof_n;
@@ -280,9 +281,16 @@ __global__ void finalize_kernel(Fin fin, const double *sums, const int *done)
     if (threadIdx.x == 0 && blockIdx.x == 0) fin(sums);
 }
 
+// Resident CTAs per SM a body is compiled for (register cap = 65536 / (256 * n)):
+// 6 (<= 40 registers) unless the body asks for fewer with `static constexpr int kMinBlocks`.
+template <class B, class = void>
+struct body_min_blocks : std::integral_constant<int, 6> {};
+template <class B>
+struct body_min_blocks<B, std::void_t<decltype(B::kMinBlocks)>> : std::integral_constant<int, B::kMinBlocks> {};
+
 // Generic fused vector pass: body(i, acc) over all elements + reduction + finalize.
 template <int ND, class Body, class Fin>
-__global__ void __launch_bounds__(256, 6)      // <= 40 registers; the grid is sized to one resident wave
+__global__ void __launch_bounds__(256, body_min_blocks<Body>::value)   // grid = one resident wave
 vec_pass_kernel(int64_t n, Body body, ReduceWs ws, Fin fin, const int *done)
 {
     static_assert(ND >= 1 && ND <= KRY_MAX_DOTS, "1..KRY_MAX_DOTS fused inner products");
@@ -307,7 +315,7 @@ vec_pass_kernel(int64_t n, Body body, ReduceWs ws, Fin fin, const int *done)
 
 // Same without inner products (pure element-wise update).
 template <class Body>
-__global__ void __launch_bounds__(256, 6)
+__global__ void __launch_bounds__(256, body_min_blocks<Body>::value)
 vec_map_kernel(int64_t n, Body body, const int *done)
 {
     if (*done) return;

@@ -67,6 +67,7 @@ extern "C" int kry_ctx_create(int device, kry_ctx **out)
     c->smem_optin = (int64_t)prop.sharedMemPerBlockOptin;
     c->nranks = 1;
     c->l2_hints = 1;
+    c->use_graphs = 1;
     KRY_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     KRY_CUDA(cudaEventCreate(&c->ev0));
     KRY_CUDA(cudaEventCreate(&c->ev1));
@@ -203,8 +204,10 @@ extern "C" int kry_launch_count(kry_ctx *c, int64_t *count)
 extern "C" int kry_ctx_set_option(kry_ctx *c, int option, int value)
 {
     KRY_REQUIRE(c, KRY_ERR_INVALID, "kry_ctx_set_option: NULL context");
-    KRY_REQUIRE(option == KRY_OPT_L2_HINTS, KRY_ERR_INVALID, "kry_ctx_set_option: unknown option %d", option);
-    c->l2_hints = value;
+    KRY_REQUIRE(option == KRY_OPT_L2_HINTS || option == KRY_OPT_GRAPHS, KRY_ERR_INVALID,
+                "kry_ctx_set_option: unknown option %d", option);
+    if (option == KRY_OPT_L2_HINTS) c->l2_hints = value;
+    else c->use_graphs = value ? 1 : 0;
     return KRY_OK;
 }
 

@@ -67,7 +67,13 @@ struct kry_solver {
     kry_solver_params params;
     bool              ready;
     bool              sharded;
+    // CUDA-graph replay of KRY_GRAPH_ITERS iterations (launch-latency bound problems)
+    cudaGraphExec_t   graph_exec;
+    int64_t           graph_launches;   // kernel launches inside one replay
+    bool              warm;             // at least one iteration ran un-captured
 };
+
+constexpr int KRY_GRAPH_ITERS = 12;     // multiple of 6 = lcm of the MINRES buffer rotations
 
 static inline double *solver_vec(kry_solver *S, const char *name)
 {

@@ -14,6 +14,8 @@
 
 #include "solver.cuh"
 
+static void solver_drop_graph(kry_solver *S);
+
 // ======================================================================= CG
 // cg/cg.py:113-158.   3 launches per iteration:
 //   K1  Ap = A p ; pAp = p.Ap ; alpha = ry/pAp (+ curvature test)       [spmv]
@@ -276,6 +278,23 @@ struct BcgBodyS {
         if (pmode) z[i] = apply_diag(pd, pmode, i, si);              // :120-123
         acc[0] = __dadd_rn(acc[0], __dmul_rn(si, si));               // :107
     }
+    static constexpr bool kPair = true;
+    __device__ void pair(int i2, double *acc) const
+    {
+        const double2 rv = ld2(r, i2), vv = ld2(v, i2);
+        double2 sn;
+        sn.x = __dsub_rn(rv.x, __dmul_rn(alpha, vv.x));
+        sn.y = __dsub_rn(rv.y, __dmul_rn(alpha, vv.y));
+        st2(sv, i2, sn);
+        if (pmode) {
+            double2 zn;
+            zn.x = apply_diag(pd, pmode, 2 * i2, sn.x);
+            zn.y = apply_diag(pd, pmode, 2 * i2 + 1, sn.y);
+            st2(z, i2, zn);
+        }
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(sn.x, sn.x));
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(sn.y, sn.y));
+    }
 };
 
 struct BcgFinS {
@@ -326,6 +345,7 @@ struct BcgFinT {
 };
 
 struct BcgBodyX {
+    static constexpr int kMinBlocks = 4;       // 10 vectors in flight: allow 64 registers
     double       *x, *r, *p, *q, *sv, *z;
     const double *t, *v, *pd;
     int           pmode;
@@ -360,6 +380,40 @@ struct BcgBodyX {
         pi = __dadd_rn(pi, ri);
         p[i] = pi;
         if (pmode) q[i] = apply_diag(pd, pmode, i, pi);                      // :96-99
+    }
+    static constexpr bool kPair = true;
+    __device__ void pair(int i2, double *acc) const
+    {
+        double2 pv = ld2(p, i2), xv = ld2(x, i2);
+        const double2 qv = pmode ? ld2(q, i2) : pv;
+        if (half) {
+            if (half == 1) {
+                xv.x = __dadd_rn(xv.x, __dmul_rn(alpha, qv.x));
+                xv.y = __dadd_rn(xv.y, __dmul_rn(alpha, qv.y));
+                st2(x, i2, xv);
+            }
+            return;
+        }
+        const double2 sn = ld2(sv, i2), tv = ld2(t, i2), vv = ld2(v, i2);
+        const double2 zs = pmode ? ld2(z, i2) : sn;
+        double2 rn;
+        rn.x = __dsub_rn(sn.x, __dmul_rn(omega, tv.x));
+        rn.y = __dsub_rn(sn.y, __dmul_rn(omega, tv.y));
+        st2(r, i2, rn);
+        xv.x = __dadd_rn(__dadd_rn(xv.x, __dmul_rn(zs.x, omega)), __dmul_rn(alpha, qv.x));
+        xv.y = __dadd_rn(__dadd_rn(xv.y, __dmul_rn(zs.y, omega)), __dmul_rn(alpha, qv.y));
+        st2(x, i2, xv);
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(rn.x, rn.x));
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(rn.y, rn.y));
+        pv.x = __dadd_rn(__dsub_rn(__dmul_rn(pv.x, beta), __dmul_rn(bo, vv.x)), rn.x);
+        pv.y = __dadd_rn(__dsub_rn(__dmul_rn(pv.y, beta), __dmul_rn(bo, vv.y)), rn.y);
+        st2(p, i2, pv);
+        if (pmode) {
+            double2 qn;
+            qn.x = apply_diag(pd, pmode, 2 * i2, pv.x);
+            qn.y = apply_diag(pd, pmode, 2 * i2 + 1, pv.y);
+            st2(q, i2, qn);
+        }
     }
 };
 
@@ -968,6 +1022,17 @@ struct MinBodyR2 {            // y = (-alfa/beta) r2 + y' ; beta'^2 = r2new . (M
         if (pmode) ypre[i] = yp;
         acc[0] = __dadd_rn(acc[0], __dmul_rn(yi, yp));                       // :251
     }
+    static constexpr bool kPair = true;
+    __device__ void pair(int i2, double *acc) const      // (no preconditioner on this path)
+    {
+        const double2 rv = ld2(r2, i2);
+        double2 yv = ld2(yn, i2);
+        yv.x = __dadd_rn(__dmul_rn(c, rv.x), yv.x);
+        yv.y = __dadd_rn(__dmul_rn(c, rv.y), yv.y);
+        st2(yn, i2, yv);
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(yv.x, yv.x));
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(yv.y, yv.y));
+    }
 };
 
 struct MinFinQR {
@@ -1088,6 +1153,18 @@ struct MinBodyW {             // w = (v - oldeps w1 - delta w2) * denom ; x += p
         wi = __dmul_rn(wi, denom);
         wnew[i] = wi;
         x[i] = __dadd_rn(x[i], __dmul_rn(phi, wi));                          // :297
+    }
+    static constexpr bool kPair = true;
+    __device__ void pair(int i2, double *) const
+    {
+        const double2 yv = ld2(yold, i2), w1 = ld2(wnew, i2), wv = ld2(w2, i2);
+        double2 xv = ld2(x, i2), wn;
+        wn.x = __dmul_rn(__dsub_rn(__dsub_rn(__dmul_rn(inv, yv.x), __dmul_rn(oldeps, w1.x)), __dmul_rn(delta, wv.x)), denom);
+        wn.y = __dmul_rn(__dsub_rn(__dsub_rn(__dmul_rn(inv, yv.y), __dmul_rn(oldeps, w1.y)), __dmul_rn(delta, wv.y)), denom);
+        st2(wnew, i2, wn);
+        xv.x = __dadd_rn(xv.x, __dmul_rn(phi, wn.x));
+        xv.y = __dadd_rn(xv.y, __dmul_rn(phi, wn.y));
+        st2(x, i2, xv);
     }
 };
 
@@ -1268,6 +1345,7 @@ extern "C" int kry_solver_destroy(kry_solver *S)
 {
     if (!S) return KRY_OK;
     cudaStreamSynchronize(S->ctx->stream);
+    solver_drop_graph(S);
     cudaFree(S->slab);
     cudaFree(S->ds);
     cudaFree(S->hist);
@@ -1295,6 +1373,8 @@ static int solver_setup_common(kry_solver *S, int guess, const kry_solver_params
     KRY_REQUIRE(p, KRY_ERR_INVALID, "kry_solver_setup: NULL params");
     KRY_REQUIRE(S->method != KRY_MINRES || (p->window >= 1 && p->window <= 16), KRY_ERR_INVALID,
                 "kry_solver_setup: MINRES window %d not in [1,16]", p->window);
+    solver_drop_graph(S);
+    S->warm = false;
     KRY_REQUIRE(!(S->method == KRY_MINRES && S->precon_mode), KRY_ERR_UNSUPPORTED,
                 "kry_solver_setup: preconditioned MINRES is not device-resident yet");
     S->params = *p;
@@ -1359,23 +1439,82 @@ extern "C" int kry_solver_setup_dev(kry_solver *S, const kry_vec *rhs, const kry
     return solver_setup_common(S, guess != nullptr, params);
 }
 
+static int iterate_once(kry_solver *S)
+{
+    switch (S->method) {
+        case KRY_CG: return cg_iterate(S);
+        case KRY_BICGSTAB: return bicgstab_iterate(S);
+        case KRY_CGS: return cgs_iterate(S);
+        case KRY_TFQMR: return tfqmr_iterate(S);
+        case KRY_MINRES: return minres_iterate(S);
+    }
+    return KRY_ERR_INVALID;
+}
+
+static void solver_drop_graph(kry_solver *S)
+{
+    if (S->graph_exec) cudaGraphExecDestroy(S->graph_exec);
+    S->graph_exec = nullptr;
+    S->graph_launches = 0;
+}
+
+// Capture KRY_GRAPH_ITERS iterations of the (static) launch sequence into a graph.
+static int solver_capture_graph(kry_solver *S)
+{
+    kry_ctx *c = S->ctx;
+    const int64_t l0 = c->launches;
+    const long long rot0 = S->rot;
+    cudaGraph_t graph = nullptr;
+    KRY_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = KRY_OK;
+    for (int i = 0; i < KRY_GRAPH_ITERS && rc == KRY_OK; ++i) rc = iterate_once(S);
+    cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+    S->graph_launches = c->launches - l0;
+    c->launches = l0;                      // nothing has executed yet
+    S->rot = rot0;
+    if (rc != KRY_OK || e != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        KRY_REQUIRE(rc == KRY_OK, rc, "graph capture: a launch failed");
+        KRY_CUDA(e);
+        return KRY_ERR_CUDA;
+    }
+    e = cudaGraphInstantiate(&S->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    KRY_CUDA(e);
+    return KRY_OK;
+}
+
 extern "C" int kry_solver_iterate(kry_solver *S, int64_t n_iters)
 {
     KRY_REQUIRE(S, KRY_ERR_INVALID, "kry_solver_iterate: NULL solver");
     KRY_REQUIRE(S->ready, KRY_ERR_STATE, "kry_solver_iterate: call kry_solver_setup first");
     KRY_REQUIRE(n_iters >= 0 && n_iters < KRY_HIST_CAP / 2, KRY_ERR_INVALID,
                 "kry_solver_iterate: n_iters=%lld not in [0,%d)", (long long)n_iters, KRY_HIST_CAP / 2);
-    KRY_CUDA(cudaSetDevice(S->ctx->device));
-    for (int64_t it = 0; it < n_iters; ++it) {
-        int rc = KRY_OK;
-        switch (S->method) {
-            case KRY_CG: rc = cg_iterate(S); break;
-            case KRY_BICGSTAB: rc = bicgstab_iterate(S); break;
-            case KRY_CGS: rc = cgs_iterate(S); break;
-            case KRY_TFQMR: rc = tfqmr_iterate(S); break;
-            case KRY_MINRES: rc = minres_iterate(S); break;
+    kry_ctx *c = S->ctx;
+    KRY_CUDA(cudaSetDevice(c->device));
+    int64_t left = n_iters;
+    // Graph replay: not on sharded runs (NCCL in the sequence), not while per-launch
+    // profiling events are being recorded, and only once the sequence ran un-captured
+    // (first-use allocations / attribute calls must not happen inside a capture).
+    const bool graphs = c->use_graphs && !S->sharded && c->prof_cap == 0;
+    if (graphs && left >= KRY_GRAPH_ITERS + 6) {
+        while (left > 0 && (!S->warm || S->rot % 6 != 0)) {
+            KRY_TRY(iterate_once(S));
+            S->warm = true;
+            --left;
         }
-        if (rc != KRY_OK) return rc;
+        if (!S->graph_exec && left >= KRY_GRAPH_ITERS) KRY_TRY(solver_capture_graph(S));
+        while (S->graph_exec && left >= KRY_GRAPH_ITERS) {
+            KRY_CUDA(cudaGraphLaunch(S->graph_exec, c->stream));
+            c->launches += S->graph_launches;
+            S->rot += KRY_GRAPH_ITERS;
+            left -= KRY_GRAPH_ITERS;
+        }
+    }
+    for (; left > 0; --left) {
+        KRY_TRY(iterate_once(S));
+        S->warm = true;
     }
     return KRY_OK;
 }
