@@ -92,6 +92,8 @@ int kry_vec_destroy(kry_vec *v);
 int kry_vec_size(const kry_vec *v, int64_t *n);
 int kry_vec_upload(kry_vec *v, const double *host, int64_t n);
 int kry_vec_download(const kry_vec *v, double *host, int64_t n);
+/* Read `count` entries starting at `offset` (e.g. x[0] for a log line). */
+int kry_vec_read(const kry_vec *v, int64_t offset, int64_t count, double *host);
 int kry_vec_fill(kry_vec *v, double value);
 int kry_vec_copy(kry_vec *dst, const kry_vec *src);
 
@@ -171,7 +173,8 @@ typedef struct kry_axpby {
     const kry_vec *w;        /* may be NULL: term b*w omitted                     */
     double a, b;             /* immediates, used when the slot is < 0             */
     int    a_slot, b_slot;   /* scalar-slot index or -1                           */
-    int    a_neg,  b_neg;    /* negate the slot value                             */
+    int    a_neg,  b_neg;    /* bit 0: negate the coefficient; bit 1: the coefficient
+                                divides its vector (`u /= beta`) instead of scaling it */
 } kry_axpby;
 typedef struct kry_dotspec { const kry_vec *u, *w; } kry_dotspec;
 int kry_multi_axpy_dot(kry_ctx *ctx, int n_ops, const kry_axpby *ops,

@@ -11,7 +11,7 @@ import pykrylov_b200 as _impl
 
 __version__ = _impl.__version__
 
-for _name in ("generic", "linop", "cg", "cgs", "tfqmr", "bicgstab", "minres", "gallery", "tools"):
+for _name in ("generic", "linop", "cg", "cgs", "tfqmr", "bicgstab", "minres", "symmlq", "lls", "gallery", "tools"):
     _mod = importlib.import_module("pykrylov_b200." + _name)
     sys.modules[__name__ + "." + _name] = _mod
     globals()[_name] = _mod

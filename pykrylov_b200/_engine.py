@@ -92,10 +92,31 @@ class HostBridge(object):
             v.upload(np.asarray(init, dtype=np.float64))
         return v
 
-    def apply(self, op, x_vec, out_vec):
-        """out = op * x through the host (counts as one operator product)."""
-        y = op * x_vec.download()
+    def vec_n(self, n, init=None):
+        v = DeviceVector(self.ctx, n)
+        if init is None:
+            v.fill(0.0)
+        else:
+            v.upload(np.asarray(init, dtype=np.float64))
+        return v
+
+    def apply(self, op, x_vec, out_vec, trans=False):
+        """out = op * x (or op.T * x): a CUDA SpMV when the operator is a CSR in HBM,
+        otherwise through the host closure.  Counts as one operator product."""
+        csr = getattr(op, "device_csr", None)
+        if csr is not None and not csr.sharded:
+            if trans and not csr.symmetric:
+                csr.build_transpose()
+            csr.spmv(x_vec, out_vec, trans=trans)
+            op._nMatvec += 1
+            return out_vec
+        y = (op.T if trans else op) * x_vec.download()
         out_vec.upload(np.asarray(y, dtype=np.float64))
+        return out_vec
+
+    def apply_callable(self, fun, x_vec, out_vec):
+        """out = fun(x) for an opaque host callable (lls preconditioners M, N)."""
+        out_vec.upload(np.asarray(fun(x_vec.download()), dtype=np.float64))
         return out_vec
 
     def apply_precon(self, precon, x_vec, out_vec):

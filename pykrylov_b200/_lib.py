@@ -90,6 +90,7 @@ PROTOTYPES = {
     "kry_vec_size": (C.c_int, [handle, c_i64p]),
     "kry_vec_upload": (C.c_int, [handle, C.c_void_p, C.c_int64]),
     "kry_vec_download": (C.c_int, [handle, C.c_void_p, C.c_int64]),
+    "kry_vec_read": (C.c_int, [handle, C.c_int64, C.c_int64, C.c_void_p]),
     "kry_vec_fill": (C.c_int, [handle, C.c_double]),
     "kry_vec_copy": (C.c_int, [handle, handle]),
     "kry_csr_create": (C.c_int, [handle, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,

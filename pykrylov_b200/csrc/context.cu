@@ -321,6 +321,18 @@ extern "C" int kry_vec_download(const kry_vec *v, double *host, int64_t n)
     return KRY_OK;
 }
 
+extern "C" int kry_vec_read(const kry_vec *v, int64_t offset, int64_t count, double *host)
+{
+    KRY_REQUIRE(v && host, KRY_ERR_INVALID, "kry_vec_read: NULL argument");
+    KRY_REQUIRE(offset >= 0 && count >= 0 && offset + count <= v->n, KRY_ERR_SHAPE,
+                "kry_vec_read: [%lld,%lld) outside a vector of %lld entries", (long long)offset,
+                (long long)(offset + count), (long long)v->n);
+    KRY_CUDA(cudaMemcpyAsync(host, v->d + offset, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost,
+                             v->ctx->stream));
+    KRY_CUDA(cudaStreamSynchronize(v->ctx->stream));
+    return KRY_OK;
+}
+
 __global__ void fill_kernel(double *d, int64_t n, double v)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -120,10 +120,18 @@ struct MultiAxpyBody {
             ca[k] = op[k].a;
             cb[k] = op[k].b;
             if (k < n_ops) {
-                if (op[k].a_slot >= 0) ca[k] = op[k].a_neg ? -slots[op[k].a_slot] : slots[op[k].a_slot];
-                if (op[k].b_slot >= 0) cb[k] = op[k].b_neg ? -slots[op[k].b_slot] : slots[op[k].b_slot];
+                if (op[k].a_slot >= 0) ca[k] = slots[op[k].a_slot];
+                if (op[k].b_slot >= 0) cb[k] = slots[op[k].b_slot];
+                if (op[k].a_neg & 1) ca[k] = -ca[k];
+                if (op[k].b_neg & 1) cb[k] = -cb[k];
             }
         }
+    }
+    // coefficient applied as a multiplier, or as a divisor when bit 1 of the flag is set
+    // (`u /= beta` in the reference is a true division, not a multiply by 1/beta)
+    __device__ static double term(double c, double v, int flag)
+    {
+        return (flag & 2) ? __ddiv_rn(v, c) : __dmul_rn(c, v);
     }
     __device__ void update(int i) const
     {
@@ -133,11 +141,11 @@ struct MultiAxpyBody {
             const double *u = op[k].u, *w = op[k].w;
             double r;
             if (u && w)
-                r = __dadd_rn(__dmul_rn(ca[k], u[i]), __dmul_rn(cb[k], w[i]));
+                r = __dadd_rn(term(ca[k], u[i], op[k].a_neg), term(cb[k], w[i], op[k].b_neg));
             else if (u)
-                r = __dmul_rn(ca[k], u[i]);
+                r = term(ca[k], u[i], op[k].a_neg);
             else if (w)
-                r = __dmul_rn(cb[k], w[i]);
+                r = term(cb[k], w[i], op[k].b_neg);
             else
                 r = 0.0;
             op[k].z[i] = r;

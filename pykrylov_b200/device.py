@@ -204,6 +204,12 @@ class DeviceVector(object):
         call("kry_vec_fill", self._h, float(value))
         return self
 
+    def peek(self, index=0):
+        """One entry (for the log lines that print x[0])."""
+        out = C.c_double(0.0)
+        call("kry_vec_read", self._h, int(index), 1, C.byref(out))
+        return out.value
+
     def copy_from(self, other):
         call("kry_vec_copy", self._h, other._h)
         return self
@@ -342,8 +348,8 @@ def multi_axpy_dot(ctx, ops, dots=(), slot0=0):
         arr[k].b = float(o.get("b", 1.0))
         arr[k].a_slot = int(o.get("a_slot", -1))
         arr[k].b_slot = int(o.get("b_slot", -1))
-        arr[k].a_neg = int(o.get("a_neg", 0))
-        arr[k].b_neg = int(o.get("b_neg", 0))
+        arr[k].a_neg = int(o.get("a_neg", 0)) | (2 if o.get("a_div") else 0)
+        arr[k].b_neg = int(o.get("b_neg", 0)) | (2 if o.get("b_div") else 0)
     darr = (L.DotSpec * max(len(dots), 1))()
     for k, (u, w) in enumerate(dots):
         darr[k].u = u._h

@@ -1,0 +1,137 @@
+"""CPU tests of the HOST-SIDE control logic of the solvers that drive device vectors
+from Python (LSQR, SYMMLQ, bridged CG).  The device calls are replaced by the
+test-only NumPy restatement in tests/fake_bridge.py, so what is checked here is the
+scalar recurrences / stopping tests / attribute contract -- bit-for-bit against the
+live reference when oracle/_ref is present, and against the golden values otherwise.
+(The same solvers on real CUDA kernels are covered by tests/test_gpu_lls.py.)"""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import GOLDEN, ROOT, mtx
+from fake_bridge import FakeBridge
+from oracle.csr_ref import CsrRef, load_mtx
+
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+HAVE_REF = os.path.isdir(os.path.join(REF_DIR, "refpykrylov"))
+
+
+@pytest.fixture()
+def fake(monkeypatch):
+    import pykrylov_b200._engine as eng
+    monkeypatch.setattr(eng, "HostBridge", FakeBridge)
+    return eng
+
+
+@pytest.fixture(scope="module")
+def gold():
+    with open(os.path.join(GOLDEN, "golden_lls.json")) as fh:
+        return json.load(fh), np.load(os.path.join(GOLDEN, "golden_lls_vectors.npz"))
+
+
+def sym_jpwh():
+    M = load_mtx(mtx("jpwh_991"))
+    S0 = M.to_scipy()
+    return CsrRef.from_scipy((S0 + S0.T) * 0.5)
+
+
+def test_lsqr_host_logic_matches_golden(fake, gold):
+    from pykrylov_b200.linop import LinearOperator
+    from pykrylov_b200.lls import LSQRFramework
+    G, V = gold
+    M = load_mtx(mtx("jpwh_991"))
+    n = M.shape[0]
+    op = LinearOperator(n, n, lambda v: M.matvec(v), matvec_transp=lambda u: M.rmatvec(u))
+    for damp in (0.0, 0.1):
+        ls = LSQRFramework(op)
+        ls.solve(M.matvec(np.ones(n)), damp=damp)
+        g = G["LSQR/jpwh_991/damp%g" % damp]
+        for k in ("istop", "itn", "r1norm", "r2norm", "Anorm", "Acond", "Arnorm", "xnorm"):
+            assert getattr(ls, k) == g[k], k
+        assert np.array_equal(ls.x, V["LSQR_jpwh_991_damp%g_x" % damp])
+        assert ls.nMatvec == 2 * ls.itn and ls.optimal
+    R = sp.random(600, 200, density=0.03, random_state=7, format="csr")
+    R.sort_indices()
+    b = np.random.default_rng(7).standard_normal(600)
+    ls = LSQRFramework(LinearOperator(200, 600, lambda v: R @ v, matvec_transp=lambda u: R.T @ u))
+    ls.solve(b, store_resids=True)
+    g = G["LSQR/random_600x200"]
+    assert (ls.istop, ls.itn, ls.r1norm, ls.Anorm, ls.Acond) == (g["istop"], g["itn"], g["r1norm"], g["Anorm"], g["Acond"])
+    assert ls.resids[:25] == g["resids"] and np.array_equal(ls.x, V["LSQR_random_600x200_x"])
+
+
+def test_symmlq_host_logic_matches_golden(fake, gold):
+    from pykrylov_b200.linop import LinearOperator
+    from pykrylov_b200.symmlq import Symmlq
+    G, V = gold
+    S = sym_jpwh()
+    n = S.shape[0]
+    op = LinearOperator(n, n, lambda v: S.matvec(v), symmetric=True)
+    for shift, key in ((None, "SYMMLQ/sym_jpwh_991"), (0.5, "SYMMLQ/sym_jpwh_991_shift0.5")):
+        sq = Symmlq(op)
+        sq.solve(S.matvec(np.ones(n)), **({} if shift is None else {"shift": shift}))
+        g = G[key]
+        assert (sq.nMatvec, sq.residNorm, sq.xNorm, sq.anorm, sq.acond) == \
+            (g["nMatvec"], g["residNorm"], g["xNorm"], g["anorm"], g["acond"])
+        assert np.array_equal(sq.x, V[key.replace("/", "_") + "_x"])
+
+
+def test_bridged_cg_host_logic_matches_oracle(fake):
+    from oracle import krylov_ref as kr
+    from pykrylov_b200.linop import LinearOperator
+    from pykrylov_b200.gallery import Poisson2dMatvec
+    from pykrylov_b200.cg import CG
+    n = 400
+    A = LinearOperator(n, n, lambda x: Poisson2dMatvec(x), symmetric=True)
+    rhs = A * np.ones(n)
+    guess = np.random.default_rng(3).standard_normal(n)
+    dinv = np.full(n, 0.25)
+    from pykrylov_b200.linop import LinearOperator as LO
+    P = LO(n, n, lambda r: dinv * r, symmetric=True)            # opaque preconditioner -> bridge
+    for kw, okw in ((dict(), dict()), (dict(guess=guess), dict(guess=guess.copy()))):
+        for precon, pfun in ((None, None), (P, lambda r: dinv * r)):
+            cg = CG(A, precon=precon)
+            cg.solve(rhs, store_iterates=True, **kw)
+            ref = kr.cg_solve(kr.poisson2d_matvec, rhs, precon=pfun, **okw)
+            assert (cg.nMatvec, cg.residNorm0, cg.residNorm, cg.converged) == \
+                (ref.nMatvec, ref.residNorm0, ref.residNorm, ref.converged)
+            assert cg.residHistory == ref.residHistory and np.array_equal(cg.bestSolution, ref.x)
+            assert len(cg.iterates) == len(ref.residHistory)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not generated (needs /root/reference)")
+def test_lsqr_and_symmlq_bit_identical_to_live_reference(fake):
+    sys.path.insert(0, REF_DIR)
+    from refpykrylov.linop import LinearOperator as RLO
+    from refpykrylov.lls import LSQRFramework as RLSQR
+    from refpykrylov.symmlq import Symmlq as RSymmlq
+    from pykrylov_b200.linop import LinearOperator
+    from pykrylov_b200.lls import LSQRFramework
+    from pykrylov_b200.symmlq import Symmlq
+    rng = np.random.default_rng(12)
+    R = sp.random(150, 90, density=0.1, random_state=3, format="csr")
+    b = rng.standard_normal(150)
+    mv, rmv = (lambda v: R @ v), (lambda u: R.T @ u)
+    Mdiag, Ndiag = 1.0 + rng.random(150), 1.0 + rng.random(90)
+    for kw in (dict(), dict(damp=0.3), dict(M=lambda u: u / Mdiag, N=lambda v: v / Ndiag), dict(atol=0, btol=0, etol=0, itnlim=60)):
+        a = LSQRFramework(LinearOperator(90, 150, mv, matvec_transp=rmv))
+        r = RLSQR(RLO(90, 150, mv, matvec_transp=rmv))
+        a.solve(b, **kw)
+        r.solve(b, **kw)
+        for k in ("istop", "itn", "r1norm", "r2norm", "Anorm", "Acond", "Arnorm", "xnorm"):
+            assert getattr(a, k) == getattr(r, k), (k, kw.keys())
+        assert np.array_equal(a.x, r.x)
+    S = sym_jpwh()
+    n = S.shape[0]
+    rhs = S.matvec(rng.standard_normal(n))
+    for kw in (dict(), dict(shift=-0.7), dict(matvec_max=30), dict(check=True)):
+        a = Symmlq(LinearOperator(n, n, lambda v: S.matvec(v), symmetric=True))
+        r = RSymmlq(RLO(n, n, lambda v: S.matvec(v), symmetric=True))
+        a.solve(rhs, **kw)
+        r.solve(rhs, **kw)
+        assert (a.nMatvec, a.residNorm, a.xNorm, a.anorm, a.acond) == (r.nMatvec, r.residNorm, r.xNorm, r.anorm, r.acond), kw
+        assert np.array_equal(a.x, r.x)
