@@ -80,8 +80,9 @@ class HostBridge(object):
     """Vectors live in HBM; an opaque Python operator is applied by copying its
     argument to the host and its result back."""
 
-    def __init__(self, n, context=None):
-        self.ctx = context or default_context()
+    def __init__(self, n, context=None, op=None):
+        csr = getattr(op, "device_csr", None)
+        self.ctx = context or (csr.ctx if csr is not None else None) or default_context()
         self.n = n
 
     def vec(self, init=None):

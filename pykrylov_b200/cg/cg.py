@@ -92,7 +92,7 @@ class CG(KrylovMethod):
     def _solve_bridged(self, rhs, guess, matvec_max, check_curvature, store_resids,
                        store_iterates, result_type):
         n = rhs.shape[0]
-        B = _engine.HostBridge(n, self.context)
+        B = _engine.HostBridge(n, self.context, self.op)
         op, precon = self.op, self.precon
         nMatvec = 0
         definite = True

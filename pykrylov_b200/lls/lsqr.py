@@ -98,7 +98,7 @@ class LSQRFramework(KrylovMethod):
             print("atol = %8.2e                 conlim = %8.2e" % (atol, conlim))
             print("btol = %8.2e                 itnlim = %8g" % (btol, itnlim))
 
-        B = _engine.HostBridge(n, self.context)
+        B = _engine.HostBridge(n, self.context, A)
         x = B.vec_n(n)
         xNrgNorm2 = 0.0
         dErr = np.zeros(window)

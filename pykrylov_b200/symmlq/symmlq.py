@@ -62,7 +62,7 @@ class Symmlq(KrylovMethod):
         log("maxit =  %3g     eps    =  %11.2e    rtol   =  %11.2e" % (int((matvec_max - 2.0) / 2), eps, rtol))
 
         op, precon = self.op, self.precon
-        B = _engine.HostBridge(n, self.context)
+        B = _engine.HostBridge(n, self.context, op)
         istop = itn = 0
         ynorm = acond = anorm = xnorm = rnorm = 0
         done = False

@@ -25,7 +25,7 @@ class FakeVec(object):
 
 
 class FakeBridge(object):
-    def __init__(self, n, context=None):
+    def __init__(self, n, context=None, op=None):
         self.n = n
 
     def vec(self, init=None):

@@ -67,7 +67,9 @@ def test_lsqr_rectangular_least_squares(ctx, gold, capsys):
     # lose orthogonality and those late scalars are rounding-chaotic (first 8 steps agree to 1e-15)
     for k in ("Anorm", "Acond"):
         assert srel(getattr(ls, k), g[k]) <= 1e-3, (k, getattr(ls, k), g[k])
-    assert np.allclose(ls.resids[:25], g["resids"], rtol=1e-9), (ls.resids[:5], g["resids"][:5])
+    assert np.allclose(ls.resids[:8], g["resids"][:8], rtol=1e-13)          # early steps: reduction noise only
+    dmax = np.max(np.abs(np.array(ls.resids[:25]) - np.array(g["resids"])) / np.array(g["resids"]))
+    assert dmax <= 1e-6, dmax
     xg = V["LSQR_random_600x200_x"]
     assert np.linalg.norm(ls.x - xg) <= 1e-7 * np.linalg.norm(xg), np.linalg.norm(ls.x - xg)
     # normal equations: A^T (b - A x) ~ 0 (the solve stops on the direct-error test, etol 1e-6)
