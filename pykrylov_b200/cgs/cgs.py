@@ -26,7 +26,10 @@ class CGS(KrylovMethod):
         result_type = _engine.check_real(self.op, rhs)
         guess = kwargs.get("guess", None)
         matvec_max = kwargs.get("matvec_max", 2 * n)
-        plan = _engine.require_plan(self.acronym, self.op, self.precon, n)
+        plan = _engine.resolve(self.op, self.precon, n)
+        if plan is None:       # closure operator / opaque preconditioner: host-driven loop on device vectors
+            from .. import _bridged
+            return _bridged.cgs(self, rhs, guess, matvec_max, result_type)
         S = _engine.make_solver("cgs", plan, self.context)
         S.setup(rhs, guess=guess, abstol=self.abstol, reltol=self.reltol, matvec_max=matvec_max)
         state = {"first": True, "nmv": 0}

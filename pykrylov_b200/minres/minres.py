@@ -64,9 +64,7 @@ class Minres(KrylovMethod):
         self.dir_errors_window = []
         self.iterates = []
         result_type = _engine.check_real(A, b)
-        if precon is not None:
-            raise NotImplementedError("preconditioned MINRES is not device-resident yet")
-        plan = _engine.require_plan(self.acronym, A, None, n)
+        plan = _engine.resolve(A, None, n) if precon is None else None
 
         if show:
             print(self.first + "Solution of symmetric Ax = b")
@@ -74,6 +72,10 @@ class Minres(KrylovMethod):
                   % (n, (precon is not None), shift))
             print("itnlim =  %3d     rtol   =  %11.2e\n" % (itnlim, rtol))
 
+        if plan is None:       # closure operator or a preconditioner: host-driven loop on device vectors
+            from .. import _bridged
+            return _bridged.minres(self, b, precon, shift, show, check, itnlim, rtol, etol,
+                                   store_iterates, window, result_type)
         S = _engine.make_solver("minres", plan, self.context)
         symmetric_ok = True
         if check:                                         # minres.py:186-189

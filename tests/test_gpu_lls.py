@@ -122,3 +122,51 @@ def test_symmlq_golden(ctx, gold):
     # loop through `while nMatvec < matvec_max` with istop still 0 (symmlq.py:234).
     assert sq.nMatvec == g["nMatvec"] and sq.istop == 0
     assert srel(sq.anorm, g["anorm"]) <= 5e-2
+
+
+def test_lsmr_rectangular_least_squares(ctx, gold):
+    from pykrylov_b200.linop import linop_from_scipy
+    from pykrylov_b200.lls import LSMRFramework
+    G, V = gold
+    R = sp.random(600, 200, density=0.03, random_state=7, format="csr")
+    R.sort_indices()
+    b = np.random.default_rng(7).standard_normal(600)
+    ls = LSMRFramework(linop_from_scipy(R, context=ctx), context=ctx)
+    x, istop, itn, normr, normar, normA, condA, normx = ls.solve(b)
+    g = G["LSMR/random_600x200"]
+    assert (istop, itn) == (g["istop"], g["itn"])
+    assert srel(normr, g["normr"]) <= 1e-8 and srel(normx, g["normx"]) <= 1e-8
+    assert srel(normA, g["normA"]) <= 1e-3 and srel(condA, g["condA"]) <= 1e-2
+    xg = V["LSMR_random_600x200_x"]
+    assert np.linalg.norm(x - xg) <= 1e-7 * np.linalg.norm(xg) and x is ls.x
+    assert np.linalg.norm(R.T @ (b - R @ x)) <= 1e-3 * np.linalg.norm(R.T @ b)
+
+
+def test_closure_operators_through_the_bridge_on_gpu(ctx):
+    """Every solver accepts the reference's closure-defined operators: vectors stay in HBM,
+    fused AXPY/dot kernels run on the GPU, the closure is applied on the host."""
+    from oracle import krylov_ref as kr
+    from pykrylov_b200.linop import LinearOperator
+    from pykrylov_b200.bicgstab import BiCGSTAB
+    from pykrylov_b200.cgs import CGS
+    from pykrylov_b200.tfqmr import TFQMR
+    from pykrylov_b200.minres import Minres
+    M = load_mtx(mtx("jpwh_991"))
+    n = M.shape[0]
+    rng = np.random.default_rng(8)
+    rhs = M.matvec(rng.standard_normal(n))
+    op = LinearOperator(n, n, lambda v: M.matvec(v))
+    for K, solve in ((BiCGSTAB, kr.bicgstab_solve), (CGS, kr.cgs_solve), (TFQMR, kr.tfqmr_solve)):
+        ks = K(op, reltol=1e-8, context=ctx)
+        ks.solve(rhs, matvec_max=2 * n)
+        ref = solve(M, rhs, reltol=1e-8, matvec_max=2 * n)
+        assert ks.converged and abs(ks.nMatvec - ref.nMatvec) <= 6
+        assert np.linalg.norm(rhs - M.matvec(ks.bestSolution)) <= 1e-6 * np.linalg.norm(rhs)
+    S0 = M.to_scipy()
+    S = CsrRef.from_scipy((S0 + S0.T) * 0.5)
+    d = 1.0 + rng.random(n)
+    mr = Minres(LinearOperator(n, n, lambda v: S.matvec(v), symmetric=True), context=ctx)
+    mr.solve(S.matvec(np.ones(n)), show=False, precon=LinearOperator(n, n, lambda v: v / d, symmetric=True))
+    ref = kr.minres_solve(S, S.matvec(np.ones(n)), precon=lambda v: v / d)
+    assert mr.istop == ref.istop and abs(mr.itn - ref.itn) <= 2
+    assert np.linalg.norm(mr.x - ref.x) <= 1e-5 * np.linalg.norm(ref.x)

@@ -135,3 +135,93 @@ def test_lsqr_and_symmlq_bit_identical_to_live_reference(fake):
         r.solve(rhs, **kw)
         assert (a.nMatvec, a.residNorm, a.xNorm, a.anorm, a.acond) == (r.nMatvec, r.residNorm, r.xNorm, r.anorm, r.acond), kw
         assert np.array_equal(a.x, r.x)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not generated (needs /root/reference)")
+def test_bridged_loops_bit_identical_to_live_reference(fake, capsys):
+    """Closure operators / opaque preconditioners: Bi-CGSTAB, CGS, TFQMR, MINRES host-driven
+    loops (pykrylov_b200/_bridged.py) against the reference run live."""
+    import io
+    from contextlib import redirect_stdout
+    sys.path.insert(0, REF_DIR)
+    import refpykrylov.linop as rlo
+    from refpykrylov.bicgstab import BiCGSTAB as RB
+    from refpykrylov.cgs import CGS as RC
+    from refpykrylov.tfqmr import TFQMR as RT
+    from refpykrylov.minres import Minres as RM
+    import pykrylov_b200.linop as lo
+    from pykrylov_b200.bicgstab import BiCGSTAB
+    from pykrylov_b200.cgs import CGS
+    from pykrylov_b200.tfqmr import TFQMR
+    from pykrylov_b200.minres import Minres
+    M = load_mtx(mtx("jpwh_991"))
+    n = M.shape[0]
+    rng = np.random.default_rng(8)
+    rhs = M.matvec(rng.standard_normal(n))
+    guess = rng.standard_normal(n)
+    d = 1.0 / np.maximum(np.abs(M.to_scipy().diagonal()), 1.0)
+    for Ours, Ref in ((BiCGSTAB, RB), (CGS, RC), (TFQMR, RT)):
+        for use_guess in (False, True):
+            for use_precon in (False, True):
+                a = Ours(lo.LinearOperator(n, n, lambda v: M.matvec(v)), reltol=1e-8,
+                         precon=lo.LinearOperator(n, n, lambda r: d * r, symmetric=True) if use_precon else None)
+                r = Ref(rlo.LinearOperator(n, n, lambda v: M.matvec(v)), reltol=1e-8,
+                        precon=rlo.DiagonalOperator(d) if use_precon else None)
+                kw = dict(matvec_max=2 * n)
+                if use_guess:
+                    a.solve(rhs, guess=guess.copy(), **kw)
+                    r.solve(rhs, guess=guess.copy(), **kw)
+                else:
+                    a.solve(rhs, **kw)
+                    r.solve(rhs, **kw)
+                assert (a.nMatvec, a.residNorm0, a.residNorm, a.converged) == \
+                    (r.nMatvec, r.residNorm0, r.residNorm, r.converged), (Ours.__name__, use_guess, use_precon)
+                assert np.array_equal(a.bestSolution, r.bestSolution)
+    S = sym_jpwh()
+    b = S.matvec(np.ones(n))
+    dpos = 1.0 + rng.random(n)
+    for kw, pre in ((dict(), None), (dict(shift=0.3), None), (dict(), dpos), (dict(itnlim=25), None)):
+        a = Minres(lo.LinearOperator(n, n, lambda v: S.matvec(v), symmetric=True))
+        r = RM(rlo.LinearOperator(n, n, lambda v: S.matvec(v), symmetric=True))
+        akw, rkw = dict(kw), dict(kw)
+        if pre is not None:
+            akw["precon"] = lo.LinearOperator(n, n, lambda v: v / pre, symmetric=True)
+            rkw["precon"] = rlo.LinearOperator(n, n, lambda v: v / pre, symmetric=True)
+        with redirect_stdout(io.StringIO()):
+            a.solve(b, show=False, **akw)
+            r.solve(b, show=False, **rkw)
+        assert (a.istop, a.itn, a.rnorm, a.Anorm, a.Acond, a.ynorm, a.Arnorm) == \
+            (r.istop, r.itn, r.rnorm, r.Anorm, r.Acond, r.ynorm, r.Arnorm), kw
+        assert a.residHistory == r.residHistory and a.dir_errors_window == r.dir_errors_window
+        assert np.array_equal(a.x, r.x)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not generated (needs /root/reference)")
+def test_lsmr_bit_identical_to_live_reference(fake):
+    sys.path.insert(0, REF_DIR)
+    from refpykrylov.linop import LinearOperator as RLO
+    from refpykrylov.lls import LSMRFramework as RLSMR
+    from pykrylov_b200.linop import LinearOperator
+    from pykrylov_b200.lls import LSMRFramework
+    rng = np.random.default_rng(13)
+    R = sp.random(150, 90, density=0.1, random_state=3, format="csr")
+    b = rng.standard_normal(150)
+    mv, rmv = (lambda v: R @ v), (lambda u: R.T @ u)
+    Mdiag, Ndiag = 1.0 + rng.random(150), 1.0 + rng.random(90)
+    for kw in (dict(), dict(damp=0.3), dict(M=lambda u: u / Mdiag, N=lambda v: v / Ndiag),
+               dict(atol=0, btol=0, etol=0, itnlim=40), dict(store_resids=True)):
+        a = LSMRFramework(LinearOperator(90, 150, mv, matvec_transp=rmv))
+        r = RLSMR(RLO(90, 150, mv, matvec_transp=rmv))
+        ra = a.solve(b, **kw)
+        rr = r.solve(b, **kw)
+        assert tuple(ra[1:]) == tuple(rr[1:]), kw.keys()
+        assert np.array_equal(ra[0], rr[0]) and np.array_equal(a.x, r.x)
+        assert a.resids == r.resids and a.dir_errors_window == r.dir_errors_window
+    M = load_mtx(mtx("jpwh_991"))
+    n = M.shape[0]
+    a = LSMRFramework(LinearOperator(n, n, lambda v: M.matvec(v), matvec_transp=lambda u: M.rmatvec(u)))
+    r = RLSMR(RLO(n, n, lambda v: M.matvec(v), matvec_transp=lambda u: M.rmatvec(u)))
+    ra, rr = a.solve(M.matvec(np.ones(n))), r.solve(M.matvec(np.ones(n)))
+    assert tuple(ra[1:]) == tuple(rr[1:]) and np.array_equal(ra[0], rr[0])
+    z = LSMRFramework(LinearOperator(90, 150, mv, matvec_transp=rmv)).solve(np.zeros(150))
+    assert z[1] == 0 and z[2] == 0 and np.array_equal(z[0], np.zeros(90))
