@@ -255,6 +255,9 @@ def main_ours(args):
     if world != args.gpus and rank == 0:
         print("warning: --gpus %d but WORLD_SIZE=%d" % (args.gpus, world), file=sys.stderr)
     g = args.grid or (G_CONFIG2 if world == 1 else G_CONFIG5)
+    if world > 1 and args.nccl_allreduce:
+        ctx.set_option(3, 0)
+    fused_allreduce = bool(world > 1 and ctx.get_option(3))
     A, rhs, n, lo, hi = build_problem(ctx, g, rank, world)
     nnz_total = 5 * n - 4 * g
     sampler = ClockSampler(ctx.device)
@@ -315,7 +318,9 @@ def main_ours(args):
                "config": {"workload": ("BASELINE.json configs[1]: CG fp64, 5-pt Poisson Laplacian (gallery), "
                                        "grid %d^2" % g) if world == 1 else
                                       ("BASELINE.json configs[4]: CG fp64, row-sharded 5-pt Laplacian grid %d^2, "
-                                       "%d row blocks, packed-halo ncclAllGather + ncclAllReduce(scalars)" % (g, world)),
+                                       "%d row blocks, packed-halo ncclAllGather + %s" % (
+                                           g, world, "in-kernel all-reduce of the scalars over NVLink peer memory"
+                                           if fused_allreduce else "ncclAllReduce(scalars)")),
                           "rows": n, "nnz": nnz_total, "rows_per_gpu": n_loc,
                           "operator": "CSR int32/fp64 generated on device (kry_csr_create_poisson2d)",
                           "rhs": "A*ones", "stopping": "abstol=reltol=0 so exactly K iterations run",
@@ -371,6 +376,8 @@ def main():
     ap.add_argument("--grid", type=int, default=0, help="override the Laplacian grid size (debugging)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-single", action="store_true", help="skip the 1-GPU same-workload leg (N>1)")
+    ap.add_argument("--nccl-allreduce", action="store_true",
+                    help="N>1: use ncclAllReduce + finalize launches instead of the fused NVLink peer-memory all-reduce")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -76,8 +76,13 @@ int kry_prof_read(kry_ctx *ctx, int64_t *samples, double *total_ms);
 
 /* Engine options (A/B switches for measurement). */
 #define KRY_OPT_L2_HINTS 1   /* L2 eviction-priority hints in the CG kernels (default 1) */
+#define KRY_OPT_P2P      3   /* sharded runs: all-reduce the fused inner products through NVLink
+                                peer memory inside the kernel instead of ncclAllReduce + a
+                                finalize launch (default 1 when CUDA IPC mapping succeeded;
+                                must be set identically on every rank)                       */
 #define KRY_OPT_GRAPHS   2   /* replay the solver loops as CUDA graphs of 12 iterations (default 1) */
 int kry_ctx_set_option(kry_ctx *ctx, int option, int value);
+int kry_ctx_get_option(kry_ctx *ctx, int option, int *value);
 
 /* Pinned host staging memory (for the end-to-end H2D/D2H legs). */
 int kry_host_alloc(int64_t bytes, void **out);

@@ -69,6 +69,66 @@ int nccl_load()
 
 static_assert(sizeof(ncclUniqueId) == KRY_COMM_ID_BYTES, "ncclUniqueId size");
 
+// ------------------------------------------- NVLink peer-memory inboxes (CUDA IPC)
+// Every rank owns a small inbox [2 slots][nranks][8 doubles]; all inboxes are mapped into
+// every process, so the last CTA of a fused reduction can deposit its totals directly in
+// its peers' memory (common.cuh, block_reduce_finalize).
+static void p2p_teardown(kry_ctx *c)
+{
+    for (int q = 0; q < 16; ++q) {
+        if (c->p2p_peer_ptr[q] && q != c->rank) cudaIpcCloseMemHandle(c->p2p_peer_ptr[q]);
+        c->p2p_peer_ptr[q] = nullptr;
+    }
+    if (c->p2p_inbox) cudaFree(c->p2p_inbox);
+    if (c->p2p_peers_dev) cudaFree(c->p2p_peers_dev);
+    if (c->p2p_seq) cudaFree(c->p2p_seq);
+    c->p2p_inbox = nullptr;
+    c->p2p_peers_dev = nullptr;
+    c->p2p_seq = nullptr;
+    c->p2p_on = 0;
+    cudaGetLastError();
+}
+
+extern "C" int kry_comm_allgather_host(kry_ctx *c, const void *send, void *recv, int64_t bytes);
+
+static int p2p_setup(kry_ctx *c)
+{
+    const int P = c->nranks;
+    const size_t inbox_bytes = (size_t)2 * P * 8 * sizeof(double);
+    KRY_TRY(kry_alloc((void **)&c->p2p_inbox, inbox_bytes));
+    KRY_CUDA(cudaMemset(c->p2p_inbox, 0, inbox_bytes));
+    KRY_TRY(kry_alloc((void **)&c->p2p_peers_dev, 16 * sizeof(double *)));
+    KRY_TRY(kry_alloc((void **)&c->p2p_seq, 256));
+    KRY_CUDA(cudaMemset(c->p2p_seq, 0, 256));
+    cudaIpcMemHandle_t mine;
+    KRY_CUDA(cudaIpcGetMemHandle(&mine, c->p2p_inbox));
+    std::vector<cudaIpcMemHandle_t> all((size_t)P);
+    KRY_TRY(kry_comm_allgather_host(c, &mine, all.data(), sizeof(mine)));
+    int ok = 1;
+    for (int q = 0; q < P && ok; ++q) {
+        if (q == c->rank) {
+            c->p2p_peer_ptr[q] = c->p2p_inbox;
+            continue;
+        }
+        void *ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, all[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            ok = 0;
+            break;
+        }
+        c->p2p_peer_ptr[q] = ptr;
+    }
+    // all ranks must agree, otherwise some would wait for peers that use NCCL
+    double flag = ok ? 1.0 : 0.0, neg = -flag;
+    double mm[2] = {flag, neg};
+    KRY_TRY(kry_comm_allreduce_host(c, mm, 2, 1));           // max(flag), max(-flag) = -min(flag)
+    KRY_REQUIRE(-mm[1] >= 1.0, KRY_ERR_COMM, "peer mapping failed on some rank");
+    KRY_CUDA(cudaMemcpy(c->p2p_peers_dev, c->p2p_peer_ptr, (size_t)P * sizeof(void *), cudaMemcpyHostToDevice));
+    KRY_CUDA(cudaDeviceSynchronize());
+    c->p2p_on = 1;
+    return KRY_OK;
+}
+
 extern "C" int kry_comm_unique_id(void *id128)
 {
     KRY_REQUIRE(id128, KRY_ERR_INVALID, "kry_comm_unique_id: NULL output");
@@ -94,6 +154,10 @@ extern "C" int kry_comm_init(kry_ctx *c, int nranks, int rank, const void *id128
     c->nccl = (void *)comm;
     c->nranks = nranks;
     c->rank = rank;
+    if (nranks > 1 && nranks <= 16) {
+        // best effort: without peer mapping the NCCL all-reduce path stays in use
+        if (p2p_setup(c) != KRY_OK) p2p_teardown(c);
+    }
     return KRY_OK;
 }
 
@@ -101,6 +165,7 @@ extern "C" int kry_comm_destroy(kry_ctx *c)
 {
     if (!c || !c->nccl) return KRY_OK;
     cudaStreamSynchronize(c->stream);
+    p2p_teardown(c);
     g_nccl.CommDestroy((ncclComm_t)c->nccl);
     c->nccl = nullptr;
     c->nranks = 1;

@@ -57,6 +57,12 @@ struct ReduceWs {
     unsigned *counter;    // retirement ticket, self-resetting
     int       stride;
     int       defer;      // 1: only write sums[]; the finalize functor runs after the all-reduce
+    // fused all-reduce over NVLink peer memory (sharded runs, see block_reduce_finalize)
+    int                 p2p;      // 1: exchange the totals through the peers' inboxes in-kernel
+    int                 nranks, rank;
+    double             *inbox;    // local  [2][nranks][8]: {ND totals ..., seq in word 7}
+    double *const      *peers;    // device array: peers[q] = rank q's inbox (IPC-mapped)
+    unsigned long long *seq;      // reduction sequence number (identical on every rank)
 };
 
 struct kry_ctx {
@@ -75,6 +81,12 @@ struct kry_ctx {
     void        *flush_buf;
     size_t       flush_bytes;
     int64_t      launches;
+    // NVLink peer-memory all-reduce (comm.cu): inboxes of all ranks mapped through CUDA IPC
+    int                 p2p_on;
+    double             *p2p_inbox;
+    double            **p2p_peers_dev;
+    unsigned long long *p2p_seq;
+    void               *p2p_peer_ptr[16];
     int          l2_hints;     // bit 0: CG vector kernels use L2 eviction-priority hints (default 1)
     int          use_graphs;   // 1: solver loops replay CUDA graphs of 12 iterations (default)
     // optional per-launch timing of the dominant kernel (kry_prof_*)
@@ -187,6 +199,51 @@ __device__ __forceinline__ void block_reduce_finalize(double (&acc)[ND], const R
     }
     __syncthreads();            // s_warp reuse
     block_sum<ND>(tot, s_warp);
+    if (ws.p2p) {
+        // One-shot all-reduce fused into this kernel: thread q of the last CTA stores this
+        // rank's totals (then, after a system-scope fence, the sequence number) into rank q's
+        // inbox over NVLink and spins until rank q's contribution with the same sequence
+        // number has landed in the local inbox.  Every rank then sums the nranks
+        // contributions in rank order, so all ranks hold bit-identical totals and run the
+        // same scalar recurrence -- no NCCL call, no extra launch.  Slots alternate with the
+        // sequence parity: a rank can be at most one reduction ahead of its slowest peer.
+        __shared__ double             s_tot[ND];
+        __shared__ unsigned long long s_seq;
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int d = 0; d < ND; ++d) s_tot[d] = tot[d];
+            s_seq = *ws.seq + 1ull;
+            *ws.seq = s_seq;
+        }
+        __syncthreads();
+        const unsigned long long seq = s_seq;
+        const size_t slot = (size_t)(seq & 1ull) * ws.nranks;
+        if ((int)threadIdx.x < ws.nranks) {
+            volatile double *dst = ws.peers[threadIdx.x] + (slot + ws.rank) * 8;
+#pragma unroll
+            for (int d = 0; d < ND; ++d) dst[d] = s_tot[d];
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned long long *>(dst + 7) = seq;
+            volatile unsigned long long *flag =
+                reinterpret_cast<volatile unsigned long long *>(ws.inbox + (slot + threadIdx.x) * 8 + 7);
+            while (*flag != seq) __nanosleep(40);
+            __threadfence_system();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const volatile double *in = ws.inbox + slot * 8;
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                double a = 0.0;
+                for (int q = 0; q < ws.nranks; ++q) a = __dadd_rn(a, in[q * 8 + d]);
+                tot[d] = a;
+                ws.sums[d] = a;
+            }
+            *ws.counter = 0u;
+            fin(tot);
+        }
+        return;
+    }
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int d = 0; d < ND; ++d) ws.sums[d] = tot[d];

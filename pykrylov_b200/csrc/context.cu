@@ -105,6 +105,12 @@ ReduceWs kry_ws(kry_ctx *c)
     ws.counter = c->counter;
     ws.stride = c->partial_stride;
     ws.defer = 0;
+    ws.p2p = 0;
+    ws.nranks = c->nranks;
+    ws.rank = c->rank;
+    ws.inbox = c->p2p_inbox;
+    ws.peers = c->p2p_peers_dev;
+    ws.seq = c->p2p_seq;
     return ws;
 }
 
@@ -204,10 +210,27 @@ extern "C" int kry_launch_count(kry_ctx *c, int64_t *count)
 extern "C" int kry_ctx_set_option(kry_ctx *c, int option, int value)
 {
     KRY_REQUIRE(c, KRY_ERR_INVALID, "kry_ctx_set_option: NULL context");
-    KRY_REQUIRE(option == KRY_OPT_L2_HINTS || option == KRY_OPT_GRAPHS, KRY_ERR_INVALID,
-                "kry_ctx_set_option: unknown option %d", option);
+    KRY_REQUIRE(option == KRY_OPT_L2_HINTS || option == KRY_OPT_GRAPHS || option == KRY_OPT_P2P,
+                KRY_ERR_INVALID, "kry_ctx_set_option: unknown option %d", option);
     if (option == KRY_OPT_L2_HINTS) c->l2_hints = value;
-    else c->use_graphs = value ? 1 : 0;
+    else if (option == KRY_OPT_GRAPHS) c->use_graphs = value ? 1 : 0;
+    else {
+        KRY_REQUIRE(!value || c->p2p_inbox, KRY_ERR_STATE,
+                    "kry_ctx_set_option: peer-memory all-reduce was not set up (kry_comm_init)");
+        c->p2p_on = value ? 1 : 0;
+    }
+    return KRY_OK;
+}
+
+extern "C" int kry_ctx_get_option(kry_ctx *c, int option, int *value)
+{
+    KRY_REQUIRE(c && value, KRY_ERR_INVALID, "kry_ctx_get_option: NULL argument");
+    switch (option) {
+        case KRY_OPT_L2_HINTS: *value = c->l2_hints; break;
+        case KRY_OPT_GRAPHS: *value = c->use_graphs; break;
+        case KRY_OPT_P2P: *value = c->p2p_on; break;
+        default: kry_set_error("kry_ctx_get_option: unknown option %d", option); return KRY_ERR_INVALID;
+    }
     return KRY_OK;
 }
 

@@ -88,7 +88,8 @@ int spmv_launch(kry_csr *M, bool trans, Gather g, Epi epi, Fin fin, const int *d
     }
     KRY_TRY(kry_ctx_ensure_partials(c, grid));
     ReduceWs ws = kry_ws(c);
-    ws.defer = defer;
+    ws.defer = (defer == 1);
+    ws.p2p = (defer == 2);
     CsrView A = csr_view(*m);
     A.hints = (c->l2_hints & 2) ? 1 : 0;     // bit 1: evict_first on the CSR streams (measured harmful)
     const bool prof = ND > 0 && c->prof_ev && c->prof_n < c->prof_cap;
@@ -124,7 +125,8 @@ int vec_pass_launch(kry_ctx *c, int64_t n, Body body, Fin fin, const int *done, 
     const int grid = vec_grid(c, n, vec_pass_kernel<ND, Body, Fin>);
     KRY_TRY(kry_ctx_ensure_partials(c, grid));
     ReduceWs ws = kry_ws(c);
-    ws.defer = defer;
+    ws.defer = (defer == 1);
+    ws.p2p = (defer == 2);
     vec_pass_kernel<ND, Body, Fin><<<grid, 256, 0, c->stream>>>(n, body, ws, fin, done);
     c->launches++;
     KRY_CUDA(cudaGetLastError());

@@ -101,6 +101,7 @@ int solver_spmv(kry_solver *S, Gather g, Epi e, Fin f, const int *done, double *
 {
     if (S->sharded) {
         KRY_TRY(kry_halo_exchange(S->A, x_dev));
+        if (S->ctx->p2p_on) return spmv_launch<ND>(S->A, false, g, e, f, done, 2);   // in-kernel all-reduce
         KRY_TRY((spmv_launch<ND>(S->A, false, g, e, f, done, 1)));
         KRY_TRY(kry_allreduce_sums(S->ctx, ND));
         return finalize_launch(S->ctx, f, done);
@@ -112,6 +113,7 @@ template <int ND, class Body, class Fin>
 int solver_pass(kry_solver *S, Body b, Fin f, const int *done)
 {
     if (S->sharded) {
+        if (S->ctx->p2p_on) return vec_pass_launch<ND>(S->ctx, S->n, b, f, done, 2);
         KRY_TRY((vec_pass_launch<ND>(S->ctx, S->n, b, f, done, 1)));
         KRY_TRY(kry_allreduce_sums(S->ctx, ND));
         return finalize_launch(S->ctx, f, done);

@@ -93,6 +93,11 @@ class Context(object):
     def set_option(self, option, value):
         call("kry_ctx_set_option", self._h, int(option), int(value))
 
+    def get_option(self, option):
+        v = C.c_int(0)
+        call("kry_ctx_get_option", self._h, int(option), C.byref(v))
+        return v.value
+
     def prof_enable(self, max_samples):
         call("kry_prof_enable", self._h, int(max_samples))
 
