@@ -227,7 +227,9 @@ static int cg_iterate(kry_solver *S)
     double *Ap = solver_vec(S, "Ap");
     const int *done = &S->ds->done;
     // option bits: 1 = vector kernels, 4 = Ap store of the SpMV epilogue (2 = CSR streams, launch.cuh)
-    const int opt = S->ctx->l2_hints;
+    // measured: the vector hints pay only while one vector fits the L2 (config 2: +2 %;
+    // 5e7 / 1e8 rows: -1.5 / -2.5 %), so they are switched off for larger vectors
+    const int opt = ((int64_t)S->n * 8 <= S->ctx->l2_bytes) ? S->ctx->l2_hints : (S->ctx->l2_hints & ~1);
     KRY_TRY((solver_spmv<1>(S, GatherPlain{p}, CgEpiAp{Ap, p, (opt & 4) ? 1 : 0, 0}, CgFinAp{S->ds}, done, p)));
     CgUpdateBody ub{x, r, p, Ap, S->dinv, S->precon_mode, S->ds, 0.0, opt & 1, 0, 0};
     KRY_TRY((solver_pass<1>(S, ub, CgFinRy{S->ds, S->hist}, done)));
