@@ -94,9 +94,16 @@ extern "C" int kry_comm_allgather_host(kry_ctx *c, const void *send, void *recv,
 static int p2p_setup(kry_ctx *c)
 {
     const int P = c->nranks;
-    const size_t inbox_bytes = (size_t)2 * P * 8 * sizeof(double);
+    // cudaIpcGetMemHandle describes the *base* of the driver allocation a pointer lives in and
+    // cudaIpcOpenMemHandle returns that base: small cudaMalloc blocks are sub-allocated, so the
+    // inbox gets a dedicated 2 MiB allocation (its own base) and the mapping is verified below
+    // with a per-rank magic word before it is trusted.
+    const size_t inbox_bytes = (size_t)2 << 20;
+    const size_t magic_at = 2 * 16 * 8;                       // first double behind the slots
     KRY_TRY(kry_alloc((void **)&c->p2p_inbox, inbox_bytes));
     KRY_CUDA(cudaMemset(c->p2p_inbox, 0, inbox_bytes));
+    const double my_magic = 7777.0 + c->rank;
+    KRY_CUDA(cudaMemcpy(c->p2p_inbox + magic_at, &my_magic, sizeof(double), cudaMemcpyHostToDevice));
     KRY_TRY(kry_alloc((void **)&c->p2p_peers_dev, 16 * sizeof(double *)));
     KRY_TRY(kry_alloc((void **)&c->p2p_seq, 256));
     KRY_CUDA(cudaMemset(c->p2p_seq, 0, 256));
@@ -117,6 +124,12 @@ static int p2p_setup(kry_ctx *c)
             break;
         }
         c->p2p_peer_ptr[q] = ptr;
+        double seen = 0.0;                                    // does the mapping address rank q's inbox?
+        if (cudaMemcpy(&seen, (double *)ptr + magic_at, sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess ||
+            seen != 7777.0 + q) {
+            cudaGetLastError();
+            ok = 0;
+        }
     }
     // all ranks must agree, otherwise some would wait for peers that use NCCL
     double flag = ok ? 1.0 : 0.0, neg = -flag;
