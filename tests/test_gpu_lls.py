@@ -170,3 +170,38 @@ def test_closure_operators_through_the_bridge_on_gpu(ctx):
     ref = kr.minres_solve(S, S.matvec(np.ones(n)), precon=lambda v: v / d)
     assert mr.istop == ref.istop and abs(mr.itn - ref.itn) <= 2
     assert np.linalg.norm(mr.x - ref.x) <= 1e-5 * np.linalg.norm(ref.x)
+
+
+def test_craig_and_craigmr_on_gpu(ctx, capsys):
+    """Least-norm solvers on a consistent under-determined system: CUDA SpMV with A and the
+    device-built A^T; checked against the oracle-side NumPy bridge run of the same code
+    (bit-identical to the reference on CPU, tests/test_host_solvers.py) and self-consistency."""
+    import pykrylov_b200._engine as eng
+    from fake_bridge import FakeBridge
+    from pykrylov_b200.linop import LinearOperator, linop_from_scipy
+    from pykrylov_b200.lls import CRAIGFramework, CRAIGMRFramework
+    rng = np.random.default_rng(14)
+    R = sp.random(90, 150, density=0.1, random_state=5, format="csr")
+    R.sort_indices()
+    b = R @ rng.standard_normal(150)
+    cr = CRAIGFramework(linop_from_scipy(R, context=ctx), context=ctx)
+    cr.solve(b)
+    assert cr.optimal and np.linalg.norm(R @ cr.x - b) <= 1e-6 * np.linalg.norm(b)
+    cm = CRAIGMRFramework(linop_from_scipy(R, context=ctx), context=ctx)
+    cm.solve(b)
+    capsys.readouterr()
+    real = eng.HostBridge
+    eng.HostBridge = FakeBridge
+    try:
+        op = LinearOperator(150, 90, lambda v: R @ v, matvec_transp=lambda u: R.T @ u)
+        cr_ref = CRAIGFramework(op)
+        cr_ref.solve(b)
+        cm_ref = CRAIGMRFramework(op)
+        cm_ref.solve(b)
+    finally:
+        eng.HostBridge = real
+    capsys.readouterr()
+    assert (cr.istop, cr.itn) == (cr_ref.istop, cr_ref.itn) and abs(cr.r1norm - cr_ref.r1norm) <= 1e-9 * max(cr_ref.r1norm, 1e-30) + 1e-12
+    assert np.linalg.norm(cr.x - cr_ref.x) <= 1e-8 * np.linalg.norm(cr_ref.x)
+    assert (cm.istop, cm.itn) == (cm_ref.istop, cm_ref.itn)
+    assert np.linalg.norm(cm.x - cm_ref.x) <= 1e-8 * np.linalg.norm(cm_ref.x)

@@ -225,3 +225,37 @@ def test_lsmr_bit_identical_to_live_reference(fake):
     assert tuple(ra[1:]) == tuple(rr[1:]) and np.array_equal(ra[0], rr[0])
     z = LSMRFramework(LinearOperator(90, 150, mv, matvec_transp=rmv)).solve(np.zeros(150))
     assert z[1] == 0 and z[2] == 0 and np.array_equal(z[0], np.zeros(90))
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not generated (needs /root/reference)")
+def test_craig_and_craigmr_bit_identical_to_live_reference(fake, capsys):
+    sys.path.insert(0, REF_DIR)
+    from refpykrylov.linop import LinearOperator as RLO
+    from refpykrylov.lls import CRAIGFramework as RC, CRAIGMRFramework as RCM
+    from pykrylov_b200.linop import LinearOperator
+    from pykrylov_b200.lls import CRAIGFramework, CRAIGMRFramework
+    rng = np.random.default_rng(14)
+    R = sp.random(90, 150, density=0.1, random_state=5, format="csr")     # m < n: consistent system
+    b = R @ rng.standard_normal(150)
+    mv, rmv = (lambda v: R @ v), (lambda u: R.T @ u)
+    Md, Nd = 1.0 + rng.random(90), 1.0 + rng.random(150)
+    for kw in (dict(), dict(M=lambda u: u / Md, N=lambda v: v / Nd), dict(itnlim=12, store_resids=True),
+               dict(btol=0, etol=0, itnlim=40)):
+        a = CRAIGFramework(LinearOperator(150, 90, mv, matvec_transp=rmv))
+        r = RC(RLO(150, 90, mv, matvec_transp=rmv))
+        a.solve(b, **kw)
+        r.solve(b, **kw)
+        for k in ("istop", "itn", "r1norm", "r2norm", "Arnorm", "xnorm", "nMatvec", "optimal"):
+            assert getattr(a, k) == getattr(r, k), (k, list(kw))
+        assert np.array_equal(a.x, r.x) and np.array_equal(a.r, r.r)
+        assert a.resids == r.resids and a.dir_errors_d_window == r.dir_errors_d_window
+    for kw in (dict(), dict(M=lambda u: u / Md, N=lambda v: v / Nd), dict(itnlim=12, store_resids=True)):
+        a = CRAIGMRFramework(LinearOperator(150, 90, mv, matvec_transp=rmv))
+        r = RCM(RLO(150, 90, mv, matvec_transp=rmv))
+        a.solve(b, **kw)
+        out_a = capsys.readouterr().out
+        r.solve(b, **kw)
+        out_r = capsys.readouterr().out
+        assert (a.istop, a.itn, a.nMatvec, a.optimal) == (r.istop, r.itn, r.nMatvec, r.optimal)
+        assert np.array_equal(a.x, r.x) and a.norms == r.norms and a.dir_errors_window == r.dir_errors_window
+        assert out_a == out_r and out_a.startswith("1 ")            # the unconditional per-iteration print
