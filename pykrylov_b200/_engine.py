@@ -55,8 +55,15 @@ def check_real(op, rhs):
 
 
 def make_solver(method, plan, context=None):
+    """Device-resident iteration state for (operator, method).  The HBM slab of a solver
+    (5-10 vectors) is kept on the operator and reused by later solves with the same method,
+    so a solve does not pay a cudaMalloc/cudaFree of several hundred MB each time."""
     ctx = context or plan.csr.ctx
-    S = DeviceSolver(ctx, method, plan.csr)
+    cache = plan.csr.__dict__.setdefault("_solver_cache", {})
+    S = cache.get(method)
+    if S is None or not S._h.value or S.ctx is not ctx:
+        S = DeviceSolver(ctx, method, plan.csr)
+        cache[method] = S
     S.set_precon_diag(plan.precon_diag, plan.precon_mode)
     return S
 

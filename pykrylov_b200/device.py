@@ -236,6 +236,9 @@ class DeviceCsr(object):
         ctx._adopt(self)
 
     def _release(self):
+        for S in list(self.__dict__.get("_solver_cache", {}).values()):
+            S._release()                      # solvers reference the operator: free them first
+        self.__dict__.pop("_solver_cache", None)
         if getattr(self, "_h", None) is not None and self._h.value:
             L.lib.kry_csr_destroy(self._h)
             self._h = L.handle()
