@@ -167,14 +167,13 @@ class CRAIGFramework(KrylovMethod):
             eta = c * zeta
             xi = s * zeta
             # v /= alpha ; d = (u - beta_hat d)/alpha_hat ; r += tau d                       (:350-352)
-            ops = []
-            if scale_v:
-                ops.append(dict(z=v, u=v, a=alpha, a_div=True))
+            if scale_v:                       # (length-n vectors: their own launch)
+                ops = [dict(z=v, u=v, a=alpha, a_div=True)]
                 if N is not None:
-                    B.fused([dict(z=Nv, u=Nv, a=alpha, a_div=True)])
-            ops += [dict(z=d, u=u, w=d, a=1.0, b=-beta_hat), dict(z=d, u=d, a=alpha_hat, a_div=True),
-                    dict(z=r, u=r, w=d, a=1.0, b=tau)]
-            B.fused(ops)
+                    ops.append(dict(z=Nv, u=Nv, a=alpha, a_div=True))
+                B.fused(ops)
+            B.fused([dict(z=d, u=u, w=d, a=1.0, b=-beta_hat), dict(z=d, u=d, a=alpha_hat, a_div=True),
+                     dict(z=r, u=r, w=d, a=1.0, b=tau)])
             # wbar *= s2 ; w = c v + s wbar ; wbar = -c wbar + s v ; x += zeta w            (:360-365)
             B.fused([dict(z=wbar, u=wbar, a=s2), dict(z=w, u=v, w=wbar, a=c, b=s),
                      dict(z=wbar, u=wbar, w=v, a=-c, b=s), dict(z=x, u=x, w=w, a=1.0, b=zeta)])

@@ -52,6 +52,10 @@ class FakeBridge(object):
         return v / c if div else c * v
 
     def fused(self, ops, dots=()):
+        sizes = {v.n for o in ops for v in (o["z"], o.get("u"), o.get("w")) if v is not None}
+        sizes |= {v.n for pair in dots for v in pair}
+        if len(sizes) > 1:               # kry_multi_axpy_dot: one launch = one vector length
+            raise ValueError("kry_multi_axpy_dot: operand size mismatch %s" % sorted(sizes))
         for o in ops:
             u, w = o.get("u"), o.get("w")
             a, b = o.get("a", 1.0), o.get("b", 1.0)
