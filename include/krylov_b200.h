@@ -81,6 +81,12 @@ int kry_prof_read(kry_ctx *ctx, int64_t *samples, double *total_ms);
                                 finalize launch (default 1 when CUDA IPC mapping succeeded;
                                 must be set identically on every rank)                       */
 #define KRY_OPT_GRAPHS   2   /* replay the solver loops as CUDA graphs of 12 iterations (default 1) */
+#define KRY_OPT_CG_FUSE  4   /* CG launch plan on unsharded operators (latched at kry_solver_setup):
+                                0: 3 launches/iteration  SpMV+dot | x,r update+dot | p update
+                                1: 2 launches  [p = beta p - r]+SpMV+dot | x,r update+dot
+                                2: 2 launches  [x += alpha p ; p = beta p - r]+SpMV+dot | r update+dot
+                                The fused forms carry the p (and x) update of a trip into the SpMV of
+                                the next one; results are bit-identical to form 0.                  */
 int kry_ctx_set_option(kry_ctx *ctx, int option, int value);
 int kry_ctx_get_option(kry_ctx *ctx, int option, int *value);
 

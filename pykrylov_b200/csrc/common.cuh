@@ -89,6 +89,7 @@ struct kry_ctx {
     void               *p2p_peer_ptr[16];
     int          l2_hints;     // bit 0: CG vector kernels use L2 eviction-priority hints (default 1)
     int          use_graphs;   // 1: solver loops replay CUDA graphs of 12 iterations (default)
+    int          cg_fuse;      // KRY_OPT_CG_FUSE: CG launch plan (0: 3 launches, 1/2: fused 2-launch forms)
     // optional per-launch timing of the dominant kernel (kry_prof_*)
     cudaEvent_t *prof_ev;      // 2 * prof_cap events
     int          prof_cap, prof_n;
@@ -294,6 +295,12 @@ __device__ __forceinline__ int ldnc_hint(const int *a, uint64_t pol)
 {
     int d;
     asm("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(d) : "l"(a), "l"(pol));
+    return d;
+}
+__device__ __forceinline__ double ld_hint(const double *a, uint64_t pol)   // coherent path (data written in-kernel)
+{
+    double d;
+    asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(d) : "l"(a), "l"(pol));
     return d;
 }
 __device__ __forceinline__ double2 ld2_hint(const double *a, int i2, uint64_t pol)

@@ -68,6 +68,7 @@ extern "C" int kry_ctx_create(int device, kry_ctx **out)
     c->nranks = 1;
     c->l2_hints = 1;
     c->use_graphs = 1;
+    c->cg_fuse = 0;
     KRY_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     KRY_CUDA(cudaEventCreate(&c->ev0));
     KRY_CUDA(cudaEventCreate(&c->ev1));
@@ -210,9 +211,14 @@ extern "C" int kry_launch_count(kry_ctx *c, int64_t *count)
 extern "C" int kry_ctx_set_option(kry_ctx *c, int option, int value)
 {
     KRY_REQUIRE(c, KRY_ERR_INVALID, "kry_ctx_set_option: NULL context");
-    KRY_REQUIRE(option == KRY_OPT_L2_HINTS || option == KRY_OPT_GRAPHS || option == KRY_OPT_P2P,
+    KRY_REQUIRE(option == KRY_OPT_L2_HINTS || option == KRY_OPT_GRAPHS || option == KRY_OPT_P2P ||
+                    option == KRY_OPT_CG_FUSE,
                 KRY_ERR_INVALID, "kry_ctx_set_option: unknown option %d", option);
     if (option == KRY_OPT_L2_HINTS) c->l2_hints = value;
+    else if (option == KRY_OPT_CG_FUSE) {
+        KRY_REQUIRE(value >= 0 && value <= 2, KRY_ERR_INVALID, "kry_ctx_set_option: CG_FUSE=%d not in 0..2", value);
+        c->cg_fuse = value;
+    }
     else if (option == KRY_OPT_GRAPHS) c->use_graphs = value ? 1 : 0;
     else {
         KRY_REQUIRE(!value || c->p2p_inbox, KRY_ERR_STATE,
@@ -229,6 +235,7 @@ extern "C" int kry_ctx_get_option(kry_ctx *c, int option, int *value)
         case KRY_OPT_L2_HINTS: *value = c->l2_hints; break;
         case KRY_OPT_GRAPHS: *value = c->use_graphs; break;
         case KRY_OPT_P2P: *value = c->p2p_on; break;
+        case KRY_OPT_CG_FUSE: *value = c->cg_fuse; break;
         default: kry_set_error("kry_ctx_get_option: unknown option %d", option); return KRY_ERR_INVALID;
     }
     return KRY_OK;

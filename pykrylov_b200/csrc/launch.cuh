@@ -73,7 +73,21 @@ int spmv_launch(kry_csr *M, bool trans, Gather g, Epi epi, Fin fin, const int *d
         if (need < 1) need = 1;
         // one resident wave (8 CTAs x 256 threads per SM) measured best: 6.25 vs 5.5 TB/s with
         // 64 CTAs/SM on the 5-pt Laplacian; `threads`/32 overrides the CTAs per SM for sweeps
-        const int64_t capg = (int64_t)c->sm_count * (M->threads >= 64 && M->tile_nnz == 0 ? M->threads / 32 : 8);
+        int per_sm = (M->threads >= 64 && M->tile_nnz == 0) ? M->threads / 32 : 8;
+        if (kind == KRY_SPMV_ROW && per_sm == 8) {
+            // ... but never more CTAs than are really resident (an epilogue above 32 registers
+            // would otherwise leave a second, partial wave)
+            static int occ = 0;              // per instantiation
+            if (occ == 0) {
+                int b = 0;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, spmv_row_kernel<ND, Gather, Epi, Fin>, 256, 0) !=
+                        cudaSuccess || b < 1)
+                    b = 8;
+                occ = b;
+            }
+            if (occ < per_sm) per_sm = occ;
+        }
+        const int64_t capg = (int64_t)c->sm_count * per_sm;
         grid = (int)(need < capg ? need : capg);
     } else {
         KRY_TRY(csr_build_partition(c, *m, tile));

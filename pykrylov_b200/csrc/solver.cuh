@@ -38,6 +38,12 @@ enum {
     M_RHS1, M_RHS2, M_TNORM2, M_YNORM2, M_CS, M_SN, M_GMAX, M_GMIN, M_PHI, M_DENOM,
     M_ANORM, M_ACOND, M_YNORM, M_ARNORM, M_XNRG2, M_INVBETA, M_TEST1, M_TEST2,
     M_C_R1, M_C_R2, M_TRNC,
+    // fused CG forms (KRY_OPT_CG_FUSE): what is still owed to p and x, see cg_settle()
+    //   S_PSTATE 0: p is materialised in P[(n_iter+1)&1]
+    //            1: p = beta * P[(n_iter-1)&1] - r is pending (normal state between trips)
+    //            2: p was materialised into P[n_iter&1] by a trip that then stopped (curvature exit)
+    //   S_XPEND  1: x += alpha * P[(n_iter-1)&1] is pending (form 2)
+    S_PSTATE, S_XPEND,
     S_COUNT
 };
 constexpr int KRY_NSCAL = 64;
@@ -71,6 +77,8 @@ struct kry_solver {
     cudaGraphExec_t   graph_exec;
     int64_t           graph_launches;   // kernel launches inside one replay
     bool              warm;             // at least one iteration ran un-captured
+    int               cg_fuse;          // CG launch plan latched at setup (KRY_OPT_CG_FUSE)
+    bool              fresh;            // fused CG: nothing pending, p sits in the next trip's source buffer
 };
 
 constexpr int KRY_GRAPH_ITERS = 12;     // multiple of 6 = lcm of the MINRES buffer rotations

@@ -113,9 +113,12 @@ struct CgUpdateBody {
 struct CgFinRy {
     DevScalars *s;
     double     *hist;
+    int         fuse;        // fused forms: the p (and x) update of this trip is now owed
     __device__ void operator()(const double *t) const
     {
         const double ry_next = t[0];
+        if (fuse) s->s[S_PSTATE] = 1.0;
+        if (fuse == 2) s->s[S_XPEND] = 1.0;
         s->s[S_BETA] = ry_next / s->s[S_RY];                         // cg.py:149
         s->s[S_RY] = ry_next;                                        // cg.py:153
         const double resid = fabs(sqrt(ry_next));                    // cg.py:154
@@ -158,6 +161,150 @@ struct CgDirBody {
         pv.y = __dsub_rn(__dmul_rn(beta, pv.y), rv.y);
         if (hints) st2_hint(p, i2, pv, el);                          // gathered by the next K1
         else st2(p, i2, pv);
+    }
+};
+
+// ---- fused forms (KRY_OPT_CG_FUSE = 1, 2): 2 launches per iteration.
+// The direction update of trip i-1 (cg.py:150-151) -- and in form 2 its x update
+// (cg.py:130) -- ride in the SpMV launch of trip i: the gather forms
+// p_i[c] = beta * p_{i-1}[c] - r_i[c] on the fly for every column it touches (same
+// expression, so every copy of p_i[c] is the same bits as the stand-alone update), the
+// row's own entry is written to the other p buffer (ping-pong: neighbours still gather
+// the old one).  Per row this moves 96 B (form 1) / 112 B (form 2) in the SpMV launch
+// and 48 / 24 B in the second one, against 80 + 48 + 24 B for the 3-launch form.
+//   trip i reads P[(i+1)&1] and writes P[i&1];  PEND = false on the first trip after a
+//   setup / settle (p is already materialised there: plain copy).
+template <bool PEND>
+struct CgGatherDir {
+    const double *p_old, *r;
+    DevScalars   *s;
+    double        beta;
+    __device__ void   init() { beta = s->s[S_BETA]; }
+    __device__ double operator()(int c) const
+    {
+        const double po = __ldg(p_old + c);
+        if constexpr (PEND) return __dsub_rn(__dmul_rn(beta, po), __ldg(r + c));    // cg.py:150-151
+        else return po;
+    }
+};
+
+template <bool PEND, bool XLAG>
+struct CgEpiFused {
+    static constexpr int kMinBlocks = 8;     // keep the row kernel at 32 registers (full occupancy)
+    double       *Ap, *p_new, *x;
+    const double *p_old, *r;
+    DevScalars   *s;
+    int           hints;      // bit 0: x is a pure stream (evict_first); bit 2: keep Ap in L2
+    double        beta, alpha;
+    uint64_t      ef, el;
+    __device__ void init()
+    {
+        beta = s->s[S_BETA];
+        alpha = s->s[S_ALPHA];
+        ef = l2_policy_evict_first();
+        el = l2_policy_evict_last();
+    }
+    __device__ void operator()(int row, double ax, double *acc) const
+    {
+        const double po = __ldg(p_old + row);
+        double pn = po;
+        if constexpr (PEND) {
+            if constexpr (XLAG) {                                    // cg.py:130 of the previous trip
+                if (hints & 1) st_hint(x + row, __dadd_rn(ld_hint(x + row, ef), __dmul_rn(alpha, po)), ef);
+                else x[row] = __dadd_rn(x[row], __dmul_rn(alpha, po));
+            }
+            pn = __dsub_rn(__dmul_rn(beta, po), __ldg(r + row));     // cg.py:150-151 of the previous trip
+        }
+        p_new[row] = pn;
+        if (hints & 4) st_hint(Ap + row, ax, el);                    // the second launch reads it next
+        else Ap[row] = ax;
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(pn, ax));               // cg.py:117
+    }
+};
+
+struct CgFinApFused {
+    DevScalars *s;
+    __device__ void operator()(const double *t) const
+    {
+        s->s[S_PSTATE] = 2.0;        // p of this trip now sits in P[n_iter & 1] ...
+        s->s[S_XPEND] = 0.0;         // ... and x is up to date (until the second launch runs)
+        CgFinAp{s}(t);
+    }
+};
+
+struct CgUpdateRBody {            // form 2, second launch: r += alpha Ap ; y = M r ; ry' = r.y
+    double       *r;
+    const double *Ap, *pd;
+    int           pmode;
+    DevScalars   *s;
+    double        alpha;
+    int           hints;
+    uint64_t      ef, el;
+    __device__ void init()
+    {
+        alpha = s->s[S_ALPHA];
+        ef = l2_policy_evict_first();
+        el = l2_policy_evict_last();
+    }
+    __device__ void operator()(int i, double *acc) const
+    {
+        const double rn = __dadd_rn(r[i], __dmul_rn(alpha, Ap[i]));  // cg.py:131
+        r[i] = rn;
+        const double y = apply_diag(pd, pmode, i, rn);               // cg.py:137-140
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(rn, y));                // cg.py:146
+    }
+    static constexpr bool kPair = true;
+    __device__ void pair(int i2, double *acc) const
+    {
+        double2 rv, av;
+        if (hints) {
+            rv = ld2_hint(r, i2, ef);
+            av = ld2_hint(Ap, i2, ef);
+        } else {
+            rv = ld2(r, i2);
+            av = ld2(Ap, i2);
+        }
+        rv.x = __dadd_rn(rv.x, __dmul_rn(alpha, av.x));
+        rv.y = __dadd_rn(rv.y, __dmul_rn(alpha, av.y));
+        if (hints) st2_hint(r, i2, rv, el);                          // gathered by the next SpMV launch
+        else st2(r, i2, rv);
+        const double y0 = apply_diag(pd, pmode, 2 * i2, rv.x), y1 = apply_diag(pd, pmode, 2 * i2 + 1, rv.y);
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(rv.x, y0));
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(rv.y, y1));
+    }
+};
+
+// Pay what the fused forms still owe (driven by the device flags, so it is right
+// whichever launch latched `done`): afterwards x is current and p is materialised
+// in P[(n_iter+1)&1], i.e. exactly the state of the 3-launch form.
+struct CgSettleBody {
+    double       *x, *P0, *P1;
+    const double *r;
+    DevScalars   *s;
+    double       *base, *other;
+    double        alpha, beta;
+    int           pstate, xpend;
+    __device__ void init()
+    {
+        const long long n = s->n_iter;
+        pstate = (int)s->s[S_PSTATE];
+        xpend = (int)s->s[S_XPEND];
+        alpha = s->s[S_ALPHA];
+        beta = s->s[S_BETA];
+        // pstate 1: base = P[(n-1)&1] == P[(n+1)&1], updated in place
+        // pstate 2: base = P[n&1] is copied to other = P[(n+1)&1]
+        base = (pstate == 2) ? ((n & 1) ? P1 : P0) : (((n + 1) & 1) ? P1 : P0);
+        other = (base == P0) ? P1 : P0;
+    }
+    __device__ void operator()(int i) const
+    {
+        if (pstate == 1) {
+            const double po = base[i];
+            if (xpend) x[i] = __dadd_rn(x[i], __dmul_rn(alpha, po));           // cg.py:130
+            base[i] = __dsub_rn(__dmul_rn(beta, po), r[i]);                    // cg.py:150-151
+        } else if (pstate == 2) {
+            other[i] = base[i];
+        }
     }
 };
 
@@ -212,6 +359,9 @@ static int cg_setup(kry_solver *S, int guess)
 {
     double *x = solver_vec(S, "x"), *r = solver_vec(S, "r"), *p = solver_vec(S, "p");
     double *rhs = solver_vec(S, "rhs");
+    S->cg_fuse = S->sharded ? 0 : S->ctx->cg_fuse;     // shards keep the 3-launch form (halo carries p)
+    S->fresh = true;
+    S->rot = 0;
     CgSetupFin fin{S->ds, S->hist, guess};
     if (guess) {
         CgSetupEpi e{r, p, rhs, S->dinv, S->precon_mode};
@@ -219,6 +369,15 @@ static int cg_setup(kry_solver *S, int guess)
     }
     CgSetupBody b{r, p, rhs, S->dinv, S->precon_mode};
     return solver_pass<1>(S, b, fin, &S->ds->done);
+}
+
+template <bool PEND, bool XLAG>
+static int cg_fused_spmv(kry_solver *S, double *p_old, double *p_new, int opt)
+{
+    double *x = solver_vec(S, "x"), *r = solver_vec(S, "r"), *Ap = solver_vec(S, "Ap");
+    CgGatherDir<PEND> g{p_old, r, S->ds, 0.0};
+    CgEpiFused<PEND, XLAG> e{Ap, p_new, x, p_old, r, S->ds, opt & 5, 0.0, 0.0, 0, 0};
+    return solver_spmv<1>(S, g, e, CgFinApFused{S->ds}, &S->ds->done, p_old);
 }
 
 static int cg_iterate(kry_solver *S)
@@ -230,11 +389,46 @@ static int cg_iterate(kry_solver *S)
     // measured: the vector hints pay only while one vector fits the L2 (config 2: +2 %;
     // 5e7 / 1e8 rows: -1.5 / -2.5 %), so they are switched off for larger vectors
     const int opt = ((int64_t)S->n * 8 <= S->ctx->l2_bytes) ? S->ctx->l2_hints : (S->ctx->l2_hints & ~1);
+    if (S->cg_fuse) {
+        // trip i = S->rot reads P[(i+1)&1] and writes P[i&1];  P[1] = "p", P[0] = "p2"
+        double *P[2] = {solver_vec(S, "p2"), p};
+        double *p_old = P[(S->rot + 1) & 1], *p_new = P[S->rot & 1];
+        const bool pend = !S->fresh, xlag = (S->cg_fuse == 2);
+        int rc;
+        if (!pend) rc = cg_fused_spmv<false, false>(S, p_old, p_new, opt);
+        else if (xlag) rc = cg_fused_spmv<true, true>(S, p_old, p_new, opt);
+        else rc = cg_fused_spmv<true, false>(S, p_old, p_new, opt);
+        KRY_TRY(rc);
+        S->fresh = false;
+        S->rot++;
+        CgFinRy fin{S->ds, S->hist, S->cg_fuse};
+        if (xlag) {
+            CgUpdateRBody ub{r, Ap, S->dinv, S->precon_mode, S->ds, 0.0, opt & 1, 0, 0};
+            return solver_pass<1>(S, ub, fin, done);
+        }
+        CgUpdateBody ub{x, r, p_new, Ap, S->dinv, S->precon_mode, S->ds, 0.0, opt & 1, 0, 0};
+        return solver_pass<1>(S, ub, fin, done);
+    }
     KRY_TRY((solver_spmv<1>(S, GatherPlain{p}, CgEpiAp{Ap, p, (opt & 4) ? 1 : 0, 0}, CgFinAp{S->ds}, done, p)));
     CgUpdateBody ub{x, r, p, Ap, S->dinv, S->precon_mode, S->ds, 0.0, opt & 1, 0, 0};
-    KRY_TRY((solver_pass<1>(S, ub, CgFinRy{S->ds, S->hist}, done)));
+    KRY_TRY((solver_pass<1>(S, ub, CgFinRy{S->ds, S->hist, 0}, done)));
     CgDirBody db{p, r, S->ds, 0.0, opt & 1, 0, 0};
     return vec_map_launch(S->ctx, S->n, db, done);
+}
+
+// Fused forms only: bring x and p to the state the 3-launch form would hold (see
+// CgSettleBody).  Called before any vector of the solver is read or written from
+// outside; the next trip then starts from a materialised p again.
+static int cg_settle(kry_solver *S)
+{
+    if (S->method != KRY_CG || !S->cg_fuse || !S->ready) return KRY_OK;
+    CgSettleBody b{solver_vec(S, "x"), solver_vec(S, "p2"), solver_vec(S, "p"), solver_vec(S, "r"), S->ds,
+                   nullptr, nullptr, 0.0, 0.0, 0, 0};
+    KRY_TRY(vec_map_launch(S->ctx, S->n, b, &S->ctx->never_done[0]));
+    KRY_CUDA(cudaMemsetAsync(&S->ds->s[S_PSTATE], 0, 2 * sizeof(double), S->ctx->stream));
+    S->fresh = true;
+    S->warm = false;      // the next trip must run un-captured (it is the PEND = false variant)
+    return KRY_OK;
 }
 
 // ================================================================ Bi-CGSTAB
@@ -1270,7 +1464,8 @@ struct VecSpec {
 
 static const VecSpec *method_vectors(kry_method m, int *count)
 {
-    static const VecSpec cg[] = {{"x", true}, {"p", true}, {"r", false}, {"Ap", false}, {"rhs", false}};
+    static const VecSpec cg[] = {{"x", true}, {"p", true}, {"r", false}, {"Ap", false}, {"rhs", false},
+                                 {"p2", true}};     // second p buffer of the fused forms (ping-pong)
     static const VecSpec bcg[] = {{"x", true}, {"p", true}, {"s", true}, {"q", true}, {"z", true},
                                   {"r0", false}, {"r", false}, {"v", false}, {"t", false}, {"rhs", false}};
     static const VecSpec cgs[] = {{"x", true}, {"p", true}, {"z", true}, {"y", true}, {"r0", false},
@@ -1280,7 +1475,7 @@ static const VecSpec *method_vectors(kry_method m, int *count)
     static const VecSpec mr[] = {{"x", false}, {"ra", true}, {"rb", true}, {"rc", true},
                                  {"wa", false}, {"wb", false}, {"rhs", false}};
     switch (m) {
-        case KRY_CG: *count = 5; return cg;
+        case KRY_CG: *count = 6; return cg;
         case KRY_BICGSTAB: *count = 10; return bcg;
         case KRY_CGS: *count = 10; return cgs;
         case KRY_TFQMR: *count = 9; return tfq;
@@ -1608,6 +1803,7 @@ extern "C" int kry_solver_history(kry_solver *S, int64_t first, int64_t count, d
 extern "C" int kry_solver_solution(kry_solver *S, double *x_host)
 {
     KRY_REQUIRE(S && x_host, KRY_ERR_INVALID, "kry_solver_solution: NULL argument");
+    KRY_TRY(cg_settle(S));
     KRY_CUDA(cudaMemcpyAsync(x_host, solver_vec(S, "x"), (size_t)S->n * sizeof(double),
                              cudaMemcpyDeviceToHost, S->ctx->stream));
     KRY_CUDA(cudaStreamSynchronize(S->ctx->stream));
@@ -1629,12 +1825,20 @@ static double *solver_vec_logical(kry_solver *S, const char *name)
         if (!strcmp(name, "w")) return solver_vec(S, W[j]);
         if (!strcmp(name, "w2")) return solver_vec(S, W[1 - j]);
     }
+    if (S->method == KRY_CG && S->cg_fuse && !strcmp(name, "p")) {
+        // after cg_settle(): p lives in P[(n_iter+1)&1] with P[1] = "p", P[0] = "p2"
+        long long itn = 0;
+        cudaMemcpyAsync(&itn, &S->ds->n_iter, sizeof(itn), cudaMemcpyDeviceToHost, S->ctx->stream);
+        cudaStreamSynchronize(S->ctx->stream);
+        return solver_vec(S, ((itn + 1) & 1) ? "p" : "p2");
+    }
     return solver_vec(S, name);
 }
 
 extern "C" int kry_solver_get_vector(kry_solver *S, const char *name, double *host)
 {
     KRY_REQUIRE(S && name && host, KRY_ERR_INVALID, "kry_solver_get_vector: NULL argument");
+    KRY_TRY(cg_settle(S));
     double *d = solver_vec_logical(S, name);
     KRY_REQUIRE(d, KRY_ERR_INVALID, "kry_solver_get_vector: no vector named '%s'", name);
     KRY_CUDA(cudaMemcpyAsync(host, d, (size_t)S->n * sizeof(double), cudaMemcpyDeviceToHost,
@@ -1646,6 +1850,7 @@ extern "C" int kry_solver_get_vector(kry_solver *S, const char *name, double *ho
 extern "C" int kry_solver_set_vector(kry_solver *S, const char *name, const double *host)
 {
     KRY_REQUIRE(S && name && host, KRY_ERR_INVALID, "kry_solver_set_vector: NULL argument");
+    KRY_TRY(cg_settle(S));
     double *d = solver_vec_logical(S, name);
     KRY_REQUIRE(d, KRY_ERR_INVALID, "kry_solver_set_vector: no vector named '%s'", name);
     KRY_CUDA(cudaMemcpyAsync(d, host, (size_t)S->n * sizeof(double), cudaMemcpyHostToDevice,

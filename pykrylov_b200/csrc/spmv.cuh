@@ -63,8 +63,15 @@ struct GatherScaled {
 };
 
 // ------------------------------------------------------------ thread per row
+// Resident CTAs per SM an epilogue asks the row kernel to be compiled for (register cap
+// 65536 / (256 * n)); 1 = no constraint beyond the 256-thread block.
+template <class E, class = void>
+struct epi_min_blocks : std::integral_constant<int, 1> {};
+template <class E>
+struct epi_min_blocks<E, std::void_t<decltype(E::kMinBlocks)>> : std::integral_constant<int, E::kMinBlocks> {};
+
 template <int ND, class Gather, class Epi, class Fin>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, epi_min_blocks<Epi>::value)
 spmv_row_kernel(CsrView A, Gather g, Epi epi, ReduceWs ws, Fin fin, const int *done)
 {
     if (*done) return;

@@ -209,6 +209,16 @@ def test_reduction_is_deterministic(ctx):
 
 
 # ==================================================== single-step solver parity
+@pytest.fixture(params=[0, 1, 2], ids=["cg3launch", "cgfuse1", "cgfuse2"])
+def cg_form(ctx, request):
+    """Every CG test runs under the three launch plans (KRY_OPT_CG_FUSE): the 3-launch
+    form and the two fused 2-launch forms must be indistinguishable from outside."""
+    default = ctx.get_option(L().KRY_OPT_CG_FUSE)
+    ctx.set_option(L().KRY_OPT_CG_FUSE, request.param)
+    yield request.param
+    ctx.set_option(L().KRY_OPT_CG_FUSE, default)
+
+
 def cg_case(name):
     M = fixtures()[name]
     n = M.shape[0]
@@ -217,7 +227,7 @@ def cg_case(name):
 
 
 @pytest.mark.parametrize("name,precon", [("1138bus", 0), ("poisson2d_123", 0), ("1138bus", 1), ("1138bus", 2)])
-def test_cg_single_step_from_identical_state(ctx, name, precon):
+def test_cg_single_step_from_identical_state(ctx, name, precon, cg_form):
     M, rhs, guess = cg_case(name)
     n = M.shape[0]
     d = np.abs(M.to_scipy().diagonal())
@@ -413,7 +423,7 @@ def test_minres_single_step_from_identical_state(ctx, shift):
 
 
 # ================================================= trajectories and known answers
-def test_cg_trajectory_poisson2d(ctx, golden):
+def test_cg_trajectory_poisson2d(ctx, golden, cg_form):
     g = 100
     ip, ix, dv = kr.poisson2d_csr(g)
     M = CsrRef((g * g, g * g), ip, ix, dv)
@@ -536,7 +546,7 @@ def test_minres_public_api(ctx, golden, capsys):
 
 
 # ================================================================ edge cases
-def test_cg_edge_cases(ctx):
+def test_cg_edge_cases(ctx, cg_form):
     from pykrylov_b200.linop import csr_operator
     from pykrylov_b200.cg import CG
     # zero right-hand side: converged at entry, x = 0, no product
@@ -581,7 +591,7 @@ def test_cg_edge_cases(ctx):
     assert len(cg.iterates) == cg.nMatvec + 1 and len(cg.resids) == cg.nMatvec + 1
 
 
-def test_cg_jacobi_precon_reproduces_reference_quirk(ctx, golden):
+def test_cg_jacobi_precon_reproduces_reference_quirk(ctx, golden, cg_form):
     """cg.py:104,150-151 build p from r, not from the preconditioned residual; with a
     Jacobi preconditioner on 1138bus the reference therefore stalls until matvec_max."""
     from pykrylov_b200.linop import csr_operator, DiagonalOperator
@@ -594,6 +604,46 @@ def test_cg_jacobi_precon_reproduces_reference_quirk(ctx, golden):
     assert cg.nMatvec == rec["nMatvec"] and cg.converged == rec["converged"]
     assert srel(cg.residNorm0, rec["residNorm0"]) <= 1e-13
     assert rel(cg.residHistory[:10], rec["residHistory"][:10]) <= 1e-10
+
+
+@pytest.mark.parametrize("name,precon,guess", [("poisson2d_123", 0, False), ("1138bus", 0, True),
+                                               ("1138bus", 2, True), ("GD97_b", 1, False)])
+def test_cg_fused_forms_are_bit_identical_to_the_3_launch_form(ctx, name, precon, guess):
+    """The fused forms only move work between launches: after any number of iterations --
+    read in the middle of a run or at the end, through CUDA-graph replays or single
+    launches -- x, r, p, Ap, every scalar and the residual history are the same bits."""
+    M = fixtures()[name]
+    n = M.shape[0]
+    rng = np.random.default_rng(31)
+    rhs = M.matvec(np.ones(n))
+    x0 = rng.standard_normal(n) if guess else None
+    d = np.abs(M.to_scipy().diagonal()) + 1.0
+    A = upload(ctx, M, symmetric=True)
+    default = ctx.get_option(L().KRY_OPT_CG_FUSE)
+    out = {}
+    try:
+        for form in (0, 1, 2):
+            ctx.set_option(L().KRY_OPT_CG_FUSE, form)
+            S = dev().DeviceSolver(ctx, "cg", A)
+            S.set_precon_diag(d if precon else None, precon)
+            S.setup(rhs, guess=x0, abstol=0.0, reltol=0.0, matvec_max=10 ** 6, check_curvature=False)
+            snaps = []
+            for chunk in (1, 2, 40, 3, 31):          # 40 and 31 go through the graph replay path
+                S.iterate(chunk)
+                st = S.status()
+                snaps.append((st.n_iter, st.n_matvec, st.resid_norm, tuple(st.aux[:4]),
+                              S.get_vector("x"), S.get_vector("r"), S.get_vector("p"), S.get_vector("Ap")))
+            snaps.append(S.drain_history())
+            out[form] = snaps
+            S._release()
+    finally:
+        ctx.set_option(L().KRY_OPT_CG_FUSE, default)
+    for form in (1, 2):
+        for a, b in zip(out[0][:-1], out[form][:-1]):
+            assert a[:4] == b[:4], (form, a[:4], b[:4])
+            for u, v in zip(a[4:], b[4:]):
+                assert np.array_equal(u, v, equal_nan=True), form
+        assert np.array_equal(out[0][-1], out[form][-1], equal_nan=True)
 
 
 def test_bicgstab_breakdown_runs_to_matvec_max_like_reference(ctx):
@@ -683,7 +733,7 @@ def test_fullsize_kernels_agree_bitwise_and_operator_is_symmetric(ctx, big):
     assert np.sqrt(s[0] / s[1]) <= 1e-14
 
 
-def test_fullsize_cg_residual_recurrence_is_consistent(ctx, big):
+def test_fullsize_cg_residual_recurrence_is_consistent(ctx, big, cg_form):
     g, A = big
     n = g * g
     ones = dev().DeviceVector(ctx, n).fill(1.0)

@@ -351,3 +351,47 @@ def test_krylov_method_contract():
     assert k.residHistory == [] and k.x is None
     with pytest.raises(NotImplementedError):
         k.solve(np.ones(2))
+
+
+def test_pinned_result_pool_recycles_blocks_and_respects_caps():
+    """device.PinnedPool hands out NumPy arrays backed by page-locked blocks and takes the
+    block back when the last view dies (allocator injected: no GPU needed here)."""
+    import ctypes as C
+    import gc
+    from pykrylov_b200.device import PinnedPool
+    libc = C.CDLL(None)
+    libc.malloc.restype = C.c_void_p
+    libc.malloc.argtypes = [C.c_size_t]
+    libc.free.argtypes = [C.c_void_p]
+    freed = []
+    pool = PinnedPool(alloc=lambda nb: libc.malloc(nb), free=lambda p: (freed.append(p), libc.free(p)),
+                      min_bytes=1024, live_cap=10 << 20, idle_cap=3 << 20)
+    a = pool.empty(1000)
+    assert a.shape == (1000,) and a.dtype == np.float64 and a.flags.writeable and a.flags.c_contiguous
+    assert pool.live_bytes == 1 << 20 and pool.misses == 1
+    a[:] = 3.0
+    view = a[10:20]
+    del a
+    gc.collect()
+    assert pool.live_bytes == 1 << 20 and view.sum() == 30.0       # a view keeps the block alive
+    del view
+    gc.collect()
+    assert pool.live_bytes == 0 and pool.idle_bytes == 1 << 20 and not freed
+    b = pool.empty(1000)                                            # same size class: recycled
+    assert pool.hits == 1 and pool.idle_bytes == 0
+    assert pool.empty(10).base is None                              # below min_bytes: ordinary array
+    many = [pool.empty(300000) for _ in range(5)]                   # 3 MiB each; live cap 10 MiB
+    assert [m.base is not None for m in many] == [True, True, True, False, False]
+    del many, b
+    gc.collect()
+    assert pool.live_bytes == 0 and pool.idle_bytes <= 3 << 20 and len(freed) >= 1   # idle cap: rest unpinned
+    # astype(copy=False) -- what the solvers do with the solution -- keeps the block
+    x = pool.empty(2000).astype(np.float64, copy=False)
+    assert x.base is not None
+    del x
+    gc.collect()
+    pool.trim()
+    assert pool.idle_bytes == 0
+    # a failing allocator (no GPU / out of pinned memory) falls back to pageable arrays
+    none = PinnedPool(alloc=lambda nb: None, free=lambda p: None, min_bytes=8)
+    assert none.empty(100).base is None and none.live_bytes == 0
