@@ -323,6 +323,7 @@ __global__ void remap_cols_kernel(int *col, int nnz, int lo, int hi, const int *
 extern "C" int kry_csr_shard_finalize(kry_csr *M, int64_t n_global, int64_t row_begin)
 {
     KRY_REQUIRE(M, KRY_ERR_INVALID, "kry_csr_shard_finalize: NULL operator");
+    KRY_CTX_LIVE(M->ctx, "kry_csr_shard_finalize");
     KRY_REQUIRE(!M->halo.active, KRY_ERR_STATE, "kry_csr_shard_finalize: already finalised");
     kry_ctx *c = M->ctx;
     const int P = c->nranks, me = c->rank;

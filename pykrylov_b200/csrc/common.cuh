@@ -90,6 +90,11 @@ struct kry_ctx {
     int          l2_hints;     // bit 0: CG vector kernels use L2 eviction-priority hints (default 1)
     int          use_graphs;   // 1: solver loops replay CUDA graphs of 12 iterations (default)
     int          cg_fuse;      // KRY_OPT_CG_FUSE: CG launch plan (0: 3 launches, 1/2: fused 2-launch forms)
+    // lifetime: vectors / operators / solvers hold a reference; kry_ctx_destroy releases the
+    // device resources at once but the struct itself lives until the last child is destroyed,
+    // so handles may be destroyed in any order (interpreter shutdown does exactly that)
+    int          refs;
+    int          closed;
     // optional per-launch timing of the dominant kernel (kry_prof_*)
     cudaEvent_t *prof_ev;      // 2 * prof_cap events
     int          prof_cap, prof_n;
@@ -137,6 +142,11 @@ struct kry_vec {
 };
 
 int  kry_ctx_ensure_partials(kry_ctx *ctx, int nblocks);
+void kry_ctx_retain(kry_ctx *ctx);
+void kry_ctx_release(kry_ctx *ctx);     // child destroyed: frees a closed context with the last one
+// every entry point that touches the device through a child handle starts with this
+#define KRY_CTX_LIVE(ctx, who)                                                      \
+    KRY_REQUIRE(!(ctx)->closed, KRY_ERR_STATE, "%s: the context of this handle was destroyed", who)
 int  kry_alloc(void **p, size_t bytes);
 ReduceWs kry_ws(kry_ctx *ctx);
 

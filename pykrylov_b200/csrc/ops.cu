@@ -25,6 +25,7 @@ struct EpiStoreDots {
 static int check_spmv_args(const char *who, kry_csr *A, int trans, const kry_vec *x, const kry_vec *y)
 {
     KRY_REQUIRE(A && x && y, KRY_ERR_INVALID, "%s: NULL argument", who);
+    KRY_CTX_LIVE(A->ctx, who);
     KRY_REQUIRE(x->ctx == A->ctx && y->ctx == A->ctx, KRY_ERR_INVALID,
                 "%s: operands belong to different contexts", who);
     KRY_REQUIRE(x->d != y->d, KRY_ERR_INVALID, "%s: x and y must not alias", who);

@@ -510,6 +510,7 @@ struct BcgFinS {
 };
 
 struct BcgEpiT {
+    static constexpr int kMinBlocks = 8;     // 32 registers: the row kernel needs full occupancy
     double       *t;
     const double *sv, *r0;
     __device__ void init() {}
@@ -779,6 +780,7 @@ struct CgsBodyQ {
 };
 
 struct CgsEpiR {
+    static constexpr int kMinBlocks = 8;     // 32 registers: the row kernel needs full occupancy
     double       *r;
     const double *r0;
     DevScalars   *s;
@@ -1534,6 +1536,7 @@ extern "C" int kry_solver_create(kry_ctx *c, kry_method method, kry_csr *A, kry_
     S->nvecs = nv;
     S->dinv = S->slab + off;
     S->precon_mode = 0;
+    kry_ctx_retain(c);
     *out = S;
     return KRY_OK;
 }
@@ -1541,11 +1544,12 @@ extern "C" int kry_solver_create(kry_ctx *c, kry_method method, kry_csr *A, kry_
 extern "C" int kry_solver_destroy(kry_solver *S)
 {
     if (!S) return KRY_OK;
-    cudaStreamSynchronize(S->ctx->stream);
+    if (!S->ctx->closed) cudaStreamSynchronize(S->ctx->stream);
     solver_drop_graph(S);
     cudaFree(S->slab);
     cudaFree(S->ds);
     cudaFree(S->hist);
+    kry_ctx_release(S->ctx);
     delete S;
     return KRY_OK;
 }
@@ -1553,6 +1557,7 @@ extern "C" int kry_solver_destroy(kry_solver *S)
 extern "C" int kry_solver_set_precon_diag(kry_solver *S, const double *diag_host, int mode)
 {
     KRY_REQUIRE(S, KRY_ERR_INVALID, "kry_solver_set_precon_diag: NULL solver");
+    KRY_CTX_LIVE(S->ctx, "kry_solver_set_precon_diag");
     if (!diag_host || mode == 0) {
         S->precon_mode = 0;
         return KRY_OK;
@@ -1606,6 +1611,7 @@ extern "C" int kry_solver_setup(kry_solver *S, const double *rhs_host, const dou
                                 const kry_solver_params *params)
 {
     KRY_REQUIRE(S && rhs_host, KRY_ERR_INVALID, "kry_solver_setup: NULL argument");
+    KRY_CTX_LIVE(S->ctx, "kry_solver_setup");
     KRY_CUDA(cudaSetDevice(S->ctx->device));
     cudaStream_t st = S->ctx->stream;
     const size_t bytes = (size_t)S->n * sizeof(double);
@@ -1622,6 +1628,7 @@ extern "C" int kry_solver_setup_dev(kry_solver *S, const kry_vec *rhs, const kry
                                     const kry_solver_params *params)
 {
     KRY_REQUIRE(S && rhs, KRY_ERR_INVALID, "kry_solver_setup_dev: NULL argument");
+    KRY_CTX_LIVE(S->ctx, "kry_solver_setup_dev");
     KRY_REQUIRE(rhs->n == S->n && (!guess || guess->n == S->n), KRY_ERR_SHAPE,
                 "kry_solver_setup_dev: rhs/guess size does not match the operator (%lld rows)",
                 (long long)S->n);
@@ -1685,6 +1692,7 @@ static int solver_capture_graph(kry_solver *S)
 extern "C" int kry_solver_iterate(kry_solver *S, int64_t n_iters)
 {
     KRY_REQUIRE(S, KRY_ERR_INVALID, "kry_solver_iterate: NULL solver");
+    KRY_CTX_LIVE(S->ctx, "kry_solver_iterate");
     KRY_REQUIRE(S->ready, KRY_ERR_STATE, "kry_solver_iterate: call kry_solver_setup first");
     KRY_REQUIRE(n_iters >= 0 && n_iters < KRY_HIST_CAP / 2, KRY_ERR_INVALID,
                 "kry_solver_iterate: n_iters=%lld not in [0,%d)", (long long)n_iters, KRY_HIST_CAP / 2);
@@ -1719,6 +1727,7 @@ extern "C" int kry_solver_iterate(kry_solver *S, int64_t n_iters)
 extern "C" int kry_solver_status_read(kry_solver *S, kry_solver_status *out)
 {
     KRY_REQUIRE(S && out, KRY_ERR_INVALID, "kry_solver_status_read: NULL argument");
+    KRY_CTX_LIVE(S->ctx, "kry_solver_status_read");
     DevScalars h;
     KRY_CUDA(cudaMemcpyAsync(&h, S->ds, sizeof(h), cudaMemcpyDeviceToHost, S->ctx->stream));
     KRY_CUDA(cudaStreamSynchronize(S->ctx->stream));
@@ -1782,6 +1791,7 @@ extern "C" int kry_solver_history(kry_solver *S, int64_t first, int64_t count, d
                                   int32_t *width)
 {
     KRY_REQUIRE(S && (host || count == 0), KRY_ERR_INVALID, "kry_solver_history: NULL argument");
+    KRY_CTX_LIVE(S->ctx, "kry_solver_history");
     if (width) *width = S->hist_width;
     KRY_REQUIRE(first >= 0 && count >= 0 && count <= KRY_HIST_CAP, KRY_ERR_INVALID,
                 "kry_solver_history: range [%lld,+%lld) invalid", (long long)first, (long long)count);
@@ -1803,6 +1813,7 @@ extern "C" int kry_solver_history(kry_solver *S, int64_t first, int64_t count, d
 extern "C" int kry_solver_solution(kry_solver *S, double *x_host)
 {
     KRY_REQUIRE(S && x_host, KRY_ERR_INVALID, "kry_solver_solution: NULL argument");
+    KRY_CTX_LIVE(S->ctx, "kry_solver_solution");
     KRY_TRY(cg_settle(S));
     KRY_CUDA(cudaMemcpyAsync(x_host, solver_vec(S, "x"), (size_t)S->n * sizeof(double),
                              cudaMemcpyDeviceToHost, S->ctx->stream));
@@ -1838,6 +1849,7 @@ static double *solver_vec_logical(kry_solver *S, const char *name)
 extern "C" int kry_solver_get_vector(kry_solver *S, const char *name, double *host)
 {
     KRY_REQUIRE(S && name && host, KRY_ERR_INVALID, "kry_solver_get_vector: NULL argument");
+    KRY_CTX_LIVE(S->ctx, "kry_solver_get_vector");
     KRY_TRY(cg_settle(S));
     double *d = solver_vec_logical(S, name);
     KRY_REQUIRE(d, KRY_ERR_INVALID, "kry_solver_get_vector: no vector named '%s'", name);
@@ -1850,6 +1862,7 @@ extern "C" int kry_solver_get_vector(kry_solver *S, const char *name, double *ho
 extern "C" int kry_solver_set_vector(kry_solver *S, const char *name, const double *host)
 {
     KRY_REQUIRE(S && name && host, KRY_ERR_INVALID, "kry_solver_set_vector: NULL argument");
+    KRY_CTX_LIVE(S->ctx, "kry_solver_set_vector");
     KRY_TRY(cg_settle(S));
     double *d = solver_vec_logical(S, name);
     KRY_REQUIRE(d, KRY_ERR_INVALID, "kry_solver_set_vector: no vector named '%s'", name);
@@ -1905,6 +1918,7 @@ static int scalar_locate(kry_solver *S, const char *name, void **addr, int *kind
 extern "C" int kry_solver_get_scalar(kry_solver *S, const char *name, double *value)
 {
     KRY_REQUIRE(S && name && value, KRY_ERR_INVALID, "kry_solver_get_scalar: NULL argument");
+    KRY_CTX_LIVE(S->ctx, "kry_solver_get_scalar");
     void *addr = nullptr;
     int kind = 0;
     KRY_TRY(scalar_locate(S, name, &addr, &kind));
@@ -1922,6 +1936,7 @@ extern "C" int kry_solver_get_scalar(kry_solver *S, const char *name, double *va
 extern "C" int kry_solver_set_scalar(kry_solver *S, const char *name, double value)
 {
     KRY_REQUIRE(S && name, KRY_ERR_INVALID, "kry_solver_set_scalar: NULL argument");
+    KRY_CTX_LIVE(S->ctx, "kry_solver_set_scalar");
     void *addr = nullptr;
     int kind = 0;
     KRY_TRY(scalar_locate(S, name, &addr, &kind));

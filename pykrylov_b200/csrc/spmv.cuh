@@ -64,9 +64,9 @@ struct GatherScaled {
 
 // ------------------------------------------------------------ thread per row
 // Resident CTAs per SM an epilogue asks the row kernel to be compiled for (register cap
-// 65536 / (256 * n)); 1 = no constraint beyond the 256-thread block.
+// 65536 / (256 * n)); 0 = no constraint beyond the 256-thread block (same as omitting it).
 template <class E, class = void>
-struct epi_min_blocks : std::integral_constant<int, 1> {};
+struct epi_min_blocks : std::integral_constant<int, 0> {};
 template <class E>
 struct epi_min_blocks<E, std::void_t<decltype(E::kMinBlocks)>> : std::integral_constant<int, E::kMinBlocks> {};
 

@@ -60,6 +60,10 @@ def emit(**kw):
     print(json.dumps(kw), flush=True)
 
 
+def note(msg):
+    print("[bench_configs] " + msg, file=sys.stderr, flush=True)
+
+
 def config0(ctx):
     import scipy.sparse as sp
     shape, ip, ix, dv, sym = read_mtx(os.path.join(GOLD, "1138bus.mtx"))
@@ -149,6 +153,7 @@ def config3(ctx):
     import scipy.sparse as sp
     m = 215
     n = m ** 3
+    note("config3: building the 7-pt operator and its transpose on device")
     A = DeviceCsr.convdiff3d(ctx, m, 0.5, build_transpose=True)
     ones = DeviceVector(ctx, n).fill(1.0)
     rhs = DeviceVector(ctx, n)
@@ -157,6 +162,7 @@ def config3(ctx):
     ms, _ = time_device(ctx, S, lambda: S.setup_dev(rhs, abstol=0.0, reltol=0.0, matvec_max=10 ** 12), 100, 10)
     spmv_b = 12 * A.nnz + 4 * (n + 1) + 16 * n
     it_bytes = 2 * spmv_b + 120 * n
+    note("config3: %.4f ms per Bi-CGSTAB iteration; timing A x / A^T x" % ms)
     # A^T x and A x stand-alone
     y = DeviceVector(ctx, n)
     res = {}
@@ -169,13 +175,15 @@ def config3(ctx):
             A.spmv(ones, y, trans=bool(trans))
         t = ctx.timer_stop() / 20
         res["spmv_T" if trans else "spmv"] = {"ms": t, "GBs": spmv_b / t / 1e6, "frac_of_peak": spmv_b / t / 1e6 / peak()}
+    note("config3: " + json.dumps(res))
     # to convergence, reltol 1e-8, zero guess, device-resident
-    S.setup_dev(rhs, abstol=1e-8, reltol=1e-8, matvec_max=2 * n)
+    S.setup_dev(rhs, abstol=1e-8, reltol=1e-8, matvec_max=20000)      # bounded: never hours on a GPU box
     t0 = time.perf_counter()
     st = S.run(32)
     solve_s = time.perf_counter() - t0
     x = S.solution()
-    # CPU reference: bounded sample (10 iterations) on the same operator
+    note("config3: solve %.3f s, %d matvecs, resid %.3e, done=%d" % (solve_s, st.n_matvec, st.resid_norm, st.done))
+    # CPU reference: bounded sample (6 iterations) on the same operator
     ip, ix, dv = kr.convdiff3d_csr(m)
     M = sp.csr_matrix((dv, ix, ip), shape=(n, n))
     rhs_h = M @ np.ones(n)
