@@ -756,3 +756,50 @@ def test_fullsize_cg_residual_recurrence_is_consistent(ctx, big, cg_form):
     s = ctx.scalars(0, 3)
     assert np.sqrt(s[0] / s[2]) <= RTOL_FINAL                      # |(Ax-b) - r| / |b|
     assert srel(np.sqrt(s[1]), runs[0][0]) <= 1e-12
+
+
+# ============================================================ lifetime / host staging
+def test_handles_can_be_destroyed_in_any_order():
+    """Interpreter shutdown finalises objects in arbitrary order: destroying the context
+    before its vectors / operators / solvers must neither crash nor leak, and a call through
+    a handle whose context is gone fails with a status code."""
+    from pykrylov_b200.device import Context, DeviceCsr, DeviceSolver
+    c = Context(0)
+    A = DeviceCsr.poisson2d(c, 8)
+    v = c.vector(np.ones(64))
+    S = DeviceSolver(c, "cg", A)
+    S.setup(np.ones(64))
+    S.iterate(3)
+    handles = (S._h, A._h, v._h)
+    lib = L().lib
+    lib.kry_ctx_destroy(c._h)                       # context first, children still alive
+    c._h = L().handle()
+    y = np.zeros(64)
+    assert lib.kry_vec_download(v._h, y.ctypes.data, 64) == L().KRY_ERR_STATE
+    assert lib.kry_solver_iterate(S._h, 1) == L().KRY_ERR_STATE
+    assert "destroyed" in L().last_error()
+    with pytest.raises(L().KrylovDeviceError):
+        A.spmv(v, v)
+    # children afterwards, in the "wrong" order; the last one frees the context struct
+    lib.kry_vec_destroy(handles[2]); v._h = L().handle()
+    lib.kry_csr_destroy(handles[1]); A._h = L().handle()
+    lib.kry_solver_destroy(handles[0]); S._h = L().handle()
+    # and the library is still healthy
+    c2 = Context(0)
+    ip, ix, dv = kr.poisson2d_csr(4)
+    assert np.array_equal(DeviceCsr.poisson2d(c2, 4).matvec(np.ones(16)), CsrRef((16, 16), ip, ix, dv).matvec(np.ones(16)))
+    c2.close()
+
+
+def test_large_results_come_back_in_pooled_pinned_memory(ctx):
+    from pykrylov_b200.device import result_pool
+    n = 1 << 18                                     # 2 MiB: above the pool's threshold
+    v = ctx.vector(np.arange(n, dtype=np.float64))
+    a = v.download()
+    assert type(a.base).__name__ == "_PinnedBlock" and np.array_equal(a, np.arange(n))
+    hits = result_pool.hits
+    del a
+    b = v.download()                                # the block is recycled, not re-pinned
+    assert result_pool.hits == hits + 1 and np.array_equal(b, np.arange(n))
+    small = ctx.vector(np.ones(10)).download()
+    assert small.base is None
