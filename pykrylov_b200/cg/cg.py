@@ -1,8 +1,8 @@
 """Conjugate gradient, device-resident.
 
 Same class surface and keyword contract as the reference's pykrylov/cg/cg.py:7-165;
-the loop of cg.py:113-158 itself runs on the GPU (libkrylov_b200, 3 fused launches
-per iteration) with the stopping test evaluated on device every iteration.  The
+the loop of cg.py:113-158 itself runs on the GPU (libkrylov_b200, 2 fused launches
+per iteration; 3 on row shards) with the stopping test evaluated on device every iteration.  The
 host only replays the log lines / ``residHistory`` from the device ring buffer at
 every ``check_interval``.
 """
