@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 echo "== smoke"; date
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke.log
 echo "== bench n1"; date
-timeout 200 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench n1 rc=$?"; cut -c1-250 gpurun_out/bench_n1.json; tail -3 gpurun_out/bench_n1.err
+timeout 200 python bench.py --no-cpu > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench n1 rc=$?"; cut -c1-250 gpurun_out/bench_n1.json; tail -3 gpurun_out/bench_n1.err
 echo "== two-GPU test"; date
 timeout 200 python -m pytest tests/test_multi_gpu.py -m gpu -q --timeout 150 > gpurun_out/pytest_2gpu.log 2>&1; echo "pytest 2gpu rc=$?"; tail -3 gpurun_out/pytest_2gpu.log
 echo "== bench n2"; date
