@@ -261,10 +261,27 @@ def load_traffic():
         return None
 
 
+class stdout_to_stderr(object):
+    """Route the process's fd 1 to fd 2 for a while: NCCL prints its version banner on stdout
+    when the communicator is created (NCCL_DEBUG=VERSION on some boxes), and stdout must carry
+    exactly one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def main_ours(args):
     from pykrylov_b200.comm import init_from_env
     from pykrylov_b200.linop import CsrLinearOperator
-    ctx, rank, world = init_from_env()
+    with stdout_to_stderr():
+        ctx, rank, world = init_from_env()
     if world != args.gpus and rank == 0:
         print("warning: --gpus %d but WORLD_SIZE=%d" % (args.gpus, world), file=sys.stderr)
     g = args.grid or (G_CONFIG2 if world == 1 else G_CONFIG5)
