@@ -295,7 +295,9 @@ def main_ours(args):
         sampler.start()
     if args.cg_fuse is not None:
         ctx.set_option(4, args.cg_fuse)
-    form = 0 if world > 1 else ctx.get_option(4)         # shards keep the 3-launch plan
+    if args.cg_fuse_shards is not None:
+        ctx.set_option(5, args.cg_fuse_shards)
+    form = ctx.get_option(4) if (world == 1 or ctx.get_option(5)) else 0    # launch plan in effect
     # timed region 1 -> `value`: K iterations exactly as a solve enqueues them (CUDA-graph replays
     # on one GPU), nothing else on the stream
     ms, launches, _, S, st = time_device_resident(ctx, A, rhs, args.steps, args.warmup, profile=False)
@@ -427,6 +429,8 @@ def main():
     ap.add_argument("--no-single", action="store_true", help="skip the 1-GPU same-workload leg (N>1)")
     ap.add_argument("--cg-fuse", type=int, default=None, choices=[0, 1, 2],
                     help="CG launch plan (KRY_OPT_CG_FUSE); default: the library's default")
+    ap.add_argument("--cg-fuse-shards", type=int, default=None, choices=[0, 1],
+                    help="N>1: row shards use the fused CG plan too (KRY_OPT_CG_FUSE_SHARDS)")
     ap.add_argument("--nccl-allreduce", action="store_true",
                     help="N>1: use ncclAllReduce + finalize launches instead of the fused NVLink peer-memory all-reduce")
     args = ap.parse_args()

@@ -272,15 +272,35 @@ __global__ void halo_pack_kernel(const double *x, const int *idx, int n_send, in
     if (i < max_send) buf[i] = (i < n_send) ? x[idx[i]] : 0.0;
 }
 
+// Fused CG forms on shards: the boundary entries travel already updated,
+// buf = beta * p[idx] - r[idx]  (cg.py:150-151; same two rounded operations as everywhere else).
+__global__ void halo_pack_dir_kernel(const double *p, const double *r, const double *beta_ptr,
+                                     const int *idx, int n_send, int max_send, double *buf)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= max_send) return;
+    double v = 0.0;
+    if (i < n_send) {
+        const int j = idx[i];
+        v = __dsub_rn(__dmul_rn(*beta_ptr, p[j]), r[j]);
+    }
+    buf[i] = v;
+}
+
 // x_dev: [n_local | nranks*max_send] -- fills the tail.  No-op for unsharded operators.
-int kry_halo_exchange(kry_csr *M, double *x_dev)
+// With r_dev/beta_dev the packed entries are beta*x - r instead of x (see above).
+int kry_halo_exchange_dir(kry_csr *M, double *x_dev, const double *r_dev, const double *beta_dev)
 {
     HaloPlan &h = M->halo;
     if (!h.active) return KRY_OK;
     kry_ctx *c = M->ctx;
     if (h.max_send == 0) return KRY_OK;
-    halo_pack_kernel<<<(h.max_send + 255) / 256, 256, 0, c->stream>>>(x_dev, h.send_idx, h.n_send,
-                                                                      h.max_send, h.send_buf);
+    if (r_dev)
+        halo_pack_dir_kernel<<<(h.max_send + 255) / 256, 256, 0, c->stream>>>(
+            x_dev, r_dev, beta_dev, h.send_idx, h.n_send, h.max_send, h.send_buf);
+    else
+        halo_pack_kernel<<<(h.max_send + 255) / 256, 256, 0, c->stream>>>(x_dev, h.send_idx, h.n_send,
+                                                                          h.max_send, h.send_buf);
     c->launches++;
     KRY_CUDA(cudaGetLastError());
     double *tail = x_dev + M->A.nrows;
@@ -293,6 +313,11 @@ int kry_halo_exchange(kry_csr *M, double *x_dev)
     KRY_NCCL(g_nccl.AllGather(h.send_buf, tail, (size_t)h.max_send, ncclDouble, (ncclComm_t)c->nccl,
                               c->stream));
     return KRY_OK;
+}
+
+int kry_halo_exchange(kry_csr *M, double *x_dev)
+{
+    return kry_halo_exchange_dir(M, x_dev, nullptr, nullptr);
 }
 
 // ------------------------------------------------------- shard finalisation

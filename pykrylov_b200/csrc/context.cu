@@ -228,9 +228,10 @@ extern "C" int kry_ctx_set_option(kry_ctx *c, int option, int value)
 {
     KRY_REQUIRE(c, KRY_ERR_INVALID, "kry_ctx_set_option: NULL context");
     KRY_REQUIRE(option == KRY_OPT_L2_HINTS || option == KRY_OPT_GRAPHS || option == KRY_OPT_P2P ||
-                    option == KRY_OPT_CG_FUSE,
+                    option == KRY_OPT_CG_FUSE || option == KRY_OPT_CG_FUSE_SHARDS,
                 KRY_ERR_INVALID, "kry_ctx_set_option: unknown option %d", option);
     if (option == KRY_OPT_L2_HINTS) c->l2_hints = value;
+    else if (option == KRY_OPT_CG_FUSE_SHARDS) c->cg_fuse_shards = value ? 1 : 0;
     else if (option == KRY_OPT_CG_FUSE) {
         KRY_REQUIRE(value >= 0 && value <= 2, KRY_ERR_INVALID, "kry_ctx_set_option: CG_FUSE=%d not in 0..2", value);
         c->cg_fuse = value;
@@ -252,6 +253,7 @@ extern "C" int kry_ctx_get_option(kry_ctx *c, int option, int *value)
         case KRY_OPT_GRAPHS: *value = c->use_graphs; break;
         case KRY_OPT_P2P: *value = c->p2p_on; break;
         case KRY_OPT_CG_FUSE: *value = c->cg_fuse; break;
+        case KRY_OPT_CG_FUSE_SHARDS: *value = c->cg_fuse_shards; break;
         default: kry_set_error("kry_ctx_get_option: unknown option %d", option); return KRY_ERR_INVALID;
     }
     return KRY_OK;

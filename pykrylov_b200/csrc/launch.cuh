@@ -9,6 +9,7 @@ constexpr int KRY_TMA_STAGES      = 3;
 
 int csr_build_partition(kry_ctx *c, CsrDev &m, int tile_nnz);
 int kry_halo_exchange(kry_csr *M, double *x_dev);    // comm.cu; no-op unless sharded
+int kry_halo_exchange_dir(kry_csr *M, double *x_dev, const double *r_dev, const double *beta_dev);
 
 template <class K>
 static inline int set_max_smem(K kernel, kry_ctx *c, size_t bytes)

@@ -108,7 +108,7 @@ template <int ND, class Gather, class Epi, class Fin>
 int solver_spmv(kry_solver *S, Gather g, Epi e, Fin f, const int *done, double *x_dev)
 {
     if (S->sharded) {
-        KRY_TRY(kry_halo_exchange(S->A, x_dev));
+        if (x_dev) KRY_TRY(kry_halo_exchange(S->A, x_dev));     // nullptr: the caller did the exchange
         if (S->ctx->p2p_on) return spmv_launch<ND>(S->A, false, g, e, f, done, 2);   // in-kernel all-reduce
         KRY_TRY((spmv_launch<ND>(S->A, false, g, e, f, done, 1)));
         KRY_TRY(kry_allreduce_sums(S->ctx, ND));

@@ -174,17 +174,25 @@ struct CgDirBody {
 // and 48 / 24 B in the second one, against 80 + 48 + 24 B for the 3-launch form.
 //   trip i reads P[(i+1)&1] and writes P[i&1];  PEND = false on the first trip after a
 //   setup / settle (p is already materialised there: plain copy).
-template <bool PEND>
+template <bool PEND, bool SHARD = false>
 struct CgGatherDir {
     const double *p_old, *r;
     DevScalars   *s;
     double        beta;
+    int           n_local;     // SHARD: columns >= n_local are halo entries, which arrive
+                               // already updated (halo_pack_dir_kernel)
     __device__ void   init() { beta = s->s[S_BETA]; }
     __device__ double operator()(int c) const
     {
         const double po = __ldg(p_old + c);
-        if constexpr (PEND) return __dsub_rn(__dmul_rn(beta, po), __ldg(r + c));    // cg.py:150-151
-        else return po;
+        if constexpr (PEND) {
+            if constexpr (SHARD) {
+                if (c >= n_local) return po;
+            }
+            return __dsub_rn(__dmul_rn(beta, po), __ldg(r + c));                   // cg.py:150-151
+        } else {
+            return po;
+        }
     }
 };
 
@@ -359,7 +367,7 @@ static int cg_setup(kry_solver *S, int guess)
 {
     double *x = solver_vec(S, "x"), *r = solver_vec(S, "r"), *p = solver_vec(S, "p");
     double *rhs = solver_vec(S, "rhs");
-    S->cg_fuse = S->sharded ? 0 : S->ctx->cg_fuse;     // shards keep the 3-launch form (halo carries p)
+    S->cg_fuse = (S->sharded && !S->ctx->cg_fuse_shards) ? 0 : S->ctx->cg_fuse;
     S->fresh = true;
     S->rot = 0;
     CgSetupFin fin{S->ds, S->hist, guess};
@@ -375,8 +383,14 @@ template <bool PEND, bool XLAG>
 static int cg_fused_spmv(kry_solver *S, double *p_old, double *p_new, int opt)
 {
     double *x = solver_vec(S, "x"), *r = solver_vec(S, "r"), *Ap = solver_vec(S, "Ap");
-    CgGatherDir<PEND> g{p_old, r, S->ds, 0.0};
     CgEpiFused<PEND, XLAG> e{Ap, p_new, x, p_old, r, S->ds, opt & 5, 0.0, 0.0, 0, 0};
+    if (S->sharded) {
+        // boundary entries of p travel already updated; the local ones are updated in the gather
+        KRY_TRY(kry_halo_exchange_dir(S->A, p_old, PEND ? r : nullptr, PEND ? &S->ds->s[S_BETA] : nullptr));
+        CgGatherDir<PEND, true> g{p_old, r, S->ds, 0.0, (int)S->n};
+        return solver_spmv<1>(S, g, e, CgFinApFused{S->ds}, &S->ds->done, nullptr);
+    }
+    CgGatherDir<PEND> g{p_old, r, S->ds, 0.0, 0};
     return solver_spmv<1>(S, g, e, CgFinApFused{S->ds}, &S->ds->done, p_old);
 }
 

@@ -147,18 +147,41 @@ GPU_WORKER = textwrap.dedent("""
     assert np.array_equal(S.get_vector("r"), r_ref[lo:hi])
     st0 = S.status()
     assert abs(st0.resid_norm0 - np.linalg.norm(r_ref)) <= 1e-12 * np.linalg.norm(r_ref)
-    # full solve from a zero guess: same iteration count and history as the 1-process oracle
-    S.setup(rhs[lo:hi], matvec_max=2 * n)
-    st = S.run(16)
+    # full solve from a zero guess: same iteration count and history as the 1-process oracle,
+    # under the 3-launch plan and under the fused plans with the updated boundary entries
+    # travelling in the packed halo (KRY_OPT_CG_FUSE_SHARDS)
     ref = kr.cg_solve(M, rhs)
-    hist = S.drain_history(st)[:, 0]
-    assert st.n_matvec == ref.nMatvec, (st.n_matvec, ref.nMatvec)
-    k = len(ref.residHistory)
-    assert np.max(np.abs(hist[:k] - np.array(ref.residHistory)) / np.array(ref.residHistory)) <= 1e-9
-    assert np.max(np.abs(S.solution() - ref.x[lo:hi])) <= 1e-9
-    # every rank holds bitwise identical scalars (NCCL all-reduce)
-    vals = ctx.allgather_bytes(np.array([st.resid_norm]).tobytes())
-    assert len(set(vals)) == 1
+    runs = {}
+    for fuse_shards, form in ((0, 0), (1, 1), (1, 2)):
+        ctx.set_option(5, fuse_shards)
+        ctx.set_option(4, form if fuse_shards else 2)
+        S.setup(rhs[lo:hi], matvec_max=2 * n)
+        st = S.run(16)
+        hist = S.drain_history(st)[:, 0]
+        assert st.n_matvec == ref.nMatvec, (fuse_shards, form, st.n_matvec, ref.nMatvec)
+        k = len(ref.residHistory)
+        assert np.max(np.abs(hist[:k] - np.array(ref.residHistory)) / np.array(ref.residHistory)) <= 1e-9
+        xs = S.solution()
+        assert np.max(np.abs(xs - ref.x[lo:hi])) <= 1e-9
+        # every rank holds bitwise identical scalars (all-reduce in rank order)
+        vals = ctx.allgather_bytes(np.array([st.resid_norm]).tobytes())
+        assert len(set(vals)) == 1
+        runs[(fuse_shards, form)] = (hist.copy(), xs.copy(), S.get_vector("r"), S.get_vector("p"))
+    for key in ((1, 1), (1, 2)):          # the plans only move work between launches: same bits
+        for a, b in zip(runs[(0, 0)], runs[key]):
+            assert np.array_equal(a, b), key
+    # mid-run reads settle what the fused plan still owes, then the run continues
+    S.setup(rhs[lo:hi], matvec_max=2 * n)
+    S.iterate(5)
+    x5 = S.solution()
+    S.iterate(4)
+    ctx.set_option(5, 0)
+    S0 = DeviceSolver(ctx, "cg", A)
+    S0.setup(rhs[lo:hi], matvec_max=2 * n)
+    S0.iterate(5)
+    assert np.array_equal(x5, S0.solution())
+    S0.iterate(4)
+    assert np.array_equal(S.solution(), S0.solution()) and np.array_equal(S.get_vector("p"), S0.get_vector("p"))
     ctx.barrier()
     print("rank %%d ok nmv=%%d" %% (rank, st.n_matvec))
 """)
