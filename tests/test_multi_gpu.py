@@ -166,10 +166,14 @@ GPU_WORKER = textwrap.dedent("""
         # every rank holds bitwise identical scalars (all-reduce in rank order)
         vals = ctx.allgather_bytes(np.array([st.resid_norm]).tobytes())
         assert len(set(vals)) == 1
-        runs[(fuse_shards, form)] = (hist.copy(), xs.copy(), S.get_vector("r"), S.get_vector("p"))
-    for key in ((1, 1), (1, 2)):          # the plans only move work between launches: same bits
-        for a, b in zip(runs[(0, 0)], runs[key]):
-            assert np.array_equal(a, b), key
+        runs[(fuse_shards, form)] = (hist.copy(), xs.copy(), S.get_vector("r"))
+    # the plans only move work between launches: history, solution and residual are the same
+    # bits.  (p is not compared after convergence: the 3-launch plan skips the direction update
+    # of the trip that latched `done`, the fused plans pay it when p is read; the reference
+    # never exposes that p.  It is compared mid-run below.)
+    for key in ((1, 1), (1, 2)):
+        for name, a, b in zip(("hist", "x", "r"), runs[(0, 0)], runs[key]):
+            assert np.array_equal(a, b), (key, name)
     # mid-run reads settle what the fused plan still owes, then the run continues
     S.setup(rhs[lo:hi], matvec_max=2 * n)
     S.iterate(5)
