@@ -357,6 +357,22 @@ def main_ours(args):
             solo.close()
         ctx.barrier()
 
+    if world == 1 and g == G_CONFIG2 and not args.no_config5:
+        # the strong-scaling base: the 10^8-row operator of configs[4] on this one GPU, so that the
+        # N = 2/4/8 lines can be compared with a number from the same series of runs
+        try:
+            A5, rhs5, n5, _, _ = build_problem(ctx, G_CONFIG5, 0, 1)
+            k5 = max(10, args.steps // 4)
+            ms5, _, _, S5, _ = time_device_resident(ctx, A5, rhs5, k5, 3, profile=False)
+            extra["config5_one_gpu"] = {"value": k5 / (ms5 / 1e3), "unit": UNIT, "steps": k5, "rows": n5,
+                                        "workload": "BASELINE.json configs[4] operator (grid %d^2) on one GPU"
+                                                    % G_CONFIG5}
+            S5._release()
+            A5._release()
+            del rhs5
+        except Exception as exc:                      # never lose the headline line over the side leg
+            extra["config5_one_gpu"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline(g)
@@ -427,6 +443,8 @@ def main():
     ap.add_argument("--grid", type=int, default=0, help="override the Laplacian grid size (debugging)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-single", action="store_true", help="skip the 1-GPU same-workload leg (N>1)")
+    ap.add_argument("--no-config5", action="store_true",
+                    help="N=1: skip the side leg that times the 10^8-row operator of configs[4] on this GPU")
     ap.add_argument("--cg-fuse", type=int, default=None, choices=[0, 1, 2],
                     help="CG launch plan (KRY_OPT_CG_FUSE); default: the library's default")
     ap.add_argument("--cg-fuse-shards", type=int, default=None, choices=[0, 1],

@@ -1,0 +1,67 @@
+"""bench.py contract, as far as it can be checked without a GPU: the reference arm runs the
+reference's CPU path and prints exactly one JSON line with the agreed keys; the other ranks of
+a torchrun launch stay silent; our own arm refuses to run without a GPU (no CPU fallback)."""
+import json
+import os
+import subprocess
+import sys
+
+from conftest import ROOT
+
+BENCH = os.path.join(ROOT, "bench.py")
+
+
+def run(args, env=None, timeout=300):
+    e = dict(os.environ)
+    e.pop("RANK", None)
+    e.pop("WORLD_SIZE", None)
+    e.update(env or {})
+    return subprocess.run([sys.executable, BENCH] + args, capture_output=True, text=True, env=e, timeout=timeout)
+
+
+def test_reference_arm_prints_one_json_line_with_the_contract_keys():
+    r = run(["--impl", "reference", "--grid", "64", "--steps", "4", "--warmup", "1"])
+    assert r.returncode == 0, r.stderr
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "cg_iters_per_s" and d["unit"] == "iters/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["dtype"] == "f64"
+    assert d["vs_baseline"] is None and d["data"] == "synthetic"
+    assert d["value"] > 0 and abs(d["ms_per_step"] - 1e3 / d["value"]) <= 1e-9 * d["ms_per_step"]
+    assert d["config"]["rows"] == 64 * 64 and d["config"]["nnz"] == 5 * 64 * 64 - 4 * 64
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_other_ranks_exit_silently():
+    r = run(["--impl", "reference", "--gpus", "2", "--grid", "64", "--steps", "2"],
+            env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_our_arm_fails_loudly_without_a_gpu():
+    import pykrylov_b200.device as dev
+    try:
+        n = dev.device_count()
+    except Exception:
+        n = 0
+    if n > 0:
+        import pytest
+        pytest.skip("a GPU is present")
+    r = run(["--steps", "2", "--grid", "32", "--no-cpu"], timeout=120)
+    assert r.returncode != 0 and r.stdout.strip() == ""
+    assert "libkrylov_b200 error" in r.stderr
+
+
+def test_algorithmic_byte_model():
+    sys.path.insert(0, ROOT)
+    import bench
+    g = 3162
+    n, nnz = g * g, 5 * g * g - 4 * g
+    assert bench.spmv_bytes(n, nnz) == 799707748
+    assert bench.cg_iter_bytes(n, nnz) == 1519581316
+    assert bench.spmv_bytes(n, nnz) + bench.K1_EXTRA_BYTES_PER_ROW[2] * n == 1119651556
+    for form in (0, 1, 2):                                   # what the two/three launches of a plan move
+        assert bench.ITER_VECTOR_BYTES_PER_ROW[form] == 72 - 8 * form
