@@ -99,6 +99,56 @@ WORKER = textwrap.dedent("""
         part = np.array([np.dot(x_local, y_local)])
         tot = sum(float(p[0]) for p in gather(part))
         assert abs(tot - np.dot(x, CsrRef((n, n), fip, fix, fdv).matvec(x))) <= 1e-12 * abs(tot)
+    # 4. the fused CG plan on row shards (KRY_OPT_CG_FUSE_SHARDS; csrc/comm.cu halo_pack_dir_kernel
+    #    + csrc/solvers.cu CgGatherDir<PEND, SHARD>): the p (and x) update of a trip rides in the
+    #    next trip's SpMV; boundary entries travel already updated, local columns are updated in
+    #    the gather.  Statement in NumPy, two ranks, against the oracle's CG from the same state.
+    g = 13; n = g * g
+    ranges = row_partition(n, world); lo, hi = ranges[rank]; nl = hi - lo
+    ip, ix, dv = kr.poisson2d_csr(g, lo, hi)
+    fip, fix, fdv = kr.poisson2d_csr(g)
+    M = CsrRef((n, n), fip, fix, fdv)
+    cols, send_idx, max_send = halo_plan(np.asarray(ix, dtype=np.int64), lo, hi, ranges, gather)
+    A_loc = CsrRef((nl, nl + world * max_send), ip, cols, dv)
+    rhs = M.matvec(np.ones(n))
+    st = kr.cg_start(M, rhs, matvec_max=10 ** 6)
+    x = np.zeros(nl); r = st.r[lo:hi].copy(); ry = float(st.ry)
+    P = [np.zeros(nl + world * max_send), np.zeros(nl + world * max_send)]
+    P[1][:nl] = st.p[lo:hi]                                    # setup: p_0 in the source buffer of trip 0
+    alpha = beta = 0.0
+    pend = False
+
+    def allsum(v):
+        return sum(float(q) for q in gather(float(v)))        # rank order on every rank
+
+    for trip in range(12):
+        src, dst = P[(trip + 1) & 1], P[trip & 1]
+        packed = np.zeros(max_send)
+        packed[:len(send_idx)] = (beta * src[send_idx] - r[send_idx]) if pend else src[send_idx]
+        src[nl:] = np.concatenate(gather(packed))              # halo: already updated entries
+        p_eff = src.copy()
+        if pend:
+            p_eff[:nl] = beta * src[:nl] - r                   # local columns: updated in the gather
+            x += alpha * src[:nl]                              # x update of the previous trip
+        Ap = A_loc.matvec(p_eff)
+        dst[:nl] = p_eff[:nl]
+        pAp = allsum(np.dot(p_eff[:nl], Ap))
+        alpha = ry / pAp
+        r += alpha * Ap
+        ry_next = allsum(np.dot(r, r))
+        beta = ry_next / ry
+        ry = ry_next
+        pend = True
+        kr.cg_step(M, st)
+        assert np.array_equal(Ap, st.Ap[lo:hi]) or np.max(np.abs(Ap - st.Ap[lo:hi])) <= 1e-13 * np.max(np.abs(st.Ap))
+        assert abs(alpha - st.alpha) <= 1e-12 * abs(st.alpha) and abs(beta - st.beta) <= 1e-12 * abs(st.beta)
+        assert np.max(np.abs(r - st.r[lo:hi])) <= 1e-12 * np.max(np.abs(st.r))
+    # settle: what the plan still owes (x += alpha p, p = beta p - r), then compare x and p
+    last = P[(12 - 1) & 1]
+    x += alpha * last[:nl]
+    p_final = beta * last[:nl] - r
+    assert np.max(np.abs(x - st.x[lo:hi])) <= 1e-12 * np.max(np.abs(st.x))
+    assert np.max(np.abs(p_final - st.p[lo:hi])) <= 1e-12 * np.max(np.abs(st.p))
     dist.barrier()
     dist.destroy_process_group()
     print("rank %%d ok" %% rank)
