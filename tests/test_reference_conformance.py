@@ -7,8 +7,10 @@ dtype promotion over allowed_types^2, Identity / Diagonal / Zero / Reduced /
 SymmetricallyReduced / linop_from_ndarray) is re-targeted from the reference package to
 `pykrylov_b200` by renaming the import and executed unchanged otherwise.  Everything in it is
 host-side operator glue (closures run on the host), so it needs no GPU -- except the two
-`CoordLinearOperator` cases, whose operator is a CSR in HBM in this package; those run in the
-GPU suite (tests/test_gpu_parity.py builds the same operator against the oracle).
+`CoordLinearOperator` cases, whose operator is a CSR in HBM in this package: their host half
+(COO -> CSR in the reference's accumulation order) is pinned in
+tests/test_host.py::test_coo_to_csr_keeps_reference_accumulation_order, the device half is the
+same `csr_operator` every GPU parity test goes through.
 """
 import os
 import types
