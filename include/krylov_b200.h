@@ -87,8 +87,8 @@ int kry_prof_read(kry_ctx *ctx, int64_t *samples, double *total_ms);
                                 2: 2 launches  [x += alpha p ; p = beta p - r]+SpMV+dot | r update+dot
                                 The fused forms carry the p (and x) update of a trip into the SpMV of
                                 the next one; results are bit-identical to form 0.                  */
-#define KRY_OPT_CG_FUSE_SHARDS 5 /* 1: row shards use the CG_FUSE plan too (the packed halo then carries
-                                beta p - r of the boundary entries); 0: shards keep plan 0         */
+#define KRY_OPT_CG_FUSE_SHARDS 5 /* 1 (default): row shards use the CG_FUSE plan too (the packed halo then
+                                carries beta p - r of the boundary entries); 0: shards keep plan 0 */
 int kry_ctx_set_option(kry_ctx *ctx, int option, int value);
 int kry_ctx_get_option(kry_ctx *ctx, int option, int *value);
 

@@ -248,6 +248,7 @@ extern "C" int kry_ctx_create(int device, kry_ctx **out)
     c->l2_hints = 1;
     c->use_graphs = 0;
     c->cg_fuse = 2;
+    c->cg_fuse_shards = 1;
     KRY_TRY(kry_alloc((void **)&c->scalars, KRY_NUM_SLOTS * sizeof(double)));
     KRY_TRY(kry_alloc((void **)&c->sums, 2 * KRY_MAX_DOTS * sizeof(double)));
     KRY_TRY(kry_alloc((void **)&c->counter, 256));
