@@ -131,3 +131,70 @@ def _sharded_cg(L, world):
     # the packed halo is one grid line per neighbour: interior ranks publish 2 g entries, so the
     # padded per-rank slot is g for two ranks and 2 g beyond, and the tail holds `world` slots
     assert all(o["max_send"] == world * g * (1 if world == 2 else 2) for o in out)
+
+
+@pytest.mark.parametrize("method,world", [("bicgstab", 2), ("bicgstab", 5), ("cgs", 3), ("tfqmr", 4), ("minres", 3),
+                                          ("minres", 8)])
+def test_other_sharded_loops_follow_the_oracle(emu_ctx, method, world):
+    """Bi-CGSTAB, CGS, TFQMR and MINRES on row shards (every SpMV input carries the halo tail,
+    every fused inner product is all-reduced): the oracle's iteration count and history, the same
+    solution, identical scalars on every rank -- with the in-kernel all-reduce protocol and with
+    the NCCL one."""
+    from pykrylov_b200 import _lib as L
+    from pykrylov_b200 import device as dev
+    from pykrylov_b200.comm import row_partition
+    m = 7
+    n = m ** 3
+    if method == "minres":                       # symmetric: the 7-point Laplacian part only
+        ip, ix, dv = kr.convdiff3d_csr(m, gamma=0.0)
+    else:
+        ip, ix, dv = kr.convdiff3d_csr(m)
+    M = CsrRef((n, n), ip, ix, dv)
+    rhs = M.matvec(np.linspace(1.0, 2.0, n))
+    oracle = dict(bicgstab=kr.bicgstab_solve, cgs=kr.cgs_solve, tfqmr=kr.tfqmr_solve)
+    if method == "minres":
+        ref = kr.minres_solve(M, rhs)
+    else:
+        ref = oracle[method](M, rhs, reltol=1e-8, matvec_max=2 * n)
+    uid = C.create_string_buffer(L.KRY_COMM_ID_BYTES)
+    L.call("kry_comm_unique_id", uid)
+    ranges = row_partition(n, world)
+
+    def worker(rank):
+        lo, hi = ranges[rank]
+        ctx = dev.Context(0)
+        ctx.comm_init(world, rank, uid.raw)
+        try:
+            A = dev.DeviceCsr.from_arrays(ctx, (hi - lo, n), ip[lo:hi + 1] - ip[lo], ix[ip[lo]:ip[hi]], dv[ip[lo]:ip[hi]],
+                                          symmetric=(method == "minres"))
+            A.shard_finalize(n, lo)
+            S = dev.DeviceSolver(ctx, method, A)
+            runs = []
+            for p2p in (1, 0):
+                ctx.set_option(L.KRY_OPT_P2P, p2p)
+                if method == "minres":
+                    S.setup(rhs[lo:hi], abstol=0.0, reltol=0.0, matvec_max=5 * n, rtol=1e-12, etol=1e-6, window=5)
+                else:
+                    S.setup(rhs[lo:hi], abstol=1e-8, reltol=1e-8, matvec_max=2 * n)
+                st = S.run(6)
+                hist = S.drain_history(st)[:, 0]
+                if method == "minres":
+                    assert (int(st.istop), int(st.n_iter)) == (ref.istop, ref.itn)
+                else:
+                    assert st.n_matvec == ref.nMatvec and bool(st.converged) == bool(ref.converged)
+                rh = np.array(ref.residHistory, dtype=float)
+                k = min(len(rh), 10)
+                assert len(hist) == len(rh) and np.max(np.abs(hist[:k] - rh[:k]) / rh[:k]) <= 1e-9
+                xs = S.solution()
+                assert np.max(np.abs(xs - ref.x[lo:hi])) <= 1e-7 * np.max(np.abs(ref.x))
+                same = ctx.allgather_bytes(np.array([st.resid_norm]).tobytes())
+                assert len(set(same)) == 1
+                runs.append((hist.copy(), xs.copy()))
+            for a, b in zip(*runs):                      # the two all-reduce paths: same bits
+                assert np.array_equal(a, b)
+            ctx.barrier()
+        finally:
+            ctx.close()
+        return True
+
+    assert all(run_ranks(world, worker))
