@@ -1248,6 +1248,7 @@ struct MinBodyR2 {            // y = (-alfa/beta) r2 + y' ; beta'^2 = r2new . (M
 };
 
 struct MinBodyR2Pre {         // preconditioned K2: r2' = (-alfa/beta) r2 + y' ; y = M r2' ; beta'^2 = r2'.y
+    static constexpr int kMinBlocks = 4;       // the fp64 division of `r ./ d` spills under 40 registers
     double       *yn, *ypre;  // yn: y' in, the new r2 out; ypre: the new (preconditioned) y
     const double *r2, *pd;
     int           pmode;
