@@ -154,6 +154,9 @@ int kry_csr_create_convdiff3d(kry_ctx *ctx, int64_t m, double gamma,
 #define KRY_SPMV_TMA     3   /* persistent CTAs, cp.async.bulk (TMA) multi-stage     */
 #define KRY_SPMV_ROWB8   4   /* one thread per row, loads batched 8 entries at a time */
 #define KRY_SPMV_ROWB4   5   /* one thread per row, loads batched 4 entries at a time */
+#define KRY_SPMV_ROWPF   6   /* one thread per row, row pointers loaded one trip ahead (candidate)  */
+#define KRY_SPMV_ROWPF2  7   /* ... two trips ahead, and the next trip's col/val window prefetched
+                                into L2 (candidate)                                                */
 int kry_csr_set_kernel(kry_csr *A, int kind, int tile_nnz, int threads);
 
 /* ------------------------------------------------------- hot-path kernels */

@@ -33,6 +33,7 @@ KRY_ERR_STATE = -7
 KRY_CSR_SYMMETRIC = 1
 KRY_CSR_BUILD_TRANSPOSE = 2
 KRY_SPMV_AUTO, KRY_SPMV_ROW, KRY_SPMV_STREAM, KRY_SPMV_TMA, KRY_SPMV_ROWB8, KRY_SPMV_ROWB4 = 0, 1, 2, 3, 4, 5
+KRY_SPMV_ROWPF, KRY_SPMV_ROWPF2 = 6, 7
 KRY_CG, KRY_BICGSTAB, KRY_CGS, KRY_TFQMR, KRY_MINRES = 1, 2, 3, 4, 5
 KRY_NUM_SLOTS = 64
 KRY_OPT_L2_HINTS, KRY_OPT_GRAPHS, KRY_OPT_P2P, KRY_OPT_CG_FUSE, KRY_OPT_CG_FUSE_SHARDS = 1, 2, 3, 4, 5

@@ -677,7 +677,7 @@ extern "C" int kry_csr_diagonal(const kry_csr *M, double *diag_host)
 extern "C" int kry_csr_set_kernel(kry_csr *M, int kind, int tile_nnz, int threads)
 {
     KRY_REQUIRE(M, KRY_ERR_INVALID, "kry_csr_set_kernel: NULL operator");
-    KRY_REQUIRE(kind >= KRY_SPMV_AUTO && kind <= KRY_SPMV_ROWB4, KRY_ERR_INVALID,
+    KRY_REQUIRE(kind >= KRY_SPMV_AUTO && kind <= KRY_SPMV_ROWPF2, KRY_ERR_INVALID,
                 "kry_csr_set_kernel: unknown kernel %d", kind);
     KRY_REQUIRE(tile_nnz == 0 || (tile_nnz >= 256 && tile_nnz <= 16384 && tile_nnz % 4 == 0),
                 KRY_ERR_INVALID, "kry_csr_set_kernel: tile_nnz %d not in [256,16384] / 4", tile_nnz);

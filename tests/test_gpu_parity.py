@@ -78,7 +78,8 @@ def fixtures():
 
 
 KERNELS = [("row", 1, 0, 0), ("stream", 2, 4096, 256), ("stream_small", 2, 512, 64),
-           ("tma", 3, 2048, 256), ("tma_small", 3, 256, 128)]
+           ("tma", 3, 2048, 256), ("tma_small", 3, 256, 128),
+           ("rowpf", 6, 0, 0), ("rowpf2", 7, 0, 0)]     # software-pipelined row kernels (candidates)
 
 
 # ============================================================== integer work
