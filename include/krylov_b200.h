@@ -87,6 +87,9 @@ int kry_prof_read(kry_ctx *ctx, int64_t *samples, double *total_ms);
                                 2: 2 launches  [x += alpha p ; p = beta p - r]+SpMV+dot | r update+dot
                                 The fused forms carry the p (and x) update of a trip into the SpMV of
                                 the next one; results are bit-identical to form 0.                  */
+#define KRY_OPT_CG_ONE_CTA 6  /* 1 (default): CG on an unsharded operator whose CSR and vectors fit the shared
+                                memory of one SM runs as ONE persistent CTA -- the whole loop inside a single
+                                launch per kry_solver_iterate call (candidate; latched at kry_solver_setup) */
 #define KRY_OPT_CG_FUSE_SHARDS 5 /* 1: row shards use the CG_FUSE plan too (the packed halo then carries
                                 beta p - r of the boundary entries); 0: shards keep plan 0         */
 int kry_ctx_set_option(kry_ctx *ctx, int option, int value);

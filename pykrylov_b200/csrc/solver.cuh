@@ -79,6 +79,8 @@ struct kry_solver {
     bool              warm;             // at least one iteration ran un-captured
     int               cg_fuse;          // CG launch plan latched at setup (KRY_OPT_CG_FUSE)
     bool              fresh;            // fused CG: nothing pending, p sits in the next trip's source buffer
+    bool              one_cta;          // CG: the whole loop runs inside one CTA (KRY_OPT_CG_ONE_CTA)
+    size_t            one_cta_smem;     // its dynamic shared memory
 };
 
 constexpr int KRY_GRAPH_ITERS = 12;     // multiple of 6 = lcm of the MINRES buffer rotations

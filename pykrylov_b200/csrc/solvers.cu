@@ -15,6 +15,7 @@
 #include "solver.cuh"
 
 static void solver_drop_graph(kry_solver *S);
+static size_t cg_one_cta_bytes(int64_t n, int64_t nnz);
 
 // ======================================================================= CG
 // cg/cg.py:113-158.   3 launches per iteration:
@@ -368,6 +369,10 @@ static int cg_setup(kry_solver *S, int guess)
     double *x = solver_vec(S, "x"), *r = solver_vec(S, "r"), *p = solver_vec(S, "p");
     double *rhs = solver_vec(S, "rhs");
     S->cg_fuse = (S->sharded && !S->ctx->cg_fuse_shards) ? 0 : S->ctx->cg_fuse;
+    S->one_cta_smem = cg_one_cta_bytes(S->n, S->A->A.nnz);
+    S->one_cta = S->ctx->cg_one_cta && !S->sharded && !S->A->halo.active &&
+                 S->one_cta_smem + 2048 <= (size_t)S->ctx->smem_optin;
+    if (S->one_cta) S->cg_fuse = 0;     // its HBM state is that of the 3-launch plan
     S->fresh = true;
     S->rot = 0;
     CgSetupFin fin{S->ds, S->hist, guess};
@@ -428,6 +433,118 @@ static int cg_iterate(kry_solver *S)
     KRY_TRY((solver_pass<1>(S, ub, CgFinRy{S->ds, S->hist, 0}, done)));
     CgDirBody db{p, r, S->ds, 0.0, opt & 1, 0, 0};
     return vec_map_launch(S->ctx, S->n, db, done);
+}
+
+// ---- CG inside one CTA (KRY_OPT_CG_ONE_CTA): problems whose CSR and four vectors fit the
+// shared memory of one SM (BASELINE config 0: 1138bus = 90 kB).  The 3-launch plan spends
+// ~10 us per iteration there on launch and grid-reduction latency; here the whole loop of
+// cg.py:113-158 runs in one launch out of shared memory, the phases separated by
+// __syncthreads() only.  Per element and per row the arithmetic is the reference's (same
+// expressions as the multi-CTA kernels), inner products are summed by a fixed block tree, the
+// scalar recurrence and stopping tests are the same functors (CgFinAp, CgFinRy) run by thread 0
+// on the same device scalar block, so status / history / done behave exactly as before.  State
+// in HBM is that of the 3-launch plan (x current, p materialised in "p").
+constexpr int KRY_ONE_CTA_THREADS = 1024;
+
+__global__ void __launch_bounds__(KRY_ONE_CTA_THREADS, 1)
+cg_one_cta_kernel(CsrView A, double *gx, double *gr, double *gp, double *gAp, const double *pd, int pmode,
+                  DevScalars *s, double *hist, long long n_iters)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double s_warp[1][32];
+    __shared__ double sh_scalar;
+    __shared__ int    sh_done;
+    const int n = A.nrows, tid = threadIdx.x, nt = blockDim.x;
+    if (s->done) return;
+    const int nnz = __ldg(A.rowptr + n);
+    // layout: val[nnz] | x[n] | r[n] | p[n] | Ap[n] | rowptr[n+1] | col[nnz]
+    double *val = reinterpret_cast<double *>(smem_raw);
+    double *x = val + nnz, *r = x + n, *p = r + n, *Ap = p + n;
+    int *rowptr = reinterpret_cast<int *>(Ap + n);
+    int *col = rowptr + n + 1;
+    for (int k = tid; k < nnz; k += nt) {
+        val[k] = __ldg(A.val + k);
+        col[k] = __ldg(A.col + k);
+    }
+    for (int i = tid; i <= n; i += nt) rowptr[i] = __ldg(A.rowptr + i);
+    for (int i = tid; i < n; i += nt) {
+        x[i] = gx[i];
+        r[i] = gr[i];
+        p[i] = gp[i];
+        Ap[i] = gAp[i];
+    }
+    __syncthreads();
+
+    for (long long it = 0; it < n_iters; ++it) {
+        // Ap = A p ; pAp = p.Ap ; alpha, curvature test                          cg.py:115-127
+        double acc[1] = {0.0};
+        for (int row = tid; row < n; row += nt) {
+            double sum = 0.0;
+            for (int k = rowptr[row]; k < rowptr[row + 1]; ++k)
+                sum = __dadd_rn(sum, __dmul_rn(val[k], p[col[k]]));
+            Ap[row] = sum;
+            acc[0] = __dadd_rn(acc[0], __dmul_rn(p[row], sum));
+        }
+        block_sum<1>(acc, s_warp);
+        if (tid == 0) {
+            CgFinAp{s}(acc);
+            sh_scalar = s->s[S_ALPHA];
+            sh_done = s->done;
+        }
+        __syncthreads();
+        if (sh_done) break;                     // x is left un-updated (cg.py:119-124)
+        const double alpha = sh_scalar;
+        // x += alpha p ; r += alpha Ap ; y = M r ; ry' = r.y ; beta, residNorm, loop test   cg.py:130-158
+        acc[0] = 0.0;
+        for (int i = tid; i < n; i += nt) {
+            x[i] = __dadd_rn(x[i], __dmul_rn(alpha, p[i]));
+            const double rn = __dadd_rn(r[i], __dmul_rn(alpha, Ap[i]));
+            r[i] = rn;
+            acc[0] = __dadd_rn(acc[0], __dmul_rn(rn, apply_diag(pd, pmode, i, rn)));
+        }
+        __syncthreads();                        // s_warp reuse
+        block_sum<1>(acc, s_warp);
+        if (tid == 0) {
+            CgFinRy{s, hist, 0}(acc);
+            sh_scalar = s->s[S_BETA];
+            sh_done = s->done;
+        }
+        __syncthreads();
+        const double beta = sh_scalar;
+        // p = beta p - r   (the reference updates p before it re-tests the loop condition)   cg.py:150-151
+        for (int i = tid; i < n; i += nt) p[i] = __dsub_rn(__dmul_rn(beta, p[i]), r[i]);
+        __syncthreads();
+        if (sh_done) break;
+    }
+    for (int i = tid; i < n; i += nt) {
+        gx[i] = x[i];
+        gr[i] = r[i];
+        gp[i] = p[i];
+        gAp[i] = Ap[i];
+    }
+}
+
+static size_t cg_one_cta_bytes(int64_t n, int64_t nnz)
+{
+    return (size_t)nnz * 12 + (size_t)n * 32 + (size_t)(n + 1) * 4 + 16;
+}
+
+static int cg_one_cta_iterate(kry_solver *S, int64_t n_iters)
+{
+    kry_ctx *c = S->ctx;
+    static bool attr_set = false;
+    if (!attr_set) {
+        KRY_CUDA(cudaFuncSetAttribute(cg_one_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(c->smem_optin - 1024)));
+        attr_set = true;
+    }
+    CsrView A = csr_view(S->A->A);
+    cg_one_cta_kernel<<<1, KRY_ONE_CTA_THREADS, S->one_cta_smem, c->stream>>>(
+        A, solver_vec(S, "x"), solver_vec(S, "r"), solver_vec(S, "p"), solver_vec(S, "Ap"), S->dinv,
+        S->precon_mode, S->ds, S->hist, (long long)n_iters);
+    c->launches++;
+    KRY_CUDA(cudaGetLastError());
+    return KRY_OK;
 }
 
 // Fused forms only: bring x and p to the state the 3-launch form would hold (see
@@ -1712,6 +1829,7 @@ extern "C" int kry_solver_iterate(kry_solver *S, int64_t n_iters)
                 "kry_solver_iterate: n_iters=%lld not in [0,%d)", (long long)n_iters, KRY_HIST_CAP / 2);
     kry_ctx *c = S->ctx;
     KRY_CUDA(cudaSetDevice(c->device));
+    if (S->method == KRY_CG && S->one_cta) return n_iters > 0 ? cg_one_cta_iterate(S, n_iters) : KRY_OK;
     int64_t left = n_iters;
     // Graph replay: not on sharded runs (NCCL in the sequence), not while per-launch
     // profiling events are being recorded, and only once the sequence ran un-captured

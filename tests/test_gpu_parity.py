@@ -210,14 +210,17 @@ def test_reduction_is_deterministic(ctx):
 
 
 # ==================================================== single-step solver parity
-@pytest.fixture(params=[0, 1, 2], ids=["cg3launch", "cgfuse1", "cgfuse2"])
+@pytest.fixture(params=[(0, 0), (1, 0), (2, 0), (2, 1)], ids=["cg3launch", "cgfuse1", "cgfuse2", "cg1cta"])
 def cg_form(ctx, request):
-    """Every CG test runs under the three launch plans (KRY_OPT_CG_FUSE): the 3-launch
-    form and the two fused 2-launch forms must be indistinguishable from outside."""
-    default = ctx.get_option(L().KRY_OPT_CG_FUSE)
-    ctx.set_option(L().KRY_OPT_CG_FUSE, request.param)
+    """Every CG test runs under the three multi-CTA launch plans (KRY_OPT_CG_FUSE: the 3-launch
+    form and the two fused 2-launch forms) and with the one-CTA loop for problems that fit one SM
+    (KRY_OPT_CG_ONE_CTA); all of them must be indistinguishable from outside."""
+    d_fuse, d_one = ctx.get_option(L().KRY_OPT_CG_FUSE), ctx.get_option(L().KRY_OPT_CG_ONE_CTA)
+    ctx.set_option(L().KRY_OPT_CG_FUSE, request.param[0])
+    ctx.set_option(L().KRY_OPT_CG_ONE_CTA, request.param[1])
     yield request.param
-    ctx.set_option(L().KRY_OPT_CG_FUSE, default)
+    ctx.set_option(L().KRY_OPT_CG_FUSE, d_fuse)
+    ctx.set_option(L().KRY_OPT_CG_ONE_CTA, d_one)
 
 
 def cg_case(name):
@@ -621,6 +624,8 @@ def test_cg_fused_forms_are_bit_identical_to_the_3_launch_form(ctx, name, precon
     d = np.abs(M.to_scipy().diagonal()) + 1.0
     A = upload(ctx, M, symmetric=True)
     default = ctx.get_option(L().KRY_OPT_CG_FUSE)
+    one_cta = ctx.get_option(L().KRY_OPT_CG_ONE_CTA)
+    ctx.set_option(L().KRY_OPT_CG_ONE_CTA, 0)           # this test is about the multi-CTA plans
     out = {}
     try:
         for form in (0, 1, 2):
@@ -639,6 +644,7 @@ def test_cg_fused_forms_are_bit_identical_to_the_3_launch_form(ctx, name, precon
             S._release()
     finally:
         ctx.set_option(L().KRY_OPT_CG_FUSE, default)
+        ctx.set_option(L().KRY_OPT_CG_ONE_CTA, one_cta)
     for form in (1, 2):
         for a, b in zip(out[0][:-1], out[form][:-1]):
             assert a[:4] == b[:4], (form, a[:4], b[:4])
@@ -804,3 +810,31 @@ def test_large_results_come_back_in_pooled_pinned_memory(ctx):
     assert result_pool.hits == hits + 1 and np.array_equal(b, np.arange(n))
     small = ctx.vector(np.ones(10)).download()
     assert small.base is None
+
+
+def test_cg_one_cta_loop_matches_oracle_and_counts_one_launch_per_call(ctx, golden):
+    """KRY_OPT_CG_ONE_CTA: 1138bus (90 kB) iterates inside one CTA -- one launch per
+    kry_solver_iterate call, same history as the oracle within the per-step bar."""
+    M = fixtures()["1138bus"]
+    n = M.shape[0]
+    rhs = M.matvec(np.ones(n))
+    A = upload(ctx, M, symmetric=True)
+    saved = ctx.get_option(L().KRY_OPT_CG_ONE_CTA)
+    ctx.set_option(L().KRY_OPT_CG_ONE_CTA, 1)
+    try:
+        S = dev().DeviceSolver(ctx, "cg", A)
+        S.setup(rhs, matvec_max=2 * n)
+        l0 = ctx.launch_count()
+        S.iterate(40)
+        assert ctx.launch_count() - l0 == 1
+        st = S.status()
+        ref = kr.cg_solve(M, rhs, matvec_max=40)
+        hist = S.drain_history(st)[:, 0]
+        assert st.n_matvec == 40 and rel(hist[:41], ref.residHistory[:41]) <= 1e-9
+        st = S.run(200)
+        full = kr.cg_solve(M, rhs)
+        assert abs(st.n_matvec - full.nMatvec) <= 0.01 * full.nMatvec       # cond ~ 1e7: SURVEY.md section 6
+        x = S.solution()
+        assert abs(np.linalg.norm(rhs - M.matvec(x)) - np.linalg.norm(rhs - M.matvec(full.x))) <= RTOL_FINAL * np.linalg.norm(rhs)
+    finally:
+        ctx.set_option(L().KRY_OPT_CG_ONE_CTA, saved)
