@@ -263,6 +263,16 @@ int kry_solver_setup_dev(kry_solver *S, const kry_vec *rhs, const kry_vec *guess
  * formulas and latch `done`; launches after that are no-ops.                       */
 int kry_solver_iterate(kry_solver *S, int64_t n_iters);
 int kry_solver_status_read(kry_solver *S, kry_solver_status *out);   /* synchronises */
+/* Pipelined form of the same read (candidate): `enqueue` queues a copy of the device status
+ * block into pinned host memory (slot 0 or 1) behind everything enqueued so far and returns at
+ * once; `wait` blocks until that copy has landed -- not until later work has finished -- so the
+ * host can keep one chunk of iterations in flight while it replays the history of the previous
+ * one.  kry_solver_history_nowait reads history entries on a separate copy stream for the same
+ * reason (only entries counted by a status that has been waited for are final).             */
+int kry_solver_status_enqueue(kry_solver *S, int slot);
+int kry_solver_status_wait(kry_solver *S, int slot, kry_solver_status *out);
+int kry_solver_history_nowait(kry_solver *S, int64_t first, int64_t count, double *host,
+                              int32_t *width);
 /* Per-iteration scalars recorded on device (residHistory replay, log lines):
  * `width` doubles per entry (CG: residNorm,pAp; others: residNorm).                */
 int kry_solver_history(kry_solver *S, int64_t first, int64_t count, double *host,

@@ -125,6 +125,9 @@ PROTOTYPES = {
     "kry_solver_iterate": (C.c_int, [handle, C.c_int64]),
     "kry_solver_status_read": (C.c_int, [handle, C.POINTER(SolverStatus)]),
     "kry_solver_history": (C.c_int, [handle, C.c_int64, C.c_int64, C.c_void_p, c_i32p]),
+    "kry_solver_status_enqueue": (C.c_int, [handle, C.c_int]),
+    "kry_solver_status_wait": (C.c_int, [handle, C.c_int, C.POINTER(SolverStatus)]),
+    "kry_solver_history_nowait": (C.c_int, [handle, C.c_int64, C.c_int64, C.c_void_p, c_i32p]),
     "kry_solver_solution": (C.c_int, [handle, C.c_void_p]),
     "kry_solver_get_vector": (C.c_int, [handle, C.c_char_p, C.c_void_p]),
     "kry_solver_set_vector": (C.c_int, [handle, C.c_char_p, C.c_void_p]),

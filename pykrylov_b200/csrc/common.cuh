@@ -68,6 +68,7 @@ struct ReduceWs {
 struct kry_ctx {
     int          device;
     cudaStream_t stream;
+    cudaStream_t copy_stream;  // small D2H reads that must not queue behind the compute stream (lazy)
     cudaEvent_t  ev0, ev1;
     int          sm_count;
     int64_t      l2_bytes;

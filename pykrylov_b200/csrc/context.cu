@@ -143,6 +143,8 @@ extern "C" int kry_ctx_destroy(kry_ctx *c)
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    c->copy_stream = nullptr;
     c->stream = nullptr;
     c->scalars = c->partials = c->sums = nullptr;
     c->counter = nullptr;

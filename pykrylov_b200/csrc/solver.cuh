@@ -80,6 +80,9 @@ struct kry_solver {
     int               cg_fuse;          // CG launch plan latched at setup (KRY_OPT_CG_FUSE)
     bool              fresh;            // fused CG: nothing pending, p sits in the next trip's source buffer
     bool              one_cta;          // CG: the whole loop runs inside one CTA (KRY_OPT_CG_ONE_CTA)
+    DevScalars       *snap_host[2];     // pinned status snapshots (kry_solver_status_enqueue / _wait)
+    cudaEvent_t       snap_ev[2];
+    bool              snap_pending[2];
     size_t            one_cta_smem;     // its dynamic shared memory
 };
 

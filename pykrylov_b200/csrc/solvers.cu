@@ -1677,6 +1677,12 @@ extern "C" int kry_solver_destroy(kry_solver *S)
     if (!S) return KRY_OK;
     if (!S->ctx->closed) cudaStreamSynchronize(S->ctx->stream);
     solver_drop_graph(S);
+    for (int k = 0; k < 2; ++k) {
+        if (S->snap_host[k]) {
+            cudaEventDestroy(S->snap_ev[k]);
+            cudaFreeHost(S->snap_host[k]);
+        }
+    }
     cudaFree(S->slab);
     cudaFree(S->ds);
     cudaFree(S->hist);
@@ -1708,6 +1714,7 @@ static int solver_setup_common(kry_solver *S, int guess, const kry_solver_params
                 "kry_solver_setup: MINRES window %d not in [1,16]", p->window);
     solver_drop_graph(S);
     S->warm = false;
+    S->snap_pending[0] = S->snap_pending[1] = false;
     KRY_REQUIRE(!(S->method == KRY_MINRES && S->precon_mode), KRY_ERR_UNSUPPORTED,
                 "kry_solver_setup: preconditioned MINRES is not device-resident yet");
     S->params = *p;
@@ -1856,6 +1863,8 @@ extern "C" int kry_solver_iterate(kry_solver *S, int64_t n_iters)
     return KRY_OK;
 }
 
+static void status_decode(const kry_solver *S, const DevScalars &h, kry_solver_status *out);
+
 extern "C" int kry_solver_status_read(kry_solver *S, kry_solver_status *out)
 {
     KRY_REQUIRE(S && out, KRY_ERR_INVALID, "kry_solver_status_read: NULL argument");
@@ -1864,6 +1873,39 @@ extern "C" int kry_solver_status_read(kry_solver *S, kry_solver_status *out)
     KRY_CUDA(cudaMemcpyAsync(&h, S->ds, sizeof(h), cudaMemcpyDeviceToHost, S->ctx->stream));
     KRY_CUDA(cudaStreamSynchronize(S->ctx->stream));
     KRY_CUDA(cudaGetLastError());
+    status_decode(S, h, out);
+    return KRY_OK;
+}
+
+extern "C" int kry_solver_status_enqueue(kry_solver *S, int slot)
+{
+    KRY_REQUIRE(S && (slot == 0 || slot == 1), KRY_ERR_INVALID, "kry_solver_status_enqueue: bad argument");
+    KRY_CTX_LIVE(S->ctx, "kry_solver_status_enqueue");
+    KRY_REQUIRE(S->ready, KRY_ERR_STATE, "kry_solver_status_enqueue: call kry_solver_setup first");
+    if (!S->snap_host[slot]) {
+        KRY_CUDA(cudaMallocHost((void **)&S->snap_host[slot], sizeof(DevScalars)));
+        KRY_CUDA(cudaEventCreateWithFlags(&S->snap_ev[slot], cudaEventDisableTiming));
+    }
+    KRY_CUDA(cudaMemcpyAsync(S->snap_host[slot], S->ds, sizeof(DevScalars), cudaMemcpyDeviceToHost,
+                             S->ctx->stream));
+    KRY_CUDA(cudaEventRecord(S->snap_ev[slot], S->ctx->stream));
+    S->snap_pending[slot] = true;
+    return KRY_OK;
+}
+
+extern "C" int kry_solver_status_wait(kry_solver *S, int slot, kry_solver_status *out)
+{
+    KRY_REQUIRE(S && out && (slot == 0 || slot == 1), KRY_ERR_INVALID, "kry_solver_status_wait: bad argument");
+    KRY_CTX_LIVE(S->ctx, "kry_solver_status_wait");
+    KRY_REQUIRE(S->snap_pending[slot], KRY_ERR_STATE, "kry_solver_status_wait: nothing enqueued in slot %d", slot);
+    KRY_CUDA(cudaEventSynchronize(S->snap_ev[slot]));
+    S->snap_pending[slot] = false;
+    status_decode(S, *S->snap_host[slot], out);
+    return KRY_OK;
+}
+
+static void status_decode(const kry_solver *S, const DevScalars &h, kry_solver_status *out)
+{
     memset(out, 0, sizeof(*out));
     out->done = h.done;
     out->definite = h.definite;
@@ -1916,18 +1958,35 @@ extern "C" int kry_solver_status_read(kry_solver *S, kry_solver_status *out)
             out->aux[7] = h.s[S_RHO_NEXT];
             break;
     }
-    return KRY_OK;
 }
+
+static int solver_history_on(kry_solver *S, cudaStream_t st, int64_t first, int64_t count, double *host,
+                             int32_t *width);
 
 extern "C" int kry_solver_history(kry_solver *S, int64_t first, int64_t count, double *host,
                                   int32_t *width)
 {
     KRY_REQUIRE(S && (host || count == 0), KRY_ERR_INVALID, "kry_solver_history: NULL argument");
     KRY_CTX_LIVE(S->ctx, "kry_solver_history");
+    return solver_history_on(S, S->ctx->stream, first, count, host, width);
+}
+
+extern "C" int kry_solver_history_nowait(kry_solver *S, int64_t first, int64_t count, double *host,
+                                         int32_t *width)
+{
+    KRY_REQUIRE(S && (host || count == 0), KRY_ERR_INVALID, "kry_solver_history_nowait: NULL argument");
+    KRY_CTX_LIVE(S->ctx, "kry_solver_history_nowait");
+    kry_ctx *c = S->ctx;
+    if (!c->copy_stream) KRY_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    return solver_history_on(S, c->copy_stream, first, count, host, width);
+}
+
+static int solver_history_on(kry_solver *S, cudaStream_t st, int64_t first, int64_t count, double *host,
+                             int32_t *width)
+{
     if (width) *width = S->hist_width;
     KRY_REQUIRE(first >= 0 && count >= 0 && count <= KRY_HIST_CAP, KRY_ERR_INVALID,
                 "kry_solver_history: range [%lld,+%lld) invalid", (long long)first, (long long)count);
-    cudaStream_t st = S->ctx->stream;
     const int w = S->hist_width;
     int64_t done = 0;
     while (done < count) {      // the ring may wrap

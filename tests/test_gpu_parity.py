@@ -838,3 +838,41 @@ def test_cg_one_cta_loop_matches_oracle_and_counts_one_launch_per_call(ctx, gold
         assert abs(np.linalg.norm(rhs - M.matvec(x)) - np.linalg.norm(rhs - M.matvec(full.x))) <= RTOL_FINAL * np.linalg.norm(rhs)
     finally:
         ctx.set_option(L().KRY_OPT_CG_ONE_CTA, saved)
+
+
+def test_pipelined_host_drive_gives_the_same_results(ctx):
+    """_engine.drive(overlap=True) keeps one chunk in flight (status snapshots through
+    kry_solver_status_enqueue/_wait, history on the copy stream); results, histories and
+    counters must not depend on it or on the check interval."""
+    import pykrylov_b200._engine as eng
+    from pykrylov_b200.linop import csr_operator
+    from pykrylov_b200.cg import CG
+    from pykrylov_b200.bicgstab import BiCGSTAB
+    from pykrylov_b200.minres import Minres
+    M = load_mtx(mtx("1138bus"))
+    op = csr_operator(M.shape, M.indptr, M.indices, M.data, symmetric=True, context=ctx)
+    rhs = M.matvec(np.ones(M.shape[0]))
+    N = load_mtx(mtx("jpwh_991"))
+    nop = csr_operator(N.shape, N.indptr, N.indices, N.data, context=ctx)
+    nrhs = N.matvec(np.random.default_rng(3).standard_normal(N.shape[0]))
+    real = eng.drive
+    out = {}
+    try:
+        for overlap in (False, True):
+            eng.drive = (lambda S, k, cb=None, overlap=True, _o=overlap: real(S, k, cb, overlap=_o and overlap))
+            for interval in (7, 64):
+                cg = CG(op, check_interval=interval)
+                cg.solve(rhs)
+                bi = BiCGSTAB(nop, reltol=1e-8, check_interval=interval)
+                bi.solve(nrhs, matvec_max=2 * N.shape[0])
+                mr = Minres(op, check_interval=interval)
+                mr.solve(rhs, show=False, check=False, itnlim=300)
+                out[(overlap, interval)] = (cg.nMatvec, tuple(cg.residHistory), cg.bestSolution.copy(),
+                                            bi.nMatvec, tuple(bi.residHistory), bi.bestSolution.copy(),
+                                            mr.itn, mr.istop, tuple(mr.residHistory), mr.x.copy())
+    finally:
+        eng.drive = real
+    base = out[(False, 7)]
+    for key, val in out.items():
+        for a, b in zip(base, val):
+            assert (np.array_equal(a, b) if isinstance(a, np.ndarray) else a == b), key
