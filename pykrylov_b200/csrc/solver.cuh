@@ -44,6 +44,8 @@ enum {
     //            2: p was materialised into P[n_iter&1] by a trip that then stopped (curvature exit)
     //   S_XPEND  1: x += alpha * P[(n_iter-1)&1] is pending (form 2)
     S_PSTATE, S_XPEND,
+    // fused MINRES plan (KRY_OPT_MINRES_FUSE): 1 = the w / x update of trip n_iter-1 is still owed
+    M_WPEND,
     S_COUNT
 };
 constexpr int KRY_NSCAL = 64;
@@ -80,6 +82,7 @@ struct kry_solver {
     int               cg_fuse;          // CG launch plan latched at setup (KRY_OPT_CG_FUSE)
     bool              fresh;            // fused CG: nothing pending, p sits in the next trip's source buffer
     bool              one_cta;          // CG: the whole loop runs inside one CTA (KRY_OPT_CG_ONE_CTA)
+    int               minres_fuse;      // MINRES launch plan latched at setup (KRY_OPT_MINRES_FUSE)
     DevScalars       *snap_host[2];     // pinned status snapshots (kry_solver_status_enqueue / _wait)
     cudaEvent_t       snap_ev[2];
     bool              snap_pending[2];

@@ -1367,10 +1367,13 @@ struct MinBodyR2 {            // y = (-alfa/beta) r2 + y' ; beta'^2 = r2new . (M
 struct MinFinQR {
     DevScalars *s;
     double     *hist;
+    int         fuse;        // 2-launch plan: this launch is the last of the trip -> it latches `done`
+                             // itself and records that the w / x update of the trip is still owed
     __device__ void operator()(const double *t) const
     {
         const double eps = 2.220446049250313e-16;
         double *v = s->s;
+        if (fuse) v[M_WPEND] = 0.0;      // the body of this launch paid what the previous trip owed
         s->n_iter++;
         s->n_matvec++;
         const long long itn = s->n_iter;
@@ -1456,8 +1459,107 @@ struct MinFinQR {
             if (test2 <= s->rtol) s->istop = 2;
             if (test1 <= s->rtol) s->istop = 1;
         }
+        if (fuse) {
+            v[M_WPEND] = 1.0;                                                // minres.py:294-297 of this trip
+            if (s->istop > 0 || itn >= s->matvec_max) s->done = 1;           // :381, :218
+            return;
+        }
         // `done` is latched by K3 (the x update of this trip must still run)
         if (s->istop > 0 || itn >= s->matvec_max) s->skip_half = 1;          // :381, :218
+    }
+};
+
+// 2-launch plan: K2 of this trip + the w / x update the previous trip still owes.  The owed
+// update uses the previous trip's buffers (y_prev = this trip's r1, the two w buffers swapped)
+// and the scalars its MinFinQR left (this launch's finalize overwrites them only after every
+// CTA has finished its body).
+template <bool PEND>
+struct MinBodyR2W {
+    static constexpr int kMinBlocks = 4;       // 7 vectors in flight: allow 64 registers
+    double       *yn;                          // K2 part (as MinBodyR2, no preconditioner)
+    const double *r2;
+    double       *wnew, *x;                    // owed part (as MinBodyW, previous trip's roles)
+    const double *w2, *yold;
+    DevScalars   *s;
+    double        c, inv, oldeps, delta, denom, phi;
+    __device__ void init()
+    {
+        c = s->s[M_C_R2];
+        inv = s->s[M_INVBETA];
+        oldeps = s->s[M_OLDEPS];
+        delta = s->s[M_DELTA];
+        denom = s->s[M_DENOM];
+        phi = s->s[M_PHI];
+    }
+    __device__ void operator()(int i, double *acc) const
+    {
+        const double yi = __dadd_rn(__dmul_rn(c, r2[i]), yn[i]);             // :246
+        yn[i] = yi;
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(yi, yi));                       // :251
+        if constexpr (PEND) {
+            const double vi = __dmul_rn(inv, yold[i]);                       // :237 of the previous trip
+            double wi = __dsub_rn(vi, __dmul_rn(oldeps, wnew[i]));           // :296
+            wi = __dsub_rn(wi, __dmul_rn(delta, w2[i]));
+            wi = __dmul_rn(wi, denom);
+            wnew[i] = wi;
+            x[i] = __dadd_rn(x[i], __dmul_rn(phi, wi));                      // :297
+        }
+    }
+    static constexpr bool kPair = true;
+    __device__ void pair(int i2, double *acc) const
+    {
+        const double2 rv = ld2(r2, i2);
+        double2 yv = ld2(yn, i2);
+        yv.x = __dadd_rn(__dmul_rn(c, rv.x), yv.x);
+        yv.y = __dadd_rn(__dmul_rn(c, rv.y), yv.y);
+        st2(yn, i2, yv);
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(yv.x, yv.x));
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(yv.y, yv.y));
+        if constexpr (PEND) {
+            const double2 yo = ld2(yold, i2), w1 = ld2(wnew, i2), wv = ld2(w2, i2);
+            double2 xv = ld2(x, i2), wn;
+            wn.x = __dmul_rn(__dsub_rn(__dsub_rn(__dmul_rn(inv, yo.x), __dmul_rn(oldeps, w1.x)), __dmul_rn(delta, wv.x)), denom);
+            wn.y = __dmul_rn(__dsub_rn(__dsub_rn(__dmul_rn(inv, yo.y), __dmul_rn(oldeps, w1.y)), __dmul_rn(delta, wv.y)), denom);
+            st2(wnew, i2, wn);
+            xv.x = __dadd_rn(xv.x, __dmul_rn(phi, wn.x));
+            xv.y = __dadd_rn(xv.y, __dmul_rn(phi, wn.y));
+            st2(x, i2, xv);
+        }
+    }
+};
+
+// Pay the owed w / x update (driven by the device flag and the device trip counter, so it
+// is right whichever launch latched `done`); afterwards the state is that of the 3-launch plan.
+struct MinSettleBody {
+    double     *R[3], *W[2], *x;
+    DevScalars *s;
+    double     *wnew;
+    const double *w2, *yold;
+    double      inv, oldeps, delta, denom, phi;
+    int         pend;
+    __device__ void init()
+    {
+        pend = (s->s[M_WPEND] != 0.0);
+        const long long t = s->n_iter - 1;              // the trip whose update is owed
+        const int k = (int)(((t % 3) + 3) % 3), j = (int)(((t % 2) + 2) % 2);
+        yold = R[k];
+        wnew = W[1 - j];
+        w2 = W[j];
+        inv = s->s[M_INVBETA];
+        oldeps = s->s[M_OLDEPS];
+        delta = s->s[M_DELTA];
+        denom = s->s[M_DENOM];
+        phi = s->s[M_PHI];
+    }
+    __device__ void operator()(int i) const
+    {
+        if (!pend) return;
+        const double vi = __dmul_rn(inv, yold[i]);
+        double wi = __dsub_rn(vi, __dmul_rn(oldeps, wnew[i]));
+        wi = __dsub_rn(wi, __dmul_rn(delta, w2[i]));
+        wi = __dmul_rn(wi, denom);
+        wnew[i] = wi;
+        x[i] = __dadd_rn(x[i], __dmul_rn(phi, wi));
     }
 };
 
@@ -1564,6 +1666,8 @@ static int minres_setup(kry_solver *S, int)
     KRY_CUDA(cudaMemsetAsync(solver_vec(S, "wa"), 0, bytes, S->ctx->stream));   // :206-207
     KRY_CUDA(cudaMemsetAsync(solver_vec(S, "wb"), 0, bytes, S->ctx->stream));
     S->rot = 0;
+    S->minres_fuse = S->ctx->minres_fuse;
+    S->fresh = true;
     return KRY_OK;
 }
 
@@ -1581,11 +1685,39 @@ static int minres_iterate(kry_solver *S)
     MinGather g{r2, S->ds, 0.0};
     MinEpiY e{rn, r2, r1, S->ds, 0, 0, 0, 0};
     KRY_TRY((solver_spmv<1>(S, g, e, MinFinAlfa{S->ds}, done, r2)));
+    if (S->minres_fuse) {
+        // 2 launches: the w / x update of the PREVIOUS trip rides in this trip's second launch.
+        // Previous trip (rot-1): y_prev = R[(k+2)%3] = r1, it wrote W[1-j_prev] = W[j] from w2 = W[1-j].
+        MinFinQR fin{S->ds, S->hist, 1};
+        if (S->fresh) {
+            MinBodyR2W<false> b{rn, r2, nullptr, x, nullptr, nullptr, S->ds, 0, 0, 0, 0, 0, 0};
+            KRY_TRY((solver_pass<1>(S, b, fin, done)));
+        } else {
+            MinBodyR2W<true> b{rn, r2, W[j], x, W[1 - j], r1, S->ds, 0, 0, 0, 0, 0, 0};
+            KRY_TRY((solver_pass<1>(S, b, fin, done)));
+        }
+        S->fresh = false;
+        S->rot++;
+        return KRY_OK;
+    }
     MinBodyR2 b2{rn, nullptr, r2, S->dinv, 0, S->ds, 0.0};
-    KRY_TRY((solver_pass<1>(S, b2, MinFinQR{S->ds, S->hist}, done)));
+    KRY_TRY((solver_pass<1>(S, b2, MinFinQR{S->ds, S->hist, 0}, done)));
     MinBodyW bw{W[1 - j], x, W[j], r2, S->ds, 0, 0, 0, 0, 0};
     KRY_TRY((solver_pass<1>(S, bw, MinFinW{S->ds}, done)));
     S->rot++;
+    return KRY_OK;
+}
+
+static int minres_settle(kry_solver *S)
+{
+    if (S->method != KRY_MINRES || !S->minres_fuse || !S->ready) return KRY_OK;
+    MinSettleBody b{{solver_vec(S, "ra"), solver_vec(S, "rb"), solver_vec(S, "rc")},
+                    {solver_vec(S, "wa"), solver_vec(S, "wb")}, solver_vec(S, "x"), S->ds,
+                    nullptr, nullptr, nullptr, 0, 0, 0, 0, 0, 0};
+    KRY_TRY(vec_map_launch(S->ctx, S->n, b, &S->ctx->never_done[0]));
+    KRY_CUDA(cudaMemsetAsync(&S->ds->s[M_WPEND], 0, sizeof(double), S->ctx->stream));
+    S->fresh = true;
+    S->warm = false;      // the next trip must run un-captured (PEND = false variant)
     return KRY_OK;
 }
 
@@ -2006,6 +2138,7 @@ extern "C" int kry_solver_solution(kry_solver *S, double *x_host)
     KRY_REQUIRE(S && x_host, KRY_ERR_INVALID, "kry_solver_solution: NULL argument");
     KRY_CTX_LIVE(S->ctx, "kry_solver_solution");
     KRY_TRY(cg_settle(S));
+    KRY_TRY(minres_settle(S));
     KRY_CUDA(cudaMemcpyAsync(x_host, solver_vec(S, "x"), (size_t)S->n * sizeof(double),
                              cudaMemcpyDeviceToHost, S->ctx->stream));
     KRY_CUDA(cudaStreamSynchronize(S->ctx->stream));
@@ -2042,6 +2175,7 @@ extern "C" int kry_solver_get_vector(kry_solver *S, const char *name, double *ho
     KRY_REQUIRE(S && name && host, KRY_ERR_INVALID, "kry_solver_get_vector: NULL argument");
     KRY_CTX_LIVE(S->ctx, "kry_solver_get_vector");
     KRY_TRY(cg_settle(S));
+    KRY_TRY(minres_settle(S));
     double *d = solver_vec_logical(S, name);
     KRY_REQUIRE(d, KRY_ERR_INVALID, "kry_solver_get_vector: no vector named '%s'", name);
     KRY_CUDA(cudaMemcpyAsync(host, d, (size_t)S->n * sizeof(double), cudaMemcpyDeviceToHost,
@@ -2055,6 +2189,7 @@ extern "C" int kry_solver_set_vector(kry_solver *S, const char *name, const doub
     KRY_REQUIRE(S && name && host, KRY_ERR_INVALID, "kry_solver_set_vector: NULL argument");
     KRY_CTX_LIVE(S->ctx, "kry_solver_set_vector");
     KRY_TRY(cg_settle(S));
+    KRY_TRY(minres_settle(S));
     double *d = solver_vec_logical(S, name);
     KRY_REQUIRE(d, KRY_ERR_INVALID, "kry_solver_set_vector: no vector named '%s'", name);
     KRY_CUDA(cudaMemcpyAsync(d, host, (size_t)S->n * sizeof(double), cudaMemcpyHostToDevice,

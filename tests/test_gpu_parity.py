@@ -390,8 +390,17 @@ def minres_case():
     return Sm, Sm.matvec(np.ones(Sm.shape[0]))
 
 
+@pytest.fixture(params=[0, 1], ids=["minres3launch", "minres2launch"])
+def minres_plan(ctx, request):
+    """MINRES tests run under both launch plans (KRY_OPT_MINRES_FUSE)."""
+    default = ctx.get_option(L().KRY_OPT_MINRES_FUSE)
+    ctx.set_option(L().KRY_OPT_MINRES_FUSE, request.param)
+    yield request.param
+    ctx.set_option(L().KRY_OPT_MINRES_FUSE, default)
+
+
 @pytest.mark.parametrize("shift", [0.0, 0.5])
-def test_minres_single_step_from_identical_state(ctx, shift):
+def test_minres_single_step_from_identical_state(ctx, shift, minres_plan):
     M, rhs = minres_case()
     A = upload(ctx, M, symmetric=True)
     st = kr.minres_start(M, rhs, shift=shift)
@@ -523,7 +532,7 @@ def test_short_runs_reproduce_doc_tables(ctx, golden):
         assert "%8.2e" % (np.linalg.norm(ks.bestSolution - e) / np.sqrt(n)) == err
 
 
-def test_minres_public_api(ctx, golden, capsys):
+def test_minres_public_api(ctx, golden, capsys, minres_plan):
     from pykrylov_b200.linop import csr_operator
     from pykrylov_b200.minres import Minres
     M, rhs = minres_case()
@@ -876,3 +885,37 @@ def test_pipelined_host_drive_gives_the_same_results(ctx):
     for key, val in out.items():
         for a, b in zip(base, val):
             assert (np.array_equal(a, b) if isinstance(a, np.ndarray) else a == b), key
+
+
+def test_minres_2_launch_plan_is_bit_identical_to_the_3_launch_plan(ctx):
+    """KRY_OPT_MINRES_FUSE only moves the w / x update of a trip into the next trip's second
+    launch: x, w, w2, r1, r2, every scalar and the history are the same bits, read mid-run
+    (which settles what is owed) or at the end, through graph replays or single launches."""
+    S0 = fixtures()["jpwh_991"].to_scipy()
+    M = CsrRef.from_scipy(((S0 + S0.T) * 0.5).tocsr())
+    n = M.shape[0]
+    rhs = M.matvec(np.ones(n))
+    A = upload(ctx, M, symmetric=True)
+    default = ctx.get_option(L().KRY_OPT_MINRES_FUSE)
+    out = {}
+    try:
+        for plan in (0, 1):
+            ctx.set_option(L().KRY_OPT_MINRES_FUSE, plan)
+            S = dev().DeviceSolver(ctx, "minres", A)
+            S.setup(rhs, matvec_max=10 ** 6, rtol=0.0, etol=0.0, window=5)
+            snaps = []
+            for chunk in (1, 2, 40, 3, 31):
+                S.iterate(chunk)
+                st = S.status()
+                snaps.append((st.n_iter, st.resid_norm, tuple(st.aux[:13])) +
+                             tuple(S.get_vector(v) for v in ("x", "w", "w2", "r1", "r2")))
+            snaps.append(S.drain_history())
+            out[plan] = snaps
+            S._release()
+    finally:
+        ctx.set_option(L().KRY_OPT_MINRES_FUSE, default)
+    for a, b in zip(out[0][:-1], out[1][:-1]):
+        assert a[:3] == b[:3], (a[:3], b[:3])
+        for u, v in zip(a[3:], b[3:]):
+            assert np.array_equal(u, v, equal_nan=True)
+    assert np.array_equal(out[0][-1], out[1][-1], equal_nan=True)
