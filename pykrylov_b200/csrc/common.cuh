@@ -155,8 +155,13 @@ int  kry_alloc(void **p, size_t bytes);
 ReduceWs kry_ws(kry_ctx *ctx);
 
 // ---------------------------------------------------------------- device
-#ifdef __CUDACC__
+// KRY_EMULATE: tests/emu compiles the device *logic* of this library (kernel loops, solver
+// functors, launch sequences) for the host with g++ to check it against the oracle without a
+// GPU.  It is test infrastructure: nothing in the product defines the macro, and the blocks it
+// switches off below (warp shuffles, PTX) have their stand-ins in tests/emu/emu_device.h.
+#if defined(__CUDACC__) || defined(KRY_EMULATE)
 
+#ifndef KRY_EMULATE
 __device__ __forceinline__ double warp_sum(double v)
 {
     // xor butterfly: every lane ends with the same, order-fixed sum
@@ -266,6 +271,7 @@ __device__ __forceinline__ void block_reduce_finalize(double (&acc)[ND], const R
         if (!ws.defer) fin(tot);
     }
 }
+#endif  // !KRY_EMULATE
 
 // Bodies that also provide pair(i2[, acc]) -- elements 2*i2 and 2*i2+1 through one
 // 16-byte access per vector -- are run in that form by the vector kernels.
@@ -283,6 +289,7 @@ __device__ __forceinline__ void st2(double *p, int i2, double2 v)
     reinterpret_cast<double2 *>(p)[i2] = v;
 }
 
+#ifndef KRY_EMULATE
 // L2 eviction-priority hints (createpolicy + ld/st .L2::cache_hint).  The three CG
 // launches hand 80 MB vectors to each other (Ap: K1->K2, r: K2->K3, p: K3->K1); marking
 // the producer's stores evict_last and the pure streams (CSR arrays, x) evict_first lets
@@ -336,6 +343,7 @@ __device__ __forceinline__ void st_hint(double *a, double v, uint64_t pol)
 {
     asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(a), "d"(v), "l"(pol) : "memory");
 }
+#endif  // !KRY_EMULATE
 
 struct NoFin {
     __device__ void operator()(const double *) const {}
@@ -409,4 +417,4 @@ vec_map_kernel(int64_t n, Body body, const int *done)
     }
 }
 
-#endif  // __CUDACC__
+#endif  // __CUDACC__ || KRY_EMULATE

@@ -55,6 +55,9 @@ int spmv_launch(kry_csr *M, bool trans, Gather g, Epi epi, Fin fin, const int *d
     // Laplacian); rows long enough to serialise a thread go to the nnz-stream kernel.
     int kind = M->kind;
     if (kind == KRY_SPMV_AUTO) kind = (m->max_row <= 64) ? KRY_SPMV_ROW : KRY_SPMV_STREAM;
+#ifdef KRY_EMULATE
+    if (kind == KRY_SPMV_STREAM || kind == KRY_SPMV_TMA) kind = KRY_SPMV_ROW;   // host emulation: row loops only
+#endif
     const int tile = M->tile_nnz ? M->tile_nnz : KRY_DEFAULT_TILE;
     const int threads = M->threads ? M->threads : KRY_DEFAULT_THREADS;
     const size_t budget = (size_t)c->smem_optin - 2048;   // static smem of the reduction + barriers
@@ -117,6 +120,17 @@ int spmv_launch(kry_csr *M, bool trans, Gather g, Epi epi, Fin fin, const int *d
     const bool prof = ND > 0 && c->prof_ev && c->prof_n < c->prof_cap;
     if (prof) KRY_CUDA(cudaEventRecord(c->prof_ev[2 * c->prof_n], c->stream));
 
+#ifdef KRY_EMULATE
+    (void)cap;
+    (void)smem;
+    (void)threads;
+    if (kind == KRY_SPMV_ROW)
+        emu_launch<ND>(grid, 256, ws, fin, [&] { spmv_row_kernel<ND, Gather, Epi, Fin>(A, g, epi, ws, fin, done); });
+    else if (kind == KRY_SPMV_ROWB8)
+        emu_launch<ND>(grid, 256, ws, fin, [&] { spmv_rowb_kernel<ND, 8, Gather, Epi, Fin>(A, g, epi, ws, fin, done); });
+    else
+        emu_launch<ND>(grid, 256, ws, fin, [&] { spmv_rowb_kernel<ND, 4, Gather, Epi, Fin>(A, g, epi, ws, fin, done); });
+#else
     if (kind == KRY_SPMV_ROW) {
         spmv_row_kernel<ND, Gather, Epi, Fin><<<grid, 256, 0, c->stream>>>(A, g, epi, ws, fin, done);
     } else if (kind == KRY_SPMV_ROWPF) {
@@ -136,6 +150,7 @@ int spmv_launch(kry_csr *M, bool trans, Gather g, Epi epi, Fin fin, const int *d
         KRY_TRY(set_max_smem(k, c, smem));
         k<<<grid, threads, smem, c->stream>>>(A, cap, g, epi, ws, fin, done);
     }
+#endif
     if (prof) {
         KRY_CUDA(cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], c->stream));
         c->prof_n++;
@@ -153,7 +168,11 @@ int vec_pass_launch(kry_ctx *c, int64_t n, Body body, Fin fin, const int *done, 
     ReduceWs ws = kry_ws(c);
     ws.defer = (defer == 1);
     ws.p2p = (defer == 2);
+#ifdef KRY_EMULATE
+    emu_launch<ND>(grid, 256, ws, fin, [&] { vec_pass_kernel<ND, Body, Fin>(n, body, ws, fin, done); });
+#else
     vec_pass_kernel<ND, Body, Fin><<<grid, 256, 0, c->stream>>>(n, body, ws, fin, done);
+#endif
     c->launches++;
     KRY_CUDA(cudaGetLastError());
     return KRY_OK;
@@ -162,7 +181,11 @@ int vec_pass_launch(kry_ctx *c, int64_t n, Body body, Fin fin, const int *done, 
 template <class Body>
 int vec_map_launch(kry_ctx *c, int64_t n, Body body, const int *done)
 {
+#ifdef KRY_EMULATE
+    emu_launch<0>(vec_grid(c, n, vec_map_kernel<Body>), 256, ReduceWs(), NoFin(), [&] { vec_map_kernel<Body>(n, body, done); });
+#else
     vec_map_kernel<Body><<<vec_grid(c, n, vec_map_kernel<Body>), 256, 0, c->stream>>>(n, body, done);
+#endif
     c->launches++;
     KRY_CUDA(cudaGetLastError());
     return KRY_OK;
@@ -171,7 +194,11 @@ int vec_map_launch(kry_ctx *c, int64_t n, Body body, const int *done)
 template <class Fin>
 int finalize_launch(kry_ctx *c, Fin fin, const int *done)
 {
+#ifdef KRY_EMULATE
+    emu_launch<0>(1, 32, ReduceWs(), NoFin(), [&] { finalize_kernel<Fin>(fin, c->sums, done); });
+#else
     finalize_kernel<Fin><<<1, 32, 0, c->stream>>>(fin, c->sums, done);
+#endif
     c->launches++;
     KRY_CUDA(cudaGetLastError());
     return KRY_OK;

@@ -100,7 +100,7 @@ static inline double *solver_vec(kry_solver *S, const char *name)
 
 int kry_allreduce_sums(kry_ctx *c, int n);
 
-#ifdef __CUDACC__
+#if defined(__CUDACC__) || defined(KRY_EMULATE)
 // append one history entry (width doubles)
 __device__ __forceinline__ void hist_push(DevScalars *s, double *hist, int width, double a, double b)
 {

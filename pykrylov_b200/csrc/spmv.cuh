@@ -45,7 +45,7 @@ static inline CsrView csr_view(const CsrDev &m)
     return v;
 }
 
-#ifdef __CUDACC__
+#if defined(__CUDACC__) || defined(KRY_EMULATE)
 
 struct GatherPlain {
     const double *x;
@@ -212,6 +212,7 @@ spmv_rowb_kernel(CsrView A, Gather g, Epi epi, ReduceWs ws, Fin fin, const int *
     if constexpr (ND > 0) block_reduce_finalize<ND>(acc, ws, fin);
 }
 
+#ifndef KRY_EMULATE      // shared-memory / TMA variants: CUDA only
 // ------------------------------------------------------- coalesced nnz stream
 // Dynamic smem: (tile_nnz + max_row) doubles of staged products.
 template <int ND, class Gather, class Epi, class Fin>
@@ -404,5 +405,6 @@ spmv_tma_kernel(CsrView A, int cap, Gather g, Epi epi, ReduceWs ws, Fin fin, con
     }
     if constexpr (ND > 0) block_reduce_finalize<ND>(acc, ws, fin);
 }
+#endif  // !KRY_EMULATE
 
-#endif  // __CUDACC__
+#endif  // __CUDACC__ || KRY_EMULATE

@@ -1,0 +1,454 @@
+// emu_context.cpp -- host stand-in for csrc/context.cu and csrc/comm.cu (TEST INFRASTRUCTURE ONLY,
+// see emu_device.h).  Contexts, vectors and CSR operators live in host memory; the hot-path entry
+// points (kry_spmv*, kry_multi_axpy_dot, kry_solver_*) come from the product's own ops.cu and
+// solvers.cu compiled next to this file.  Also defines the handful of CUDA runtime calls those
+// two files make, as plain host operations.
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+thread_local EmuDim threadIdx, blockIdx, blockDim, gridDim;
+thread_local double emu_tot[EMU_MAX_DOTS];
+thread_local int    emu_reduced;
+
+// ------------------------------------------------------------------ CUDA runtime, host edition
+extern "C" {
+cudaError_t cudaMalloc(void **p, size_t n) { *p = calloc(1, n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+cudaError_t cudaMallocHost(void **p, size_t n) { return cudaMalloc(p, n); }
+cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { if (n) memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { if (n) memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { if (n) memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaMemset(void *d, int v, size_t n) { if (n) memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
+cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
+cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = nullptr; return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *e = nullptr; return cudaSuccess; }
+cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = nullptr; return cudaSuccess; }
+cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *b, const void *, int, size_t) { *b = 2; return cudaSuccess; }
+cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(int *b, const void *, int, size_t, unsigned) { *b = 2; return cudaSuccess; }
+cudaError_t cudaFuncSetAttribute(const void *, cudaFuncAttribute, int) { return cudaSuccess; }
+// graphs are never used under emulation (use_graphs = 0); the symbols only have to link
+cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode) { return cudaErrorNotSupported; }
+cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t *g) { *g = nullptr; return cudaErrorNotSupported; }
+cudaError_t cudaGraphInstantiate(cudaGraphExec_t *, cudaGraph_t, unsigned long long) { return cudaErrorNotSupported; }
+cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t) { return cudaErrorNotSupported; }
+cudaError_t cudaGraphDestroy(cudaGraph_t) { return cudaSuccess; }
+cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return cudaSuccess; }
+}
+
+// ------------------------------------------------------------------ errors / misc
+static thread_local char g_err[512] = "";
+
+void kry_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *kry_last_error(void) { return g_err; }
+extern "C" int kry_abi_version(void) { return KRY_ABI_VERSION; }
+extern "C" int kry_device_count(int *count) { *count = 1; return KRY_OK; }
+
+int kry_alloc(void **p, size_t bytes)
+{
+    KRY_CUDA(cudaMalloc(p, bytes ? bytes : 256));
+    return KRY_OK;
+}
+
+int kry_ctx_ensure_partials(kry_ctx *, int) { return KRY_OK; }
+
+ReduceWs kry_ws(kry_ctx *c)
+{
+    ReduceWs ws;
+    memset(&ws, 0, sizeof(ws));
+    ws.sums = c->sums;
+    ws.nranks = 1;
+    return ws;
+}
+
+void kry_ctx_retain(kry_ctx *c) { c->refs++; }
+void kry_ctx_release(kry_ctx *c)
+{
+    if (--c->refs <= 0 && c->closed) delete c;
+}
+
+// ------------------------------------------------------------------ context
+extern "C" int kry_ctx_create(int device, kry_ctx **out)
+{
+    KRY_REQUIRE(out && device == 0, KRY_ERR_INVALID, "kry_ctx_create (emulation): device 0 only");
+    kry_ctx *c = new kry_ctx();
+    memset(c, 0, sizeof(*c));
+    c->sm_count = 2;                       // small grids: the host plays every thread
+    c->l2_bytes = 126 << 20;
+    c->smem_optin = 227 * 1024;
+    c->nranks = 1;
+    c->l2_hints = 1;
+    c->use_graphs = 0;
+    c->cg_fuse = 2;
+    KRY_TRY(kry_alloc((void **)&c->scalars, KRY_NUM_SLOTS * sizeof(double)));
+    KRY_TRY(kry_alloc((void **)&c->sums, 2 * KRY_MAX_DOTS * sizeof(double)));
+    KRY_TRY(kry_alloc((void **)&c->counter, 256));
+    KRY_TRY(kry_alloc((void **)&c->never_done, 256));
+    *out = c;
+    return KRY_OK;
+}
+
+extern "C" int kry_ctx_destroy(kry_ctx *c)
+{
+    if (!c || c->closed) return KRY_OK;
+    free(c->scalars);
+    free(c->sums);
+    free(c->counter);
+    free(c->never_done);
+    c->scalars = c->sums = nullptr;
+    c->counter = nullptr;
+    c->never_done = nullptr;
+    c->closed = 1;
+    if (c->refs <= 0) delete c;
+    return KRY_OK;
+}
+
+extern "C" int kry_ctx_sync(kry_ctx *) { return KRY_OK; }
+extern "C" int kry_ctx_props(kry_ctx *c, int64_t p[6])
+{
+    p[0] = c->sm_count; p[1] = p[2] = (int64_t)1 << 34; p[3] = 100; p[4] = c->l2_bytes; p[5] = c->smem_optin;
+    return KRY_OK;
+}
+extern "C" int kry_timer_start(kry_ctx *) { return KRY_OK; }
+extern "C" int kry_timer_stop(kry_ctx *, double *ms) { *ms = 0.0; return KRY_OK; }
+extern "C" int kry_flush_l2(kry_ctx *) { return KRY_OK; }
+extern "C" int kry_launch_count(kry_ctx *c, int64_t *n) { *n = c->launches; return KRY_OK; }
+extern "C" int kry_prof_enable(kry_ctx *, int) { return KRY_OK; }
+extern "C" int kry_prof_read(kry_ctx *, int64_t *n, double *ms) { *n = 0; *ms = 0.0; return KRY_OK; }
+extern "C" int kry_host_alloc(int64_t bytes, void **out) { *out = malloc(bytes > 0 ? bytes : 1); return *out ? KRY_OK : KRY_ERR_NOMEM; }
+extern "C" int kry_host_free(void *p) { free(p); return KRY_OK; }
+
+extern "C" int kry_ctx_set_option(kry_ctx *c, int option, int value)
+{
+    switch (option) {
+        case KRY_OPT_L2_HINTS: c->l2_hints = value; return KRY_OK;
+        case KRY_OPT_GRAPHS: return KRY_OK;                   // no graphs on the host
+        case KRY_OPT_CG_FUSE:
+            KRY_REQUIRE(value >= 0 && value <= 2, KRY_ERR_INVALID, "CG_FUSE=%d not in 0..2", value);
+            c->cg_fuse = value;
+            return KRY_OK;
+#ifdef KRY_OPT_MINRES_FUSE
+        case KRY_OPT_MINRES_FUSE: c->minres_fuse = value ? 1 : 0; return KRY_OK;
+#endif
+#ifdef KRY_OPT_CG_ONE_CTA
+        case KRY_OPT_CG_ONE_CTA: return KRY_OK;               // needs shared memory: not emulated
+#endif
+        default: kry_set_error("kry_ctx_set_option (emulation): option %d", option); return KRY_ERR_INVALID;
+    }
+}
+
+extern "C" int kry_ctx_get_option(kry_ctx *c, int option, int *value)
+{
+    switch (option) {
+        case KRY_OPT_L2_HINTS: *value = c->l2_hints; return KRY_OK;
+        case KRY_OPT_GRAPHS: *value = 0; return KRY_OK;
+        case KRY_OPT_P2P: *value = 0; return KRY_OK;
+        case KRY_OPT_CG_FUSE: *value = c->cg_fuse; return KRY_OK;
+        case KRY_OPT_CG_FUSE_SHARDS: *value = 0; return KRY_OK;
+#ifdef KRY_OPT_MINRES_FUSE
+        case KRY_OPT_MINRES_FUSE: *value = c->minres_fuse; return KRY_OK;
+#endif
+#ifdef KRY_OPT_CG_ONE_CTA
+        case KRY_OPT_CG_ONE_CTA: *value = 0; return KRY_OK;
+#endif
+        default: kry_set_error("kry_ctx_get_option (emulation): option %d", option); return KRY_ERR_INVALID;
+    }
+}
+
+// ------------------------------------------------------------------ vectors
+extern "C" int kry_vec_create_cap(kry_ctx *c, int64_t n, int64_t cap, kry_vec **out)
+{
+    KRY_REQUIRE(c && out && n >= 0 && cap >= n, KRY_ERR_INVALID, "kry_vec_create: bad argument");
+    kry_vec *v = new kry_vec();
+    v->ctx = c; v->n = n; v->cap = cap; v->owned = true;
+    KRY_TRY(kry_alloc((void **)&v->d, (size_t)(cap + 4) * sizeof(double)));
+    kry_ctx_retain(c);
+    *out = v;
+    return KRY_OK;
+}
+extern "C" int kry_vec_create(kry_ctx *c, int64_t n, kry_vec **out) { return kry_vec_create_cap(c, n, n, out); }
+extern "C" int kry_vec_destroy(kry_vec *v)
+{
+    if (!v) return KRY_OK;
+    free(v->d);
+    kry_ctx_release(v->ctx);
+    delete v;
+    return KRY_OK;
+}
+extern "C" int kry_vec_size(const kry_vec *v, int64_t *n) { *n = v->n; return KRY_OK; }
+extern "C" int kry_vec_upload(kry_vec *v, const double *h, int64_t n)
+{
+    KRY_REQUIRE(v && h, KRY_ERR_INVALID, "kry_vec_upload: NULL argument");
+    KRY_CTX_LIVE(v->ctx, "kry_vec_upload");
+    KRY_REQUIRE(n == v->n, KRY_ERR_SHAPE, "kry_vec_upload: host has %lld entries, vector %lld", (long long)n, (long long)v->n);
+    memcpy(v->d, h, (size_t)n * sizeof(double));
+    return KRY_OK;
+}
+extern "C" int kry_vec_download(const kry_vec *v, double *h, int64_t n)
+{
+    KRY_REQUIRE(v && h, KRY_ERR_INVALID, "kry_vec_download: NULL argument");
+    KRY_CTX_LIVE(v->ctx, "kry_vec_download");
+    KRY_REQUIRE(n == v->n, KRY_ERR_SHAPE, "kry_vec_download: host has %lld entries, vector %lld", (long long)n, (long long)v->n);
+    memcpy(h, v->d, (size_t)n * sizeof(double));
+    return KRY_OK;
+}
+extern "C" int kry_vec_read(const kry_vec *v, int64_t off, int64_t cnt, double *h)
+{
+    KRY_REQUIRE(v && h && off >= 0 && cnt >= 0 && off + cnt <= v->n, KRY_ERR_SHAPE, "kry_vec_read: bad range");
+    memcpy(h, v->d + off, (size_t)cnt * sizeof(double));
+    return KRY_OK;
+}
+extern "C" int kry_vec_fill(kry_vec *v, double value)
+{
+    KRY_REQUIRE(v, KRY_ERR_INVALID, "kry_vec_fill: NULL vector");
+    for (int64_t i = 0; i < v->n; ++i) v->d[i] = value;
+    return KRY_OK;
+}
+extern "C" int kry_vec_copy(kry_vec *dst, const kry_vec *src)
+{
+    KRY_REQUIRE(dst && src, KRY_ERR_INVALID, "kry_vec_copy: NULL vector");
+    KRY_REQUIRE(dst->n == src->n, KRY_ERR_SHAPE, "kry_vec_copy: sizes %lld != %lld", (long long)dst->n, (long long)src->n);
+    memcpy(dst->d, src->d, (size_t)src->n * sizeof(double));
+    return KRY_OK;
+}
+extern "C" int kry_scalars_read(kry_ctx *c, int first, int count, double *h)
+{
+    KRY_REQUIRE(c && h && first >= 0 && count >= 0 && first + count <= KRY_NUM_SLOTS, KRY_ERR_INVALID, "kry_scalars_read: range");
+    memcpy(h, c->scalars + first, (size_t)count * sizeof(double));
+    return KRY_OK;
+}
+extern "C" int kry_scalars_write(kry_ctx *c, int first, int count, const double *h)
+{
+    KRY_REQUIRE(c && h && first >= 0 && count >= 0 && first + count <= KRY_NUM_SLOTS, KRY_ERR_INVALID, "kry_scalars_write: range");
+    memcpy(c->scalars + first, h, (size_t)count * sizeof(double));
+    return KRY_OK;
+}
+
+// ------------------------------------------------------------------ operators
+static void csr_free(CsrDev &m)
+{
+    free(m.rowptr); free(m.col); free(m.val); free(m.rowblk);
+    m = CsrDev();
+}
+
+static int csr_from_host(CsrDev &m, int64_t nrows, int64_t ncols, const std::vector<int> &rp,
+                         const std::vector<int> &col, const std::vector<double> &val)
+{
+    const int64_t nnz = (int64_t)col.size();
+    m.nrows = nrows; m.ncols = ncols; m.nnz = nnz;
+    KRY_TRY(kry_alloc((void **)&m.rowptr, (size_t)(nrows + 1 + 8) * sizeof(int)));
+    KRY_TRY(kry_alloc((void **)&m.col, (size_t)(nnz + 8) * sizeof(int)));
+    KRY_TRY(kry_alloc((void **)&m.val, (size_t)(nnz + 8) * sizeof(double)));
+    memcpy(m.rowptr, rp.data(), (size_t)(nrows + 1) * sizeof(int));
+    if (nnz) {
+        memcpy(m.col, col.data(), (size_t)nnz * sizeof(int));
+        memcpy(m.val, val.data(), (size_t)nnz * sizeof(double));
+    }
+    int mx = 0;
+    for (int64_t i = 0; i < nrows; ++i) mx = std::max(mx, rp[i + 1] - rp[i]);
+    m.max_row = mx;
+    return KRY_OK;
+}
+
+// stable counting sort by column: inside a row of A^T the entries keep ascending original-row
+// order, which is what the device build (stable radix sort of (col, k)) produces
+static int csr_transpose(const CsrDev &A, CsrDev &T)
+{
+    std::vector<int> rp((size_t)A.ncols + 1, 0), col((size_t)A.nnz);
+    std::vector<double> val((size_t)A.nnz);
+    for (int64_t k = 0; k < A.nnz; ++k) rp[(size_t)A.col[k] + 1]++;
+    for (int64_t c = 0; c < A.ncols; ++c) rp[(size_t)c + 1] += rp[(size_t)c];
+    std::vector<int> next(rp.begin(), rp.end() - 1);
+    for (int64_t r = 0; r < A.nrows; ++r)
+        for (int k = A.rowptr[r]; k < A.rowptr[r + 1]; ++k) {
+            const int dst = next[(size_t)A.col[k]]++;
+            col[(size_t)dst] = (int)r;
+            val[(size_t)dst] = A.val[k];
+        }
+    return csr_from_host(T, A.ncols, A.nrows, rp, col, val);
+}
+
+int csr_build_partition(kry_ctx *, CsrDev &, int) { return KRY_OK; }    // nnz-tiled kernels: CUDA only
+
+static int new_csr(kry_ctx *c, uint32_t flags, int64_t nrows, int64_t ncols, const std::vector<int> &rp,
+                   const std::vector<int> &col, const std::vector<double> &val, kry_csr **out)
+{
+    kry_csr *M = new kry_csr();
+    M->ctx = c;
+    M->flags = flags;
+    KRY_TRY(csr_from_host(M->A, nrows, ncols, rp, col, val));
+    if ((flags & KRY_CSR_BUILD_TRANSPOSE) && !(flags & KRY_CSR_SYMMETRIC)) {
+        KRY_TRY(csr_transpose(M->A, M->T));
+        M->has_T = true;
+    }
+    kry_ctx_retain(c);
+    *out = M;
+    return KRY_OK;
+}
+
+extern "C" int kry_csr_create(kry_ctx *c, int64_t nrows, int64_t ncols, int64_t nnz, const int32_t *rowptr,
+                              const int32_t *col, const double *val, uint32_t flags, kry_csr **out)
+{
+    KRY_REQUIRE(c && out && rowptr && (nnz == 0 || (col && val)), KRY_ERR_INVALID, "kry_csr_create: NULL argument");
+    KRY_REQUIRE(nrows >= 0 && ncols >= 0 && nnz >= 0, KRY_ERR_INVALID, "csr: negative size");
+    KRY_REQUIRE(rowptr[0] == 0 && rowptr[nrows] == nnz, KRY_ERR_INVALID, "kry_csr_create: rowptr[0]=%d, rowptr[nrows]=%d but nnz=%lld",
+                rowptr[0], rowptr[nrows], (long long)nnz);
+    std::vector<int> rp(rowptr, rowptr + nrows + 1), cc(col, col + nnz);
+    std::vector<double> vv(val, val + nnz);
+    return new_csr(c, flags, nrows, ncols, rp, cc, vv, out);
+}
+
+extern "C" int kry_csr_destroy(kry_csr *M)
+{
+    if (!M) return KRY_OK;
+    csr_free(M->A);
+    csr_free(M->T);
+    kry_ctx_release(M->ctx);
+    delete M;
+    return KRY_OK;
+}
+
+extern "C" int kry_csr_shape(const kry_csr *M, int64_t *nrows, int64_t *ncols, int64_t *nnz)
+{
+    KRY_REQUIRE(M, KRY_ERR_INVALID, "kry_csr_shape: NULL operator");
+    if (nrows) *nrows = M->A.nrows;
+    if (ncols) *ncols = M->A.ncols;
+    if (nnz) *nnz = M->A.nnz;
+    return KRY_OK;
+}
+
+extern "C" int kry_csr_build_transpose(kry_csr *M)
+{
+    KRY_REQUIRE(M, KRY_ERR_INVALID, "kry_csr_build_transpose: NULL operator");
+    if (M->has_T || (M->flags & KRY_CSR_SYMMETRIC)) return KRY_OK;
+    KRY_TRY(csr_transpose(M->A, M->T));
+    M->has_T = true;
+    return KRY_OK;
+}
+
+extern "C" int kry_csr_download(const kry_csr *M, int transposed, int32_t *rowptr, int32_t *col, double *val)
+{
+    KRY_REQUIRE(M, KRY_ERR_INVALID, "kry_csr_download: NULL operator");
+    const CsrDev *m = &M->A;
+    if (transposed && !(M->flags & KRY_CSR_SYMMETRIC)) {
+        KRY_REQUIRE(M->has_T, KRY_ERR_STATE, "kry_csr_download: transpose not built");
+        m = &M->T;
+    }
+    memcpy(rowptr, m->rowptr, (size_t)(m->nrows + 1) * sizeof(int));
+    memcpy(col, m->col, (size_t)m->nnz * sizeof(int));
+    memcpy(val, m->val, (size_t)m->nnz * sizeof(double));
+    return KRY_OK;
+}
+
+extern "C" int kry_csr_diagonal(const kry_csr *M, double *diag)
+{
+    KRY_REQUIRE(M && diag, KRY_ERR_INVALID, "kry_csr_diagonal: NULL argument");
+    for (int64_t r = 0; r < M->A.nrows; ++r) {
+        double d = 0.0;
+        for (int k = M->A.rowptr[r]; k < M->A.rowptr[r + 1]; ++k)
+            if (M->A.col[k] == r) d += M->A.val[k];
+        diag[r] = d;
+    }
+    return KRY_OK;
+}
+
+extern "C" int kry_csr_set_kernel(kry_csr *M, int kind, int tile_nnz, int threads)
+{
+    KRY_REQUIRE(M, KRY_ERR_INVALID, "kry_csr_set_kernel: NULL operator");
+    M->kind = kind; M->tile_nnz = tile_nnz; M->threads = threads;
+    return KRY_OK;
+}
+
+// gallery: the stencils of csrc/context.cu restated as host loops (sorted columns)
+template <class Emit>
+static int stencil_rows(kry_ctx *c, int64_t n, int64_t row_begin, int64_t row_end, uint32_t flags, Emit emit,
+                        kry_csr **out)
+{
+    KRY_REQUIRE(c && out, KRY_ERR_INVALID, "stencil: NULL argument");
+    if (row_end < 0) row_end = n;
+    KRY_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= n, KRY_ERR_INVALID, "stencil: bad row range");
+    std::vector<int> rp(1, 0), col;
+    std::vector<double> val;
+    for (int64_t r = row_begin; r < row_end; ++r) {
+        emit(r, col, val);
+        rp.push_back((int)col.size());
+    }
+    KRY_TRY(new_csr(c, flags, row_end - row_begin, n, rp, col, val, out));
+    (*out)->halo.n_global = n;
+    (*out)->halo.row_begin = row_begin;
+    return KRY_OK;
+}
+
+extern "C" int kry_csr_create_poisson1d(kry_ctx *c, int64_t n, int64_t rb, int64_t re, uint32_t flags, kry_csr **out)
+{
+    return stencil_rows(c, n, rb, re, flags, [n](int64_t r, std::vector<int> &col, std::vector<double> &val) {
+        if (r > 0) { col.push_back((int)(r - 1)); val.push_back(-1.0); }
+        col.push_back((int)r); val.push_back(2.0);
+        if (r < n - 1) { col.push_back((int)(r + 1)); val.push_back(-1.0); }
+    }, out);
+}
+
+extern "C" int kry_csr_create_poisson2d(kry_ctx *c, int64_t g, int64_t rb, int64_t re, uint32_t flags, kry_csr **out)
+{
+    return stencil_rows(c, g * g, rb, re, flags, [g](int64_t r, std::vector<int> &col, std::vector<double> &val) {
+        const int64_t i = r / g, j = r % g;
+        if (i > 0) { col.push_back((int)(r - g)); val.push_back(-1.0); }
+        if (j > 0) { col.push_back((int)(r - 1)); val.push_back(-1.0); }
+        col.push_back((int)r); val.push_back(4.0);
+        if (j < g - 1) { col.push_back((int)(r + 1)); val.push_back(-1.0); }
+        if (i < g - 1) { col.push_back((int)(r + g)); val.push_back(-1.0); }
+    }, out);
+}
+
+extern "C" int kry_csr_create_convdiff3d(kry_ctx *c, int64_t m, double gamma, int64_t rb, int64_t re, uint32_t flags,
+                                         kry_csr **out)
+{
+    const int64_t m2 = m * m;
+    return stencil_rows(c, m * m2, rb, re, flags, [=](int64_t r, std::vector<int> &col, std::vector<double> &val) {
+        const int64_t i = r / m2, j = (r / m) % m, k = r % m;
+        if (i > 0) { col.push_back((int)(r - m2)); val.push_back(-1.0 - gamma); }
+        if (j > 0) { col.push_back((int)(r - m)); val.push_back(-1.0 - gamma); }
+        if (k > 0) { col.push_back((int)(r - 1)); val.push_back(-1.0 - gamma); }
+        col.push_back((int)r); val.push_back(6.0 + 3.0 * gamma);
+        if (k < m - 1) { col.push_back((int)(r + 1)); val.push_back(-1.0); }
+        if (j < m - 1) { col.push_back((int)(r + m)); val.push_back(-1.0); }
+        if (i < m - 1) { col.push_back((int)(r + m2)); val.push_back(-1.0); }
+    }, out);
+}
+
+// ------------------------------------------------------------------ multi-GPU: not emulated
+int kry_halo_exchange(kry_csr *, double *) { return KRY_OK; }
+int kry_halo_exchange_dir(kry_csr *, double *, const double *, const double *) { return KRY_OK; }
+int kry_allreduce_sums(kry_ctx *, int) { kry_set_error("emulation: no communicator"); return KRY_ERR_COMM; }
+static int no_comm(const char *who) { kry_set_error("%s: not available in the host emulation", who); return KRY_ERR_COMM; }
+extern "C" int kry_comm_unique_id(void *) { return no_comm("kry_comm_unique_id"); }
+extern "C" int kry_comm_init(kry_ctx *, int, int, const void *) { return no_comm("kry_comm_init"); }
+extern "C" int kry_comm_destroy(kry_ctx *) { return KRY_OK; }
+extern "C" int kry_comm_size(kry_ctx *, int *n, int *r) { *n = 1; *r = 0; return KRY_OK; }
+extern "C" int kry_comm_barrier(kry_ctx *) { return KRY_OK; }
+extern "C" int kry_comm_allgather_host(kry_ctx *, const void *, void *, int64_t) { return no_comm("kry_comm_allgather_host"); }
+extern "C" int kry_comm_allreduce_host(kry_ctx *, double *, int, int) { return no_comm("kry_comm_allreduce_host"); }
+extern "C" int kry_csr_shard_finalize(kry_csr *, int64_t, int64_t) { return no_comm("kry_csr_shard_finalize"); }

@@ -1,0 +1,74 @@
+"""The GPU parity tests, run on the CPU against a host emulation of the device logic.
+
+tests/emu builds the library's OWN csrc/solvers.cu and csrc/ops.cu for the host (g++
+-DKRY_EMULATE): the kernel loops of spmv_row_kernel / vec_pass_kernel / vec_map_kernel, every
+solver functor (bodies, epilogues, scalar recurrences, stopping tests), the launch sequences of
+the three CG plans, the settle logic and the whole C ABI run unchanged, with one host thread
+playing every CUDA thread in turn.  That library is swapped in behind the ctypes layer for the
+duration of this module, and the test functions of tests/test_gpu_parity.py and
+tests/test_gpu_lls.py are collected here a second time with `ctx` bound to an emulated context.
+
+What this does and does not show.  It checks the *logic* of the device code -- operation order
+per element and per row (the file is built with -ffp-contract=off), pointer roles, buffer
+rotations, flags, counters, the Python host layer on top -- against the oracle on every
+machine, GPU or not.  It does not exercise the memory system, warp shuffles, atomics, PTX,
+CUDA graphs, the smem / TMA kernel variants or NCCL; the `-m gpu` suite remains the parity
+proof.  The emulation is test infrastructure: the product never loads it
+(tests/test_host.py::test_product_never_imports_the_oracle covers tests/emu as well).
+"""
+import ctypes as C
+import gc
+
+import pytest
+
+from emu import build_emu
+
+import test_gpu_lls as GL
+import test_gpu_parity as GP
+
+# fixtures the collected tests ask for
+from test_gpu_parity import cg_form          # noqa: F401
+from test_gpu_lls import gold                # noqa: F401
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    path = build_emu.build()
+    if path is None:
+        pytest.skip("host emulation cannot be built here (needs g++ and the CUDA headers)")
+    from pykrylov_b200 import _lib as L
+    from pykrylov_b200 import device
+    emu = C.CDLL(path)
+    for name, (restype, argtypes) in L.PROTOTYPES.items():
+        fn = getattr(emu, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    real_lib, real_default = L.lib, device._default
+    L.lib, device._default = emu, None
+    c = device.Context(0)
+    try:
+        yield c
+    finally:
+        # everything created on the emulated library must be gone before the real one is back
+        c.close()
+        if device._default is not None:
+            device._default.close()
+        gc.collect()
+        device.result_pool.trim()
+        L.lib, device._default = real_lib, real_default
+
+
+def _emulable(name):
+    skip = ("fullsize",                   # 10^7-row operators: minutes on one host thread
+            "gallery_equals_oracle",      # would test emu_context.cpp's generators, not the product
+            "handles_can_be_destroyed",   # creates its own Context on cuda:0
+            "lsqr_rectangular")           # its 1e-3 bar on Anorm/Acond (rounding-chaotic after convergence,
+                                          # see the test) is calibrated to the GPU's reduction tree
+    return name.startswith("test_") and not any(s in name for s in skip)
+
+
+for _mod in (GP, GL):
+    for _name in dir(_mod):
+        if _emulable(_name) and callable(getattr(_mod, _name)):
+            globals()[_name + "__emulated"] = getattr(_mod, _name)
+del _mod, _name

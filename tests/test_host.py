@@ -325,6 +325,13 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(base, f), errors="replace").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "refpykrylov" not in text and "krylov_ref" not in text, f
+                # ... nor the host emulation of tests/emu: the product neither loads libkrylov_emu
+                # nor defines KRY_EMULATE (the guards in csrc/*.cuh only *test* the macro)
+                assert "libkrylov_emu" not in text and "build_emu" not in text, f
+                assert not re.search(r"#\s*include[^\n]*emu_", text), f
+                assert not re.search(r"#\s*define\s+KRY_EMULATE", text), f
+    make = open(os.path.join(pkg, "csrc", "Makefile")).read()
+    assert "KRY_EMULATE" not in make
 
 
 def test_pykrylov_alias_and_pysparse_shim_import():
