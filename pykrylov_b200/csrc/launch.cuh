@@ -126,6 +126,10 @@ int spmv_launch(kry_csr *M, bool trans, Gather g, Epi epi, Fin fin, const int *d
     (void)threads;
     if (kind == KRY_SPMV_ROW)
         emu_launch<ND>(grid, 256, ws, fin, [&] { spmv_row_kernel<ND, Gather, Epi, Fin>(A, g, epi, ws, fin, done); });
+    else if (kind == KRY_SPMV_ROWPF)
+        emu_launch<ND>(grid, 256, ws, fin, [&] { spmv_rowpf_kernel<ND, 1, Gather, Epi, Fin>(A, g, epi, ws, fin, done); });
+    else if (kind == KRY_SPMV_ROWPF2)
+        emu_launch<ND>(grid, 256, ws, fin, [&] { spmv_rowpf_kernel<ND, 2, Gather, Epi, Fin>(A, g, epi, ws, fin, done); });
     else if (kind == KRY_SPMV_ROWB8)
         emu_launch<ND>(grid, 256, ws, fin, [&] { spmv_rowb_kernel<ND, 8, Gather, Epi, Fin>(A, g, epi, ws, fin, done); });
     else

@@ -444,6 +444,7 @@ static int cg_iterate(kry_solver *S)
 // scalar recurrence and stopping tests are the same functors (CgFinAp, CgFinRy) run by thread 0
 // on the same device scalar block, so status / history / done behave exactly as before.  State
 // in HBM is that of the 3-launch plan (x current, p materialised in "p").
+#ifndef KRY_EMULATE      // shared memory + __syncthreads(): not played by the host emulation
 constexpr int KRY_ONE_CTA_THREADS = 1024;
 
 __global__ void __launch_bounds__(KRY_ONE_CTA_THREADS, 1)
@@ -524,6 +525,8 @@ cg_one_cta_kernel(CsrView A, double *gx, double *gr, double *gp, double *gAp, co
     }
 }
 
+#endif  // !KRY_EMULATE
+
 static size_t cg_one_cta_bytes(int64_t n, int64_t nnz)
 {
     return (size_t)nnz * 12 + (size_t)n * 32 + (size_t)(n + 1) * 4 + 16;
@@ -531,6 +534,12 @@ static size_t cg_one_cta_bytes(int64_t n, int64_t nnz)
 
 static int cg_one_cta_iterate(kry_solver *S, int64_t n_iters)
 {
+#ifdef KRY_EMULATE
+    (void)S;
+    (void)n_iters;
+    kry_set_error("cg_one_cta: not available in the host emulation");
+    return KRY_ERR_UNSUPPORTED;
+#else
     kry_ctx *c = S->ctx;
     static bool attr_set = false;
     if (!attr_set) {
@@ -545,6 +554,7 @@ static int cg_one_cta_iterate(kry_solver *S, int64_t n_iters)
     c->launches++;
     KRY_CUDA(cudaGetLastError());
     return KRY_OK;
+#endif
 }
 
 // Fused forms only: bring x and p to the state the 3-launch form would hold (see

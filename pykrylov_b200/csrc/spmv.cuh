@@ -111,7 +111,11 @@ spmv_row_kernel(CsrView A, Gather g, Epi epi, ReduceWs ws, Fin fin, const int *d
 // the next trip finds rowptr in a register and col/val in L2.
 __device__ __forceinline__ void prefetch_l2(const void *p)
 {
+#ifndef KRY_EMULATE
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
 }
 
 template <int ND, int DEPTH, class Gather, class Epi, class Fin>

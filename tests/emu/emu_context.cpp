@@ -103,6 +103,9 @@ extern "C" int kry_ctx_create(int device, kry_ctx **out)
     c->l2_hints = 1;
     c->use_graphs = 0;
     c->cg_fuse = 2;
+#ifdef KRY_OPT_MINRES_FUSE
+    c->minres_fuse = 1;
+#endif
     KRY_TRY(kry_alloc((void **)&c->scalars, KRY_NUM_SLOTS * sizeof(double)));
     KRY_TRY(kry_alloc((void **)&c->sums, 2 * KRY_MAX_DOTS * sizeof(double)));
     KRY_TRY(kry_alloc((void **)&c->counter, 256));
