@@ -37,3 +37,36 @@ def ctx():
 
 def mtx(name):
     return os.path.join(GOLDEN, name + ".mtx")
+
+
+@pytest.fixture(scope="module")
+def emu_ctx():
+    """A Context on the HOST EMULATION of the device logic (tests/emu, test infrastructure only):
+    the library's own solvers.cu / ops.cu built for the host are swapped in behind the ctypes
+    layer for the duration of the requesting module.  Skips where it cannot be built."""
+    import ctypes as C
+    import gc
+    from emu import build_emu
+    path = build_emu.build()
+    if path is None:
+        pytest.skip("host emulation cannot be built here (needs g++ and the CUDA headers)")
+    from pykrylov_b200 import _lib as L
+    from pykrylov_b200 import device
+    emu = C.CDLL(path)
+    for name, (restype, argtypes) in L.PROTOTYPES.items():
+        fn = getattr(emu, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    real_lib, real_default = L.lib, device._default
+    L.lib, device._default = emu, None
+    c = device.Context(0)
+    try:
+        yield c
+    finally:
+        # everything created on the emulated library must be gone before the real one is back
+        c.close()
+        if device._default is not None:
+            device._default.close()
+        gc.collect()
+        device.result_pool.trim()
+        L.lib, device._default = real_lib, real_default

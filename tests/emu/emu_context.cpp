@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <new>
 #include <vector>
 
@@ -135,8 +136,13 @@ extern "C" int kry_ctx_props(kry_ctx *c, int64_t p[6])
     p[0] = c->sm_count; p[1] = p[2] = (int64_t)1 << 34; p[3] = 100; p[4] = c->l2_bytes; p[5] = c->smem_optin;
     return KRY_OK;
 }
-extern "C" int kry_timer_start(kry_ctx *) { return KRY_OK; }
-extern "C" int kry_timer_stop(kry_ctx *, double *ms) { *ms = 0.0; return KRY_OK; }
+static thread_local std::chrono::steady_clock::time_point g_t0;
+extern "C" int kry_timer_start(kry_ctx *) { g_t0 = std::chrono::steady_clock::now(); return KRY_OK; }
+extern "C" int kry_timer_stop(kry_ctx *, double *ms)
+{
+    *ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - g_t0).count();
+    return KRY_OK;
+}
 extern "C" int kry_flush_l2(kry_ctx *) { return KRY_OK; }
 extern "C" int kry_launch_count(kry_ctx *c, int64_t *n) { *n = c->launches; return KRY_OK; }
 extern "C" int kry_prof_enable(kry_ctx *, int) { return KRY_OK; }

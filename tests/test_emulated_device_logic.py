@@ -16,12 +16,7 @@ CUDA graphs, the smem / TMA kernel variants or NCCL; the `-m gpu` suite remains 
 proof.  The emulation is test infrastructure: the product never loads it
 (tests/test_host.py::test_product_never_imports_the_oracle covers tests/emu as well).
 """
-import ctypes as C
-import gc
-
 import pytest
-
-from emu import build_emu
 
 import test_gpu_lls as GL
 import test_gpu_parity as GP
@@ -32,30 +27,9 @@ from test_gpu_lls import gold                # noqa: F401
 
 
 @pytest.fixture(scope="module")
-def ctx():
-    path = build_emu.build()
-    if path is None:
-        pytest.skip("host emulation cannot be built here (needs g++ and the CUDA headers)")
-    from pykrylov_b200 import _lib as L
-    from pykrylov_b200 import device
-    emu = C.CDLL(path)
-    for name, (restype, argtypes) in L.PROTOTYPES.items():
-        fn = getattr(emu, name)
-        fn.restype = restype
-        fn.argtypes = argtypes
-    real_lib, real_default = L.lib, device._default
-    L.lib, device._default = emu, None
-    c = device.Context(0)
-    try:
-        yield c
-    finally:
-        # everything created on the emulated library must be gone before the real one is back
-        c.close()
-        if device._default is not None:
-            device._default.close()
-        gc.collect()
-        device.result_pool.trim()
-        L.lib, device._default = real_lib, real_default
+def ctx(emu_ctx):
+    """The collected tests ask for `ctx`: here it is the emulated context (conftest.emu_ctx)."""
+    return emu_ctx
 
 
 def _emulable(name):
