@@ -158,10 +158,12 @@ ReduceWs kry_ws(kry_ctx *ctx);
 // KRY_EMULATE: tests/emu compiles the device *logic* of this library (kernel loops, solver
 // functors, launch sequences) for the host with g++ to check it against the oracle without a
 // GPU.  It is test infrastructure: nothing in the product defines the macro, and the blocks it
-// switches off below (warp shuffles, PTX) have their stand-ins in tests/emu/emu_device.h.
+// switches off below (PTX) have their stand-ins in tests/emu/emu_device.h.
 #if defined(__CUDACC__) || defined(KRY_EMULATE)
 
-#ifndef KRY_EMULATE
+#ifdef KRY_EMULATE      // the genuine two-stage reduction below is compiled as ..._real: the emulation runs
+#define block_reduce_finalize block_reduce_finalize_real   // it on SIMT fibers, or a sequential stand-in
+#endif                  // in its place for speed (tests/emu/emu_device.h picks)
 __device__ __forceinline__ double warp_sum(double v)
 {
     // xor butterfly: every lane ends with the same, order-fixed sum
@@ -271,7 +273,9 @@ __device__ __forceinline__ void block_reduce_finalize(double (&acc)[ND], const R
         if (!ws.defer) fin(tot);
     }
 }
-#endif  // !KRY_EMULATE
+#ifdef KRY_EMULATE
+#undef block_reduce_finalize
+#endif
 
 // Bodies that also provide pair(i2[, acc]) -- elements 2*i2 and 2*i2+1 through one
 // 16-byte access per vector -- are run in that form by the vector kernels.

@@ -19,6 +19,138 @@ thread_local EmuDim threadIdx, blockIdx, blockDim, gridDim;
 thread_local double emu_tot[EMU_MAX_DOTS];
 thread_local int    emu_reduced;
 
+// ------------------------------------------------------------------ SIMT mode: one fiber per CUDA thread
+// Blocks run one after the other; inside a block the threads are ucontext fibers resumed
+// round-robin.  __syncthreads() and the warp-level barrier behind the shuffles count arrivals
+// (threads that have returned no longer count, as on the hardware) and spin by yielding.
+#include <ucontext.h>
+
+int emu_fibers_on = 0;
+unsigned char emu_shfl_slots[32][32][8];
+
+namespace {
+constexpr size_t kFiberStack = 128 * 1024;
+struct Fiber {
+    ucontext_t uc;
+    int        tid;
+    bool       done;
+};
+struct Block {
+    int      live, arrived;
+    unsigned gen;
+    int      wlive[32], warrived[32];
+    unsigned wgen[32];
+} g_blk;
+std::vector<Fiber> g_fibers;
+std::vector<char>  g_stacks;
+ucontext_t         g_sched;
+Fiber             *g_cur = nullptr;
+const void        *g_closure = nullptr;
+void (*g_invoke)(const void *) = nullptr;
+
+void release_if_complete()
+{
+    if (g_blk.live > 0 && g_blk.arrived == g_blk.live) {
+        g_blk.arrived = 0;
+        g_blk.gen++;
+    }
+}
+void warp_release_if_complete(int w)
+{
+    if (g_blk.wlive[w] > 0 && g_blk.warrived[w] == g_blk.wlive[w]) {
+        g_blk.warrived[w] = 0;
+        g_blk.wgen[w]++;
+    }
+}
+void fiber_main()
+{
+    g_invoke(g_closure);
+    Fiber *me = g_cur;
+    me->done = true;
+    g_blk.live--;
+    release_if_complete();
+    const int w = me->tid >> 5;
+    g_blk.wlive[w]--;
+    warp_release_if_complete(w);
+    // returning resumes uc_link = the scheduler
+}
+}  // namespace
+
+void emu_yield()
+{
+    if (!g_cur) return;                         // sequential mode: nothing to switch to
+    swapcontext(&g_cur->uc, &g_sched);
+}
+
+void emu_block_barrier()
+{
+    if (!g_cur) {
+        fprintf(stderr, "emulation: __syncthreads() reached outside the SIMT mode (kry_emu_set_fibers)\n");
+        abort();
+    }
+    const unsigned gen = g_blk.gen;
+    g_blk.arrived++;
+    release_if_complete();
+    while (g_blk.gen == gen) emu_yield();
+}
+
+void emu_warp_barrier(int w)
+{
+    if (!g_cur) {
+        fprintf(stderr, "emulation: warp-level synchronisation reached outside the SIMT mode\n");
+        abort();
+    }
+    const unsigned gen = g_blk.wgen[w];
+    g_blk.warrived[w]++;
+    warp_release_if_complete(w);
+    while (g_blk.wgen[w] == gen) emu_yield();
+}
+
+void emu_launch_fibers(int grid, int block, const void *closure, void (*invoke)(const void *))
+{
+    if ((int)g_fibers.size() < block) g_fibers.resize((size_t)block);
+    if (g_stacks.size() < (size_t)block * kFiberStack) g_stacks.resize((size_t)block * kFiberStack);
+    g_closure = closure;
+    g_invoke = invoke;
+    gridDim = EmuDim{(unsigned)grid, 1, 1};
+    blockDim = EmuDim{(unsigned)block, 1, 1};
+    for (int b = 0; b < grid; ++b) {
+        blockIdx = EmuDim{(unsigned)b, 0, 0};
+        memset(&g_blk, 0, sizeof(g_blk));
+        g_blk.live = block;
+        for (int t = 0; t < block; ++t) g_blk.wlive[t >> 5]++;
+        for (int t = 0; t < block; ++t) {
+            Fiber &f = g_fibers[(size_t)t];
+            f.tid = t;
+            f.done = false;
+            getcontext(&f.uc);
+            f.uc.uc_stack.ss_sp = g_stacks.data() + (size_t)t * kFiberStack;
+            f.uc.uc_stack.ss_size = kFiberStack;
+            f.uc.uc_link = &g_sched;
+            makecontext(&f.uc, fiber_main, 0);
+        }
+        int remaining = block;
+        while (remaining > 0) {
+            for (int t = 0; t < block; ++t) {
+                Fiber &f = g_fibers[(size_t)t];
+                if (f.done) continue;
+                g_cur = &f;
+                threadIdx = EmuDim{(unsigned)t, 0, 0};
+                swapcontext(&g_sched, &f.uc);
+                if (f.done) remaining--;
+            }
+        }
+        g_cur = nullptr;
+    }
+}
+
+// emulation-only switch (not part of the product ABI): 1 = SIMT fibers + the genuine reduction
+extern "C" int kry_emu_set_fibers(int on)
+{
+    emu_fibers_on = on ? 1 : 0;
+    return KRY_OK;
+}
+
 // ------------------------------------------------------------------ CUDA runtime, host edition
 extern "C" {
 cudaError_t cudaMalloc(void **p, size_t n) { *p = calloc(1, n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
@@ -80,7 +212,10 @@ ReduceWs kry_ws(kry_ctx *c)
 {
     ReduceWs ws;
     memset(&ws, 0, sizeof(ws));
+    ws.partials = c->partials;
     ws.sums = c->sums;
+    ws.counter = c->counter;
+    ws.stride = c->partial_stride;
     ws.nranks = 1;
     return ws;
 }
@@ -111,6 +246,8 @@ extern "C" int kry_ctx_create(int device, kry_ctx **out)
     KRY_TRY(kry_alloc((void **)&c->sums, 2 * KRY_MAX_DOTS * sizeof(double)));
     KRY_TRY(kry_alloc((void **)&c->counter, 256));
     KRY_TRY(kry_alloc((void **)&c->never_done, 256));
+    c->partial_stride = 1024;
+    KRY_TRY(kry_alloc((void **)&c->partials, (size_t)KRY_MAX_DOTS * c->partial_stride * sizeof(double)));
     *out = c;
     return KRY_OK;
 }
@@ -122,6 +259,8 @@ extern "C" int kry_ctx_destroy(kry_ctx *c)
     free(c->sums);
     free(c->counter);
     free(c->never_done);
+    free(c->partials);
+    c->partials = nullptr;
     c->scalars = c->sums = nullptr;
     c->counter = nullptr;
     c->never_done = nullptr;

@@ -43,24 +43,77 @@ static inline double2 ld2_hint(const double *a, int i2, uint64_t) { return reint
 static inline void st2_hint(double *a, int i2, double2 v, uint64_t) { reinterpret_cast<double2 *>(a)[i2] = v; }
 static inline void st_hint(double *a, double v, uint64_t) { *a = v; }
 
-// ---- reduction: every played thread adds its accumulators to the launch totals, in thread
-// order; the launcher hands the totals to the finalize functor after the last thread
+// ---- block-level CUDA, played by fibers (emu_context.cpp): when the SIMT mode is on
+// (kry_emu_set_fibers), every thread of a block is a fiber, __syncthreads() and the warp shuffles
+// are real barriers between them, __shared__ variables are shared by the block, and the
+// library's genuine block_reduce_finalize (warp butterflies, per-warp partials, last-CTA ticket,
+// ordered final sum) runs as written.  The default mode plays the threads one after the other
+// -- only valid for kernels without block-level synchronisation -- and replaces the reduction
+// by a sequential stand-in; it is ~100x faster and is what most emulated tests use.
+#undef __shared__
+#define __shared__ static
+
+extern int emu_fibers_on;
+void emu_yield();
+void emu_block_barrier();
+void emu_warp_barrier(int warp);
+extern unsigned char emu_shfl_slots[32][32][8];
+
+static inline void __syncthreads() { emu_block_barrier(); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { emu_warp_barrier((int)(threadIdx.x >> 5)); }
+static inline void __threadfence() {}
+static inline void __threadfence_system() {}
+static inline void __nanosleep(unsigned) { emu_yield(); }
+static inline unsigned atomicAdd(unsigned *p, unsigned v) { const unsigned o = *p; *p = o + v; return o; }
+static inline int atomicMax(int *p, int v) { const int o = *p; if (v > o) *p = v; return o; }
+
+template <class T>
+static inline T __shfl_xor_sync(unsigned, T v, int lane_mask)
+{
+    static_assert(sizeof(T) <= 8, "shuffle of up to 8 bytes");
+    const int lane = (int)(threadIdx.x & 31), warp = (int)(threadIdx.x >> 5);
+    memcpy(emu_shfl_slots[warp][lane], &v, sizeof(T));
+    emu_warp_barrier(warp);
+    T r;
+    memcpy(&r, emu_shfl_slots[warp][lane ^ lane_mask], sizeof(T));
+    emu_warp_barrier(warp);
+    return r;
+}
+
+// ---- reduction: the genuine code (common.cuh, compiled as block_reduce_finalize_real) in SIMT
+// mode; otherwise every played thread adds its accumulators to the launch totals, in thread
+// order, and the launcher hands the totals to the finalize functor after the last thread
 constexpr int EMU_MAX_DOTS = 4;
 extern thread_local double emu_tot[EMU_MAX_DOTS];
 extern thread_local int    emu_reduced;
 
 struct ReduceWs;
 template <int ND, class Fin>
-static inline void block_reduce_finalize(double (&acc)[ND], const ReduceWs &, Fin &)
+void block_reduce_finalize_real(double (&acc)[ND], const ReduceWs &ws, Fin &fin);
+
+template <int ND, class Fin>
+static inline void block_reduce_finalize(double (&acc)[ND], const ReduceWs &ws, Fin &fin)
 {
+    if (emu_fibers_on) {
+        block_reduce_finalize_real<ND>(acc, ws, fin);
+        return;
+    }
     for (int d = 0; d < ND; ++d) emu_tot[d] = emu_tot[d] + acc[d];
     emu_reduced = 1;
 }
 
-// ---- launcher: play grid x block threads one after the other
+// ---- launchers
+void emu_launch_fibers(int grid, int block, const void *kernel_closure, void (*invoke)(const void *));
+
 template <int ND, class Ws, class Fin, class Kernel>
 static inline void emu_launch(int grid, int block, const Ws &ws, Fin fin, Kernel kernel)
 {
+    if (emu_fibers_on && ND > 0) {
+        // SIMT mode: blocks one after the other, the threads of a block as fibers; the kernel's own
+        // last-CTA code finalises
+        emu_launch_fibers(grid, block, &kernel, [](const void *k) { (*static_cast<const Kernel *>(k))(); });
+        return;
+    }
     for (int d = 0; d < EMU_MAX_DOTS; ++d) emu_tot[d] = 0.0;
     emu_reduced = 0;
     gridDim = EmuDim{(unsigned)grid, 1, 1};
