@@ -444,14 +444,17 @@ static int cg_iterate(kry_solver *S)
 // scalar recurrence and stopping tests are the same functors (CgFinAp, CgFinRy) run by thread 0
 // on the same device scalar block, so status / history / done behave exactly as before.  State
 // in HBM is that of the 3-launch plan (x current, p materialised in "p").
-#ifndef KRY_EMULATE      // shared memory + __syncthreads(): not played by the host emulation
 constexpr int KRY_ONE_CTA_THREADS = 1024;
 
 __global__ void __launch_bounds__(KRY_ONE_CTA_THREADS, 1)
 cg_one_cta_kernel(CsrView A, double *gx, double *gr, double *gp, double *gAp, const double *pd, int pmode,
                   DevScalars *s, double *hist, long long n_iters)
 {
+#ifdef KRY_EMULATE
+    unsigned char *smem_raw = emu_dynamic_smem;          // tests/emu: the launcher sized it
+#else
     extern __shared__ __align__(16) unsigned char smem_raw[];
+#endif
     __shared__ double s_warp[1][32];
     __shared__ double sh_scalar;
     __shared__ int    sh_done;
@@ -525,8 +528,6 @@ cg_one_cta_kernel(CsrView A, double *gx, double *gr, double *gp, double *gAp, co
     }
 }
 
-#endif  // !KRY_EMULATE
-
 static size_t cg_one_cta_bytes(int64_t n, int64_t nnz)
 {
     return (size_t)nnz * 12 + (size_t)n * 32 + (size_t)(n + 1) * 4 + 16;
@@ -534,13 +535,18 @@ static size_t cg_one_cta_bytes(int64_t n, int64_t nnz)
 
 static int cg_one_cta_iterate(kry_solver *S, int64_t n_iters)
 {
-#ifdef KRY_EMULATE
-    (void)S;
-    (void)n_iters;
-    kry_set_error("cg_one_cta: not available in the host emulation");
-    return KRY_ERR_UNSUPPORTED;
-#else
     kry_ctx *c = S->ctx;
+#ifdef KRY_EMULATE
+    // tests/emu, SIMT mode: one block of fibers plays the CTA
+    KRY_REQUIRE(emu_fibers_on, KRY_ERR_UNSUPPORTED, "cg_one_cta needs the SIMT mode of the emulation");
+    CsrView Ae = csr_view(S->A->A);
+    double *ex = solver_vec(S, "x"), *er = solver_vec(S, "r"), *ep = solver_vec(S, "p"), *eAp = solver_vec(S, "Ap");
+    emu_set_dynamic_smem(S->one_cta_smem);
+    auto body = [&] { cg_one_cta_kernel(Ae, ex, er, ep, eAp, S->dinv, S->precon_mode, S->ds, S->hist, (long long)n_iters); };
+    emu_launch_fibers(1, KRY_ONE_CTA_THREADS, &body, [](const void *k) { (*static_cast<const decltype(body) *>(k))(); });
+    c->launches++;
+    return KRY_OK;
+#else
     static bool attr_set = false;
     if (!attr_set) {
         KRY_CUDA(cudaFuncSetAttribute(cg_one_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

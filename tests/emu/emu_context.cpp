@@ -144,6 +144,14 @@ void emu_launch_fibers(int grid, int block, const void *closure, void (*invoke)(
     }
 }
 
+unsigned char *emu_dynamic_smem = nullptr;
+void emu_set_dynamic_smem(size_t bytes)
+{
+    static std::vector<double> buf;                   // 8-byte aligned
+    if (buf.size() * 8 < bytes + 16) buf.resize(bytes / 8 + 4);
+    emu_dynamic_smem = reinterpret_cast<unsigned char *>(buf.data());
+}
+
 // emulation-only switch (not part of the product ABI): 1 = SIMT fibers + the genuine reduction
 extern "C" int kry_emu_set_fibers(int on)
 {
@@ -302,7 +310,7 @@ extern "C" int kry_ctx_set_option(kry_ctx *c, int option, int value)
         case KRY_OPT_MINRES_FUSE: c->minres_fuse = value ? 1 : 0; return KRY_OK;
 #endif
 #ifdef KRY_OPT_CG_ONE_CTA
-        case KRY_OPT_CG_ONE_CTA: return KRY_OK;               // needs shared memory: not emulated
+        case KRY_OPT_CG_ONE_CTA: c->cg_one_cta = (value && emu_fibers_on) ? 1 : 0; return KRY_OK;   // SIMT mode only
 #endif
         default: kry_set_error("kry_ctx_set_option (emulation): option %d", option); return KRY_ERR_INVALID;
     }
@@ -320,7 +328,7 @@ extern "C" int kry_ctx_get_option(kry_ctx *c, int option, int *value)
         case KRY_OPT_MINRES_FUSE: *value = c->minres_fuse; return KRY_OK;
 #endif
 #ifdef KRY_OPT_CG_ONE_CTA
-        case KRY_OPT_CG_ONE_CTA: *value = 0; return KRY_OK;
+        case KRY_OPT_CG_ONE_CTA: *value = c->cg_one_cta; return KRY_OK;
 #endif
         default: kry_set_error("kry_ctx_get_option (emulation): option %d", option); return KRY_ERR_INVALID;
     }

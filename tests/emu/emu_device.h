@@ -102,6 +102,10 @@ static inline void block_reduce_finalize(double (&acc)[ND], const ReduceWs &ws, 
     emu_reduced = 1;
 }
 
+// ---- dynamic shared memory of a launch (extern __shared__ in CUDA)
+extern unsigned char *emu_dynamic_smem;
+void emu_set_dynamic_smem(size_t bytes);
+
 // ---- launchers
 void emu_launch_fibers(int grid, int block, const void *kernel_closure, void (*invoke)(const void *));
 
