@@ -7,7 +7,9 @@
 // local SpMV over columns remapped to [local | halo].  Per fused inner product:
 // ONE ncclAllReduce of <= 3 doubles, then a one-thread kernel runs the scalar
 // recurrence.  Nothing else crosses NVLink.
+#ifndef KRY_EMULATE
 #include <cub/cub.cuh>
+#endif
 #include <dlfcn.h>
 #include <nccl.h>
 #include <string.h>
@@ -31,9 +33,20 @@ struct NcclApi {
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
 } g_nccl;
 
+#ifdef KRY_EMULATE
+extern "C" void emu_nccl_table(void **get_unique_id, void **comm_init_rank, void **comm_destroy, void **all_reduce,
+                               void **all_gather, void **get_error_string);
+#endif
+
 int nccl_load()
 {
     if (g_nccl.lib) return KRY_OK;
+#ifdef KRY_EMULATE      // tests/emu: ranks are threads of one process, the collectives are host barriers
+    emu_nccl_table((void **)&g_nccl.GetUniqueId, (void **)&g_nccl.CommInitRank, (void **)&g_nccl.CommDestroy,
+                   (void **)&g_nccl.AllReduce, (void **)&g_nccl.AllGather, (void **)&g_nccl.GetErrorString);
+    g_nccl.lib = (void *)&g_nccl;
+    return KRY_OK;
+#endif
     const char *names[] = {"libnccl.so.2", "libnccl.so"};
     void *h = nullptr;
     for (const char *n : names) {
@@ -295,12 +308,21 @@ int kry_halo_exchange_dir(kry_csr *M, double *x_dev, const double *r_dev, const 
     if (!h.active) return KRY_OK;
     kry_ctx *c = M->ctx;
     if (h.max_send == 0) return KRY_OK;
+#ifdef KRY_EMULATE
+    if (r_dev)
+        emu_launch<0>((h.max_send + 255) / 256, 256, ReduceWs(), NoFin(), [&] {
+            halo_pack_dir_kernel(x_dev, r_dev, beta_dev, h.send_idx, h.n_send, h.max_send, h.send_buf); });
+    else
+        emu_launch<0>((h.max_send + 255) / 256, 256, ReduceWs(), NoFin(), [&] {
+            halo_pack_kernel(x_dev, h.send_idx, h.n_send, h.max_send, h.send_buf); });
+#else
     if (r_dev)
         halo_pack_dir_kernel<<<(h.max_send + 255) / 256, 256, 0, c->stream>>>(
             x_dev, r_dev, beta_dev, h.send_idx, h.n_send, h.max_send, h.send_buf);
     else
         halo_pack_kernel<<<(h.max_send + 255) / 256, 256, 0, c->stream>>>(x_dev, h.send_idx, h.n_send,
                                                                           h.max_send, h.send_buf);
+#endif
     c->launches++;
     KRY_CUDA(cudaGetLastError());
     double *tail = x_dev + M->A.nrows;
@@ -366,6 +388,13 @@ extern "C" int kry_csr_shard_finalize(kry_csr *M, int64_t n_global, int64_t row_
     int *d_sel = nullptr, *d_sorted = nullptr, *d_count = nullptr;
     void *tmp = nullptr;
     std::vector<int> need;
+#ifdef KRY_EMULATE      // tests/emu: the same set with the host's sort / unique
+    (void)d_sel; (void)d_sorted; (void)d_count; (void)tmp;
+    for (int k = 0; k < nnz; ++k)
+        if (M->A.col[k] < lo || M->A.col[k] >= hi) need.push_back(M->A.col[k]);
+    std::sort(need.begin(), need.end());
+    need.erase(std::unique(need.begin(), need.end()), need.end());
+#else
     {
         KRY_TRY(kry_alloc((void **)&d_sel, (size_t)(nnz + 1) * sizeof(int)));
         KRY_TRY(kry_alloc((void **)&d_sorted, (size_t)(nnz + 1) * sizeof(int)));
@@ -396,6 +425,7 @@ extern "C" int kry_csr_shard_finalize(kry_csr *M, int64_t n_global, int64_t row_
         cudaFree(d_count);
         cudaFree(d_sel);
     }
+#endif
 
     // 2. everyone learns every shard's row range and need list
     std::vector<int64_t> ranges((size_t)2 * P);
@@ -462,8 +492,13 @@ extern "C" int kry_csr_shard_finalize(kry_csr *M, int64_t n_global, int64_t row_
         KRY_CUDA(cudaMemcpyAsync(d_map, halo_map.data(), need.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     }
     if (nnz > 0) {
+#ifdef KRY_EMULATE
+        emu_launch<0>(c->sm_count * 8, 256, ReduceWs(), NoFin(), [&] {
+            remap_cols_kernel(M->A.col, nnz, lo, hi, d_need, d_map, (int)need.size()); });
+#else
         remap_cols_kernel<<<c->sm_count * 8, 256, 0, st>>>(M->A.col, nnz, lo, hi, d_need, d_map,
                                                            (int)need.size());
+#endif
         c->launches++;
     }
     KRY_CUDA(cudaStreamSynchronize(st));

@@ -70,9 +70,10 @@ extern "C" int kry_ctx_create(int device, kry_ctx **out)
     c->use_graphs = 1;
     c->cg_one_cta = 1;
     c->minres_fuse = 1;
-    c->cg_fuse_shards = 1;     // candidate: verified on 2 GPUs in round 1 (+2.7 %), to be checked at 4 and 8
     c->cg_fuse = 2;        // measured on B200, 10^7-row 5-pt Laplacian: 0.222 ms/iteration against 0.233
                            // (form 1) and 0.249 (form 0) -- profiles/r1b_ab_cgfuse*.json, r1_final_bench_n1.json
+    c->cg_fuse_shards = 1; // row shards use the same plan: 2 x B200, 10^8 rows: 825.7 vs 803.8 it/s with the same
+                           // residual bits (profiles/r1e_*); 2-8 emulated ranks: tests/test_emulated_multi_rank.py
     KRY_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     KRY_CUDA(cudaEventCreate(&c->ev0));
     KRY_CUDA(cudaEventCreate(&c->ev1));

@@ -13,7 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "pykrylov_b200", "csrc")
 OUT = os.path.join(HERE, "_build", "libkrylov_emu.so")
-SOURCES = [os.path.join(CSRC, "solvers.cu"), os.path.join(CSRC, "ops.cu"), os.path.join(HERE, "emu_context.cpp")]
+SOURCES = [os.path.join(CSRC, "solvers.cu"), os.path.join(CSRC, "ops.cu"), os.path.join(CSRC, "comm.cu"),
+           os.path.join(HERE, "emu_context.cpp")]
 DEPS = SOURCES + [os.path.join(CSRC, h) for h in ("common.cuh", "spmv.cuh", "launch.cuh", "solver.cuh")] + \
     [os.path.join(HERE, "emu_device.h"), os.path.join(ROOT, "include", "krylov_b200.h")]
 
@@ -38,7 +39,7 @@ def build(force=False):
            # un-fused, individually rounded multiplies and adds: the contract of __dmul_rn / __dadd_rn
            "-ffp-contract=off", "-fno-fast-math",
            "-DKRY_EMULATE", "-Wno-unknown-pragmas", "-include", os.path.join(HERE, "emu_device.h"),
-           "-I" + inc, "-I" + CSRC, "-x", "c++"] + SOURCES + ["-o", OUT]
+           "-I" + inc, "-I" + CSRC, "-x", "c++"] + SOURCES + ["-o", OUT, "-lpthread"]
     try:
         subprocess.check_call(cmd)
     except (OSError, subprocess.CalledProcessError) as exc:

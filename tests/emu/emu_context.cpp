@@ -23,10 +23,11 @@ thread_local int    emu_reduced;
 // Blocks run one after the other; inside a block the threads are ucontext fibers resumed
 // round-robin.  __syncthreads() and the warp-level barrier behind the shuffles count arrivals
 // (threads that have returned no longer count, as on the hardware) and spin by yielding.
+#include <sched.h>
 #include <ucontext.h>
 
 int emu_fibers_on = 0;
-unsigned char emu_shfl_slots[32][32][8];
+thread_local unsigned char emu_shfl_slots[32][32][8];
 
 namespace {
 constexpr size_t kFiberStack = 128 * 1024;
@@ -40,13 +41,15 @@ struct Block {
     unsigned gen;
     int      wlive[32], warrived[32];
     unsigned wgen[32];
-} g_blk;
-std::vector<Fiber> g_fibers;
-std::vector<char>  g_stacks;
-ucontext_t         g_sched;
-Fiber             *g_cur = nullptr;
-const void        *g_closure = nullptr;
-void (*g_invoke)(const void *) = nullptr;
+};
+// one set per host thread: the ranks of an emulated multi-GPU run are threads of this process
+thread_local Block              g_blk;
+thread_local std::vector<Fiber> g_fibers;
+thread_local std::vector<char>  g_stacks;
+thread_local ucontext_t         g_sched;
+thread_local Fiber             *g_cur = nullptr;
+thread_local const void        *g_closure = nullptr;
+thread_local void (*g_invoke)(const void *) = nullptr;
 
 void release_if_complete()
 {
@@ -224,7 +227,11 @@ ReduceWs kry_ws(kry_ctx *c)
     ws.sums = c->sums;
     ws.counter = c->counter;
     ws.stride = c->partial_stride;
-    ws.nranks = 1;
+    ws.nranks = c->nranks;
+    ws.rank = c->rank;
+    ws.inbox = c->p2p_inbox;
+    ws.peers = c->p2p_peers_dev;
+    ws.seq = c->p2p_seq;
     return ws;
 }
 
@@ -233,6 +240,8 @@ void kry_ctx_release(kry_ctx *c)
 {
     if (--c->refs <= 0 && c->closed) delete c;
 }
+
+extern "C" int kry_comm_destroy(kry_ctx *ctx);
 
 // ------------------------------------------------------------------ context
 extern "C" int kry_ctx_create(int device, kry_ctx **out)
@@ -247,6 +256,7 @@ extern "C" int kry_ctx_create(int device, kry_ctx **out)
     c->l2_hints = 1;
     c->use_graphs = 0;
     c->cg_fuse = 2;
+    c->cg_fuse_shards = 1;
 #ifdef KRY_OPT_MINRES_FUSE
     c->minres_fuse = 1;
 #endif
@@ -263,6 +273,7 @@ extern "C" int kry_ctx_create(int device, kry_ctx **out)
 extern "C" int kry_ctx_destroy(kry_ctx *c)
 {
     if (!c || c->closed) return KRY_OK;
+    if (c->nccl) kry_comm_destroy(c);
     free(c->scalars);
     free(c->sums);
     free(c->counter);
@@ -306,6 +317,11 @@ extern "C" int kry_ctx_set_option(kry_ctx *c, int option, int value)
             KRY_REQUIRE(value >= 0 && value <= 2, KRY_ERR_INVALID, "CG_FUSE=%d not in 0..2", value);
             c->cg_fuse = value;
             return KRY_OK;
+        case KRY_OPT_CG_FUSE_SHARDS: c->cg_fuse_shards = value ? 1 : 0; return KRY_OK;
+        case KRY_OPT_P2P:
+            KRY_REQUIRE(!value || c->p2p_inbox, KRY_ERR_STATE, "peer-memory all-reduce was not set up");
+            c->p2p_on = value ? 1 : 0;
+            return KRY_OK;
 #ifdef KRY_OPT_MINRES_FUSE
         case KRY_OPT_MINRES_FUSE: c->minres_fuse = value ? 1 : 0; return KRY_OK;
 #endif
@@ -321,9 +337,9 @@ extern "C" int kry_ctx_get_option(kry_ctx *c, int option, int *value)
     switch (option) {
         case KRY_OPT_L2_HINTS: *value = c->l2_hints; return KRY_OK;
         case KRY_OPT_GRAPHS: *value = 0; return KRY_OK;
-        case KRY_OPT_P2P: *value = 0; return KRY_OK;
+        case KRY_OPT_P2P: *value = c->p2p_on; return KRY_OK;
         case KRY_OPT_CG_FUSE: *value = c->cg_fuse; return KRY_OK;
-        case KRY_OPT_CG_FUSE_SHARDS: *value = 0; return KRY_OK;
+        case KRY_OPT_CG_FUSE_SHARDS: *value = c->cg_fuse_shards; return KRY_OK;
 #ifdef KRY_OPT_MINRES_FUSE
         case KRY_OPT_MINRES_FUSE: *value = c->minres_fuse; return KRY_OK;
 #endif
@@ -595,16 +611,165 @@ extern "C" int kry_csr_create_convdiff3d(kry_ctx *c, int64_t m, double gamma, in
     }, out);
 }
 
-// ------------------------------------------------------------------ multi-GPU: not emulated
-int kry_halo_exchange(kry_csr *, double *) { return KRY_OK; }
-int kry_halo_exchange_dir(kry_csr *, double *, const double *, const double *) { return KRY_OK; }
-int kry_allreduce_sums(kry_ctx *, int) { kry_set_error("emulation: no communicator"); return KRY_ERR_COMM; }
-static int no_comm(const char *who) { kry_set_error("%s: not available in the host emulation", who); return KRY_ERR_COMM; }
-extern "C" int kry_comm_unique_id(void *) { return no_comm("kry_comm_unique_id"); }
-extern "C" int kry_comm_init(kry_ctx *, int, int, const void *) { return no_comm("kry_comm_init"); }
-extern "C" int kry_comm_destroy(kry_ctx *) { return KRY_OK; }
-extern "C" int kry_comm_size(kry_ctx *, int *n, int *r) { *n = 1; *r = 0; return KRY_OK; }
-extern "C" int kry_comm_barrier(kry_ctx *) { return KRY_OK; }
-extern "C" int kry_comm_allgather_host(kry_ctx *, const void *, void *, int64_t) { return no_comm("kry_comm_allgather_host"); }
-extern "C" int kry_comm_allreduce_host(kry_ctx *, double *, int, int) { return no_comm("kry_comm_allreduce_host"); }
-extern "C" int kry_csr_shard_finalize(kry_csr *, int64_t, int64_t) { return no_comm("kry_csr_shard_finalize"); }
+// ------------------------------------------------------------------ multi-GPU: ranks are threads
+// csrc/comm.cu is compiled as it is (shard finalisation, halo exchange, peer-memory inboxes); what
+// it gets from NCCL and CUDA IPC comes from here.  Every rank of an emulated run is a host thread
+// with its own context; the collectives are barriers between those threads, "peer memory" is
+// simply the other thread's allocation.
+#include <nccl.h>
+
+#include <condition_variable>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+
+namespace {
+struct EmuComm {
+    int                       nranks = 0, joined = 0, arrived = 0;
+    unsigned                  gen = 0;
+    std::mutex                m;
+    std::condition_variable   cv;
+    std::vector<const void *> send;
+    void barrier()
+    {
+        std::unique_lock<std::mutex> lk(m);
+        const unsigned g = gen;
+        if (++arrived == nranks) {
+            arrived = 0;
+            gen++;
+            cv.notify_all();
+        } else {
+            cv.wait(lk, [&] { return gen != g; });
+        }
+    }
+};
+struct EmuRank {
+    std::shared_ptr<EmuComm> comm;
+    int                      rank;
+};
+std::mutex                                      g_comms_m;
+std::map<std::string, std::shared_ptr<EmuComm>> g_comms;
+unsigned long long                              g_next_id = 1;
+
+size_t dtype_size(ncclDataType_t t) { return t == ncclDouble ? 8 : 1; }
+
+ncclResult_t emu_get_unique_id(ncclUniqueId *id)
+{
+    std::lock_guard<std::mutex> lk(g_comms_m);
+    memset(id, 0, sizeof(*id));
+    snprintf(id->internal, sizeof(id->internal), "emu-comm-%llu", g_next_id++);
+    return ncclSuccess;
+}
+
+ncclResult_t emu_comm_init_rank(ncclComm_t *out, int nranks, ncclUniqueId id, int rank)
+{
+    std::shared_ptr<EmuComm> c;
+    {
+        std::lock_guard<std::mutex> lk(g_comms_m);
+        auto &slot = g_comms[std::string(id.internal, sizeof(id.internal))];
+        if (!slot) {
+            slot = std::make_shared<EmuComm>();
+            slot->nranks = nranks;
+            slot->send.assign((size_t)nranks, nullptr);
+        }
+        c = slot;
+    }
+    if (c->nranks != nranks) return ncclInvalidArgument;
+    *out = reinterpret_cast<ncclComm_t>(new EmuRank{c, rank});
+    c->barrier();                                   // every rank has joined
+    return ncclSuccess;
+}
+
+ncclResult_t emu_comm_destroy(ncclComm_t comm)
+{
+    delete reinterpret_cast<EmuRank *>(comm);
+    return ncclSuccess;
+}
+
+ncclResult_t emu_all_gather(const void *send, void *recv, size_t count, ncclDataType_t t, ncclComm_t comm, cudaStream_t)
+{
+    EmuRank *r = reinterpret_cast<EmuRank *>(comm);
+    EmuComm &c = *r->comm;
+    const size_t bytes = count * dtype_size(t);
+    c.send[(size_t)r->rank] = send;
+    c.barrier();
+    for (int q = 0; q < c.nranks; ++q) memcpy((char *)recv + (size_t)q * bytes, c.send[(size_t)q], bytes);
+    c.barrier();
+    return ncclSuccess;
+}
+
+ncclResult_t emu_all_reduce(const void *send, void *recv, size_t count, ncclDataType_t t, ncclRedOp_t op, ncclComm_t comm,
+                            cudaStream_t)
+{
+    if (t != ncclDouble) return ncclInvalidArgument;
+    EmuRank *r = reinterpret_cast<EmuRank *>(comm);
+    EmuComm &c = *r->comm;
+    c.send[(size_t)r->rank] = send;
+    c.barrier();
+    std::vector<double> acc(count);
+    for (size_t i = 0; i < count; ++i) {            // rank order on every rank: identical bits everywhere
+        double a = ((const double *)c.send[0])[i];
+        for (int q = 1; q < c.nranks; ++q) {
+            const double v = ((const double *)c.send[(size_t)q])[i];
+            a = (op == ncclMax) ? (v > a ? v : a) : a + v;
+        }
+        acc[i] = a;
+    }
+    c.barrier();                                    // everyone has read the inputs (recv may alias send)
+    memcpy(recv, acc.data(), count * sizeof(double));
+    return ncclSuccess;
+}
+
+const char *emu_get_error_string(ncclResult_t) { return "emulated NCCL error"; }
+}  // namespace
+
+extern "C" void emu_nccl_table(void **get_unique_id, void **comm_init_rank, void **comm_destroy, void **all_reduce,
+                               void **all_gather, void **get_error_string)
+{
+    *get_unique_id = (void *)emu_get_unique_id;
+    *comm_init_rank = (void *)emu_comm_init_rank;
+    *comm_destroy = (void *)emu_comm_destroy;
+    *all_reduce = (void *)emu_all_reduce;
+    *all_gather = (void *)emu_all_gather;
+    *get_error_string = (void *)emu_get_error_string;
+}
+
+// CUDA IPC inside one process: the handle carries the pointer
+extern "C" {
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p)
+{
+    memset(h, 0, sizeof(*h));
+    memcpy(h, &p, sizeof(p));
+    return cudaSuccess;
+}
+cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, &h, sizeof(*p)); return cudaSuccess; }
+cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
+}
+
+// Fast mode stand-in for the in-kernel all-reduce over the peers' inboxes (common.cuh,
+// block_reduce_finalize, ws.p2p): the same protocol -- totals then sequence number into every
+// peer's inbox, wait for every peer's, sum in rank order -- spoken by the launching host thread.
+void emu_p2p_allreduce(const ReduceWs &ws, double *tot, int nd)
+{
+    const unsigned long long seq = *ws.seq + 1ull;
+    *ws.seq = seq;
+    const size_t slot = (size_t)(seq & 1ull) * ws.nranks;
+    for (int q = 0; q < ws.nranks; ++q) {
+        volatile double *dst = ws.peers[q] + (slot + ws.rank) * 8;
+        for (int d = 0; d < nd; ++d) dst[d] = tot[d];
+        __atomic_thread_fence(__ATOMIC_SEQ_CST);
+        *reinterpret_cast<volatile unsigned long long *>(dst + 7) = seq;
+    }
+    for (int q = 0; q < ws.nranks; ++q) {
+        volatile unsigned long long *flag = reinterpret_cast<volatile unsigned long long *>(ws.inbox + (slot + q) * 8 + 7);
+        while (*flag != seq) sched_yield();
+    }
+    __atomic_thread_fence(__ATOMIC_SEQ_CST);
+    const volatile double *in = ws.inbox + slot * 8;
+    for (int d = 0; d < nd; ++d) {
+        double a = 0.0;
+        for (int q = 0; q < ws.nranks; ++q) a = a + in[q * 8 + d];
+        tot[d] = a;
+    }
+}

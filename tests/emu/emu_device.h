@@ -51,18 +51,18 @@ static inline void st_hint(double *a, double v, uint64_t) { *a = v; }
 // -- only valid for kernels without block-level synchronisation -- and replaces the reduction
 // by a sequential stand-in; it is ~100x faster and is what most emulated tests use.
 #undef __shared__
-#define __shared__ static
+#define __shared__ static thread_local      // per host thread: the ranks of a multi-GPU run are threads
 
 extern int emu_fibers_on;
 void emu_yield();
 void emu_block_barrier();
 void emu_warp_barrier(int warp);
-extern unsigned char emu_shfl_slots[32][32][8];
+extern thread_local unsigned char emu_shfl_slots[32][32][8];
 
 static inline void __syncthreads() { emu_block_barrier(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu_warp_barrier((int)(threadIdx.x >> 5)); }
 static inline void __threadfence() {}
-static inline void __threadfence_system() {}
+static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __nanosleep(unsigned) { emu_yield(); }
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { const unsigned o = *p; *p = o + v; return o; }
 static inline int atomicMax(int *p, int v) { const int o = *p; if (v > o) *p = v; return o; }
@@ -107,6 +107,7 @@ extern unsigned char *emu_dynamic_smem;
 void emu_set_dynamic_smem(size_t bytes);
 
 // ---- launchers
+void emu_p2p_allreduce(const ReduceWs &ws, double *tot, int nd);
 void emu_launch_fibers(int grid, int block, const void *kernel_closure, void (*invoke)(const void *));
 
 template <int ND, class Ws, class Fin, class Kernel>
@@ -131,6 +132,7 @@ static inline void emu_launch(int grid, int block, const Ws &ws, Fin fin, Kernel
     }
     if constexpr (ND > 0) {
         if (emu_reduced) {
+            if (ws.p2p) emu_p2p_allreduce(ws, emu_tot, ND);      // sharded runs: all-reduce over the inboxes
             for (int d = 0; d < ND; ++d) ws.sums[d] = emu_tot[d];
             if (!ws.defer) fin(emu_tot);
         }
