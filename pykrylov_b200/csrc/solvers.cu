@@ -1380,6 +1380,24 @@ struct MinBodyR2 {            // y = (-alfa/beta) r2 + y' ; beta'^2 = r2new . (M
     }
 };
 
+struct MinBodyR2Pre {         // preconditioned K2: r2' = (-alfa/beta) r2 + y' ; y = M r2' ; beta'^2 = r2'.y
+    static constexpr int kMinBlocks = 4;       // the fp64 division of `r ./ d` spills under 40 registers
+    double       *yn, *ypre;  // yn: y' in, the new r2 out; ypre: the new (preconditioned) y
+    const double *r2, *pd;
+    int           pmode;
+    DevScalars   *s;
+    double        c;
+    __device__ void init() { c = s->s[M_C_R2]; }
+    __device__ void operator()(int i, double *acc) const
+    {
+        const double yi = __dadd_rn(__dmul_rn(c, r2[i]), yn[i]);             // :246
+        yn[i] = yi;                                                          // :248 (new r2)
+        const double yp = apply_diag(pd, pmode, i, yi);                      // :249
+        ypre[i] = yp;
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(yi, yp));                       // :251
+    }
+};
+
 struct MinFinQR {
     DevScalars *s;
     double     *hist;
@@ -1676,9 +1694,18 @@ static int minres_setup(kry_solver *S, int)
 {
     // y = b.copy() lives in R[0]; r2 == y value-wise (no preconditioner), r1 is
     // first read on trip 2, when it is the rotated r2 (minres.py:160-165, 208).
-    MinSetupBody sb{solver_vec(S, "ra"), solver_vec(S, "rhs"), S->dinv, 0};
-    KRY_TRY((solver_pass<1>(S, sb, MinSetupFin{S->ds}, &S->ds->done)));
     const size_t bytes = (size_t)S->n * sizeof(double);
+    if (S->precon_mode) {
+        // with a preconditioner y = M r2 is a vector of its own (two buffers: a trip reads one and
+        // writes the other); r2 = r1 = b                                      minres.py:160-165
+        KRY_CUDA(cudaMemcpyAsync(solver_vec(S, "ra"), solver_vec(S, "rhs"), bytes, cudaMemcpyDeviceToDevice,
+                                 S->ctx->stream));
+        MinSetupBody sb{solver_vec(S, "ya"), solver_vec(S, "rhs"), S->dinv, S->precon_mode};
+        KRY_TRY((solver_pass<1>(S, sb, MinSetupFin{S->ds}, &S->ds->done)));
+    } else {
+        MinSetupBody sb{solver_vec(S, "ra"), solver_vec(S, "rhs"), S->dinv, 0};
+        KRY_TRY((solver_pass<1>(S, sb, MinSetupFin{S->ds}, &S->ds->done)));
+    }
     KRY_CUDA(cudaMemsetAsync(solver_vec(S, "wa"), 0, bytes, S->ctx->stream));   // :206-207
     KRY_CUDA(cudaMemsetAsync(solver_vec(S, "wb"), 0, bytes, S->ctx->stream));
     S->rot = 0;
@@ -1698,6 +1725,20 @@ static int minres_iterate(kry_solver *S)
     const int k = (int)(S->rot % 3), j = (int)(S->rot % 2);
     double *r2 = R[k], *r1 = R[(k + 2) % 3], *rn = R[(k + 1) % 3];
     const int *done = &S->ds->done;
+    if (S->precon_mode) {
+        // preconditioned: v = y/beta is built from y = M r2 (Y[j]); K2 writes the next y to Y[1-j]
+        double *Y[2] = {solver_vec(S, "ya"), solver_vec(S, "yb")};
+        double *y = Y[j], *ynext = Y[1 - j];
+        MinGather g{y, S->ds, 0.0};
+        MinEpiY e{rn, y, r1, S->ds, 0, 0, 0, 0};
+        KRY_TRY((solver_spmv<1>(S, g, e, MinFinAlfa{S->ds}, done, y)));
+        MinBodyR2Pre b2{rn, ynext, r2, S->dinv, S->precon_mode, S->ds, 0.0};
+        KRY_TRY((solver_pass<1>(S, b2, MinFinQR{S->ds, S->hist}, done)));
+        MinBodyW bw{W[1 - j], x, W[j], y, S->ds, 0, 0, 0, 0, 0};
+        KRY_TRY((solver_pass<1>(S, bw, MinFinW{S->ds}, done)));
+        S->rot++;
+        return KRY_OK;
+    }
     MinGather g{r2, S->ds, 0.0};
     MinEpiY e{rn, r2, r1, S->ds, 0, 0, 0, 0};
     KRY_TRY((solver_spmv<1>(S, g, e, MinFinAlfa{S->ds}, done, r2)));
@@ -1754,13 +1795,14 @@ static const VecSpec *method_vectors(kry_method m, int *count)
     static const VecSpec tfq[] = {{"x", true}, {"y", true}, {"z", true}, {"r0", false}, {"w", false},
                                   {"d", false}, {"u", false}, {"v", false}, {"rhs", false}};
     static const VecSpec mr[] = {{"x", false}, {"ra", true}, {"rb", true}, {"rc", true},
-                                 {"wa", false}, {"wb", false}, {"rhs", false}};
+                                 {"wa", false}, {"wb", false}, {"rhs", false},
+                                 {"ya", true}, {"yb", true}};    // y = M r2 of the preconditioned form
     switch (m) {
         case KRY_CG: *count = 6; return cg;
         case KRY_BICGSTAB: *count = 10; return bcg;
         case KRY_CGS: *count = 10; return cgs;
         case KRY_TFQMR: *count = 9; return tfq;
-        case KRY_MINRES: *count = 7; return mr;
+        case KRY_MINRES: *count = 9; return mr;
     }
     *count = 0;
     return nullptr;
@@ -1863,8 +1905,6 @@ static int solver_setup_common(kry_solver *S, int guess, const kry_solver_params
     solver_drop_graph(S);
     S->warm = false;
     S->snap_pending[0] = S->snap_pending[1] = false;
-    KRY_REQUIRE(!(S->method == KRY_MINRES && S->precon_mode), KRY_ERR_UNSUPPORTED,
-                "kry_solver_setup: preconditioned MINRES is not device-resident yet");
     S->params = *p;
     DevScalars h;
     memset(&h, 0, sizeof(h));
@@ -2171,6 +2211,7 @@ static double *solver_vec_logical(kry_solver *S, const char *name)
         cudaStreamSynchronize(S->ctx->stream);
         const char *R[3] = {"ra", "rb", "rc"}, *W[2] = {"wa", "wb"};
         const int k = (int)(itn % 3), j = (int)(itn % 2);
+        if (!strcmp(name, "y") && S->precon_mode) return solver_vec(S, (itn % 2) ? "yb" : "ya");
         if (!strcmp(name, "r2") || !strcmp(name, "y")) return solver_vec(S, R[k]);
         if (!strcmp(name, "r1")) return solver_vec(S, R[(k + 2) % 3]);
         if (!strcmp(name, "w")) return solver_vec(S, W[j]);

@@ -5,7 +5,9 @@ Keyword contract of the reference's ``solve`` (minres.py:121-130): ``precon``,
 randomised symmetry test), ``itnlim`` (5n), ``rtol`` (1e-12), ``etol`` (1e-6),
 ``store_resids``, ``store_iterates``, ``window`` (5).  The Lanczos step
 (minres.py:236-256), the QR update (:270-297) and all stopping tests (:323-361)
-run on the GPU, 3 fused launches per iteration.
+run on the GPU, 3 fused launches per iteration; so does a diagonal preconditioner
+(``DiagonalOperator`` or a bmark-style ``r / diag`` object).  Closure operators and opaque
+preconditioners go through the host-callback bridge.
 """
 import numpy as np
 
@@ -64,7 +66,7 @@ class Minres(KrylovMethod):
         self.dir_errors_window = []
         self.iterates = []
         result_type = _engine.check_real(A, b)
-        plan = _engine.resolve(A, None, n) if precon is None else None
+        plan = _engine.resolve(A, precon, n)        # device operator + no / a diagonal preconditioner
 
         if show:
             print(self.first + "Solution of symmetric Ax = b")
@@ -72,7 +74,7 @@ class Minres(KrylovMethod):
                   % (n, (precon is not None), shift))
             print("itnlim =  %3d     rtol   =  %11.2e\n" % (itnlim, rtol))
 
-        if plan is None:       # closure operator or a preconditioner: host-driven loop on device vectors
+        if plan is None:       # closure operator or an opaque preconditioner: host-driven loop on device vectors
             from .. import _bridged
             return _bridged.minres(self, b, precon, shift, show, check, itnlim, rtol, etol,
                                    store_iterates, window, result_type)

@@ -105,3 +105,60 @@ def test_smoke_logic_under_emulation(emu_ctx, capsys):
     import __graft_entry__ as entry
     entry.smoke()
     assert "smoke ok" in capsys.readouterr().out
+
+
+def test_our_arm_multi_rank_code_path_under_emulation(emu_ctx, capsys, monkeypatch):
+    """bench.main_ours as the driver launches it for N > 1 (one rank per GPU, row-sharded operator,
+    max-over-ranks timing, the 1-GPU same-workload leg on rank 0), with three emulated ranks as
+    threads of this process.  Numbers are meaningless here; every leg must run, only rank 0 may
+    print, and the line must say which launch plan the shards ran."""
+    import argparse
+    import ctypes as C
+    import threading
+    sys.path.insert(0, ROOT)
+    import bench
+    import pykrylov_b200.comm as comm
+    from pykrylov_b200 import _lib as L
+    from pykrylov_b200 import device as dev
+    world = 3
+    monkeypatch.setattr(bench, "G_CONFIG5", 30)
+    uid = C.create_string_buffer(L.KRY_COMM_ID_BYTES)
+    L.call("kry_comm_unique_id", uid)
+    local = threading.local()
+
+    def init_from_env(*a, **k):
+        ctx = dev.Context(0)
+        ctx.comm_init(world, local.rank, uid.raw)
+        local.ctx = ctx
+        return ctx, local.rank, world
+
+    monkeypatch.setattr(comm, "init_from_env", init_from_env)
+    errors = [None] * world
+
+    def body(rank):
+        local.rank = rank
+        args = argparse.Namespace(gpus=world, steps=24, warmup=3, impl="ours", grid=0, no_cpu=True, no_single=False,
+                                  no_config5=False, cg_fuse=None, cg_fuse_shards=None, nccl_allreduce=False)
+        try:
+            bench.main_ours(args)
+        except BaseException as exc:                    # noqa: BLE001
+            errors[rank] = exc
+        finally:
+            if getattr(local, "ctx", None) is not None:
+                local.ctx.close()
+
+    threads = [threading.Thread(target=body, args=(r,), daemon=True) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(240)
+    assert not any(t.is_alive() for t in threads), "a rank is stuck"
+    assert errors == [None] * world, errors
+    lines = [ln for ln in capsys.readouterr().out.splitlines() if ln.strip()]
+    assert len(lines) == 1                                           # rank 0 only
+    d = json.loads(lines[0])
+    assert d["n_gpus"] == world and d["scaling"] == "strong" and d["value"] > 0
+    assert d["config"]["rows"] == 30 * 30 and d["config"]["rows_per_gpu"] == 300
+    assert d["roofline"]["cg_launch_plan"] == 2 and d["gpu_launches"] >= 2 * 24      # fused plan on shards (+ halo packs)
+    assert d["one_gpu_same_workload"]["value"] > 0 and d["speedup_vs_one_gpu"] > 0
+    assert d["e2e"]["value"] > 0 and "config5_one_gpu" not in d

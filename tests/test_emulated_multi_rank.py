@@ -198,3 +198,46 @@ def test_other_sharded_loops_follow_the_oracle(emu_ctx, method, world):
         return True
 
     assert all(run_ranks(world, worker))
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_preconditioned_minres_follows_the_oracle(emu_ctx, world):
+    """MINRES with a diagonal preconditioner, device-resident on row shards (the preconditioned
+    y = M r2 is the SpMV input there and carries the halo tail)."""
+    from pykrylov_b200 import _lib as L
+    from pykrylov_b200 import device as dev
+    from pykrylov_b200.comm import row_partition
+    m = 6
+    n = m ** 3
+    ip, ix, dv = kr.convdiff3d_csr(m, gamma=0.0)
+    M = CsrRef((n, n), ip, ix, dv)
+    rhs = M.matvec(np.linspace(1.0, 2.0, n))
+    d = 0.5 + np.random.default_rng(4).random(n)
+    ref = kr.minres_solve(M, rhs, precon=lambda r: r / d)
+    uid = C.create_string_buffer(L.KRY_COMM_ID_BYTES)
+    L.call("kry_comm_unique_id", uid)
+    ranges = row_partition(n, world)
+
+    def worker(rank):
+        lo, hi = ranges[rank]
+        ctx = dev.Context(0)
+        ctx.comm_init(world, rank, uid.raw)
+        try:
+            A = dev.DeviceCsr.from_arrays(ctx, (hi - lo, n), ip[lo:hi + 1] - ip[lo], ix[ip[lo]:ip[hi]], dv[ip[lo]:ip[hi]],
+                                          symmetric=True)
+            A.shard_finalize(n, lo)
+            S = dev.DeviceSolver(ctx, "minres", A)
+            S.set_precon_diag(d[lo:hi], 2)
+            S.setup(rhs[lo:hi], abstol=0.0, reltol=0.0, matvec_max=5 * n, rtol=1e-12, etol=1e-6, window=5)
+            st = S.run(5)
+            hist = S.drain_history(st)[:, 0]
+            assert (int(st.istop), int(st.n_iter)) == (ref.istop, ref.itn)
+            rh = np.array(ref.residHistory, dtype=float)
+            assert len(hist) == len(rh) and np.max(np.abs(hist[:10] - rh[:10]) / rh[:10]) <= 1e-9
+            assert np.max(np.abs(S.solution() - ref.x[lo:hi])) <= 1e-7 * np.max(np.abs(ref.x))
+            ctx.barrier()
+        finally:
+            ctx.close()
+        return True
+
+    assert all(run_ranks(world, worker))

@@ -919,3 +919,49 @@ def test_minres_2_launch_plan_is_bit_identical_to_the_3_launch_plan(ctx):
         for u, v in zip(a[3:], b[3:]):
             assert np.array_equal(u, v, equal_nan=True)
     assert np.array_equal(out[0][-1], out[1][-1], equal_nan=True)
+
+
+@pytest.mark.parametrize("pmode", [1, 2])
+def test_minres_with_diagonal_preconditioner_is_device_resident(ctx, pmode):
+    """Minres.solve(precon=<diagonal>) iterates on the device (no host bridge) and follows the
+    reference loop: same stop reason and iteration count, history and solution to rounding."""
+    import pykrylov_b200._engine as eng
+    from pykrylov_b200.linop import DiagonalOperator, csr_operator
+    from pykrylov_b200.minres import Minres
+    S0 = fixtures()["jpwh_991"].to_scipy()
+    M = CsrRef.from_scipy(((S0 + S0.T) * 0.5).tocsr())
+    n = M.shape[0]
+    rhs = M.matvec(np.ones(n))
+    d = 0.5 + np.random.default_rng(12).random(n)
+    ref = kr.minres_solve(M, rhs, precon=(lambda r: d * r) if pmode == 1 else (lambda r: r / d))
+    op = csr_operator(M.shape, M.indptr, M.indices, M.data, symmetric=True, context=ctx)
+
+    class DiagonalPrec(object):                     # examples/bmark.py:14-22
+        def __init__(self, diag):
+            self.diag = diag
+
+        def __call__(self, y):
+            return y / self.diag
+
+        __mul__ = __call__
+
+    precon = DiagonalOperator(d) if pmode == 1 else DiagonalPrec(d)
+    bridged = []
+    real = eng.HostBridge
+
+    class Spy(real):
+        def __init__(self, *a, **k):
+            bridged.append(1)
+            real.__init__(self, *a, **k)
+
+    eng.HostBridge = Spy
+    try:
+        mr = Minres(op, context=ctx)
+        mr.solve(rhs, precon=precon, show=False, check=False)
+    finally:
+        eng.HostBridge = real
+    assert not bridged
+    assert mr.istop == ref.istop and abs(mr.itn - ref.itn) <= 1
+    k = min(len(ref.residHistory), len(mr.residHistory), 20)
+    assert rel(mr.residHistory[:k], ref.residHistory[:k]) <= 1e-9
+    assert np.linalg.norm(mr.x - ref.x) <= 1e-6 * np.linalg.norm(ref.x)
