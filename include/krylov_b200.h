@@ -93,6 +93,10 @@ int kry_prof_read(kry_ctx *ctx, int64_t *samples, double *total_ms);
 #define KRY_OPT_MINRES_FUSE 7 /* 1 (default): MINRES runs 2 launches per iteration -- the w / x update of a trip
                                 (minres.py:294-297, no reduction in it) rides in the second launch of the next
                                 trip; 0: 3 launches.  Candidate; latched at kry_solver_setup.               */
+#define KRY_OPT_MINRES_PERSISTENT 8 /* 1 (default): unsharded, unpreconditioned MINRES runs as ONE cooperative
+                                persistent kernel per kry_solver_iterate call: one CTA wave, the three phases of
+                                a trip separated by two grid-wide barriers that carry the reductions -- no launch
+                                between trips.  Candidate; latched at kry_solver_setup.                        */
 #define KRY_OPT_CG_FUSE_SHARDS 5 /* 1 (default): row shards use the CG_FUSE plan too (the packed halo then
                                 carries beta p - r of the boundary entries); 0: shards keep plan 0 */
 int kry_ctx_set_option(kry_ctx *ctx, int option, int value);

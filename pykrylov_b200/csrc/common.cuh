@@ -94,6 +94,7 @@ struct kry_ctx {
     int          cg_fuse_shards;   // KRY_OPT_CG_FUSE_SHARDS: the plan also applies to row shards
     int          cg_one_cta;       // KRY_OPT_CG_ONE_CTA: small problems iterate inside one CTA
     int          minres_fuse;      // KRY_OPT_MINRES_FUSE: 2-launch MINRES plan
+    int          minres_persistent;    // KRY_OPT_MINRES_PERSISTENT: one cooperative kernel per iterate call
     // lifetime: vectors / operators / solvers hold a reference; kry_ctx_destroy releases the
     // device resources at once but the struct itself lives until the last child is destroyed,
     // so handles may be destroyed in any order (interpreter shutdown does exactly that)

@@ -70,6 +70,7 @@ extern "C" int kry_ctx_create(int device, kry_ctx **out)
     c->use_graphs = 1;
     c->cg_one_cta = 1;
     c->minres_fuse = 1;
+    c->minres_persistent = 1;
     c->cg_fuse = 2;        // measured on B200, 10^7-row 5-pt Laplacian: 0.222 ms/iteration against 0.233
                            // (form 1) and 0.249 (form 0) -- profiles/r1b_ab_cgfuse*.json, r1_final_bench_n1.json
     c->cg_fuse_shards = 1; // row shards use the same plan: 2 x B200, 10^8 rows: 825.7 vs 803.8 it/s with the same
@@ -235,12 +236,14 @@ extern "C" int kry_ctx_set_option(kry_ctx *c, int option, int value)
     KRY_REQUIRE(c, KRY_ERR_INVALID, "kry_ctx_set_option: NULL context");
     KRY_REQUIRE(option == KRY_OPT_L2_HINTS || option == KRY_OPT_GRAPHS || option == KRY_OPT_P2P ||
                     option == KRY_OPT_CG_FUSE || option == KRY_OPT_CG_FUSE_SHARDS ||
-                    option == KRY_OPT_CG_ONE_CTA || option == KRY_OPT_MINRES_FUSE,
+                    option == KRY_OPT_CG_ONE_CTA || option == KRY_OPT_MINRES_FUSE ||
+                    option == KRY_OPT_MINRES_PERSISTENT,
                 KRY_ERR_INVALID, "kry_ctx_set_option: unknown option %d", option);
     if (option == KRY_OPT_L2_HINTS) c->l2_hints = value;
     else if (option == KRY_OPT_CG_FUSE_SHARDS) c->cg_fuse_shards = value ? 1 : 0;
     else if (option == KRY_OPT_CG_ONE_CTA) c->cg_one_cta = value ? 1 : 0;
     else if (option == KRY_OPT_MINRES_FUSE) c->minres_fuse = value ? 1 : 0;
+    else if (option == KRY_OPT_MINRES_PERSISTENT) c->minres_persistent = value ? 1 : 0;
     else if (option == KRY_OPT_CG_FUSE) {
         KRY_REQUIRE(value >= 0 && value <= 2, KRY_ERR_INVALID, "kry_ctx_set_option: CG_FUSE=%d not in 0..2", value);
         c->cg_fuse = value;
@@ -265,6 +268,7 @@ extern "C" int kry_ctx_get_option(kry_ctx *c, int option, int *value)
         case KRY_OPT_CG_FUSE_SHARDS: *value = c->cg_fuse_shards; break;
         case KRY_OPT_CG_ONE_CTA: *value = c->cg_one_cta; break;
         case KRY_OPT_MINRES_FUSE: *value = c->minres_fuse; break;
+        case KRY_OPT_MINRES_PERSISTENT: *value = c->minres_persistent; break;
         default: kry_set_error("kry_ctx_get_option: unknown option %d", option); return KRY_ERR_INVALID;
     }
     return KRY_OK;

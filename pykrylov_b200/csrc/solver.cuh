@@ -46,6 +46,8 @@ enum {
     S_PSTATE, S_XPEND,
     // fused MINRES plan (KRY_OPT_MINRES_FUSE): 1 = the w / x update of trip n_iter-1 is still owed
     M_WPEND,
+    // persistent MINRES kernel: 1 = the reference left the trip before the w / x update (beta < 0)
+    M_STOPNOW,
     S_COUNT
 };
 constexpr int KRY_NSCAL = 64;
@@ -83,6 +85,7 @@ struct kry_solver {
     bool              fresh;            // fused CG: nothing pending, p sits in the next trip's source buffer
     bool              one_cta;          // CG: the whole loop runs inside one CTA (KRY_OPT_CG_ONE_CTA)
     int               minres_fuse;      // MINRES launch plan latched at setup (KRY_OPT_MINRES_FUSE)
+    bool              minres_persistent;    // ... or the cooperative persistent kernel (KRY_OPT_MINRES_PERSISTENT)
     DevScalars       *snap_host[2];     // pinned status snapshots (kry_solver_status_enqueue / _wait)
     cudaEvent_t       snap_ev[2];
     bool              snap_pending[2];

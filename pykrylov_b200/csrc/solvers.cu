@@ -1407,7 +1407,8 @@ struct MinFinQR {
     {
         const double eps = 2.220446049250313e-16;
         double *v = s->s;
-        if (fuse) v[M_WPEND] = 0.0;      // the body of this launch paid what the previous trip owed
+        if (fuse == 1) v[M_WPEND] = 0.0; // the body of this launch paid what the previous trip owed
+        if (fuse == 2) v[M_STOPNOW] = 0.0;
         s->n_iter++;
         s->n_matvec++;
         const long long itn = s->n_iter;
@@ -1418,6 +1419,7 @@ struct MinFinQR {
         if (beta < 0) {                                                      // :252-254
             s->istop = 6;
             s->done = 1;
+            if (fuse == 2) v[M_STOPNOW] = 1.0;
             return;
         }
         beta = sqrt(beta);                                                   // :255
@@ -1493,9 +1495,13 @@ struct MinFinQR {
             if (test2 <= s->rtol) s->istop = 2;
             if (test1 <= s->rtol) s->istop = 1;
         }
-        if (fuse) {
+        if (fuse == 1) {
             v[M_WPEND] = 1.0;                                                // minres.py:294-297 of this trip
             if (s->istop > 0 || itn >= s->matvec_max) s->done = 1;           // :381, :218
+            return;
+        }
+        if (fuse == 2) {             // persistent kernel: every CTA reads `done` right after this barrier, runs
+            if (s->istop > 0 || itn >= s->matvec_max) s->done = 1;   // the w / x update of the trip and leaves
             return;
         }
         // `done` is latched by K3 (the x update of this trip must still run)
@@ -1710,6 +1716,12 @@ static int minres_setup(kry_solver *S, int)
     KRY_CUDA(cudaMemsetAsync(solver_vec(S, "wb"), 0, bytes, S->ctx->stream));
     S->rot = 0;
     S->minres_fuse = S->ctx->minres_fuse;
+    S->minres_persistent = S->ctx->minres_persistent && !S->sharded && !S->A->halo.active && !S->precon_mode &&
+                           (S->A->kind == KRY_SPMV_AUTO || S->A->kind == KRY_SPMV_ROW) && S->A->A.max_row <= 64;
+#ifdef KRY_EMULATE
+    if (!emu_fibers_on) S->minres_persistent = false;          // the host emulation plays it in SIMT mode only
+#endif
+    if (S->minres_persistent) S->minres_fuse = 0;                // its HBM state is that of the 3-launch plan
     S->fresh = true;
     return KRY_OK;
 }
@@ -1762,6 +1774,148 @@ static int minres_iterate(kry_solver *S)
     MinBodyW bw{W[1 - j], x, W[j], r2, S->ds, 0, 0, 0, 0, 0};
     KRY_TRY((solver_pass<1>(S, bw, MinFinW{S->ds}, done)));
     S->rot++;
+    return KRY_OK;
+}
+
+// ---- MINRES as one cooperative persistent kernel (KRY_OPT_MINRES_PERSISTENT).  At N = 10^6
+// (BASELINE config 2) a trip moves ~180 MB, i.e. ~30 us of HBM time, and three dependent launches
+// cost about as much again in launch gaps, ramp-up, tails and last-CTA finalisation.  Here one
+// CTA wave stays resident for the whole kry_solver_iterate call; the three phases of a trip are
+// the same loops and functors as the three kernels (MinGather/MinEpiY, MinBodyR2, MinBodyW), and
+// the two reductions ride in grid-wide barriers: the CTA that arrives last sums the partials in
+// index order, runs the scalar step (MinFinAlfa / MinFinQR) and releases the others.  Nothing
+// __shared__ is live across such a barrier.  Phase 3 needs no barrier before the next trip's
+// phase 1 (disjoint buffers; the next barrier orders everything else).
+template <int ND, class Fin>
+__device__ __forceinline__ void grid_reduce_sync(double (&acc)[ND], const ReduceWs &ws, Fin &fin,
+                                                 unsigned *gen_ptr, unsigned &my_gen)
+{
+    __shared__ double s_warp[ND][32];
+    __shared__ int    s_last;
+    block_sum<ND>(acc, s_warp);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int d = 0; d < ND; ++d) ws.partials[(size_t)d * ws.stride + blockIdx.x] = acc[d];
+        __threadfence();
+        const unsigned ticket = atomicAdd(ws.counter, 1u);
+        s_last = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        double tot[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            double a = 0.0;
+            const volatile double *p = ws.partials + (size_t)d * ws.stride;
+            for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) a = __dadd_rn(a, p[i]);
+            tot[d] = a;
+        }
+        __syncthreads();            // s_warp reuse
+        block_sum<ND>(tot, s_warp);
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int d = 0; d < ND; ++d) ws.sums[d] = tot[d];
+            *ws.counter = 0u;
+            fin(tot);
+            __threadfence();
+            atomicAdd(gen_ptr, 1u);                               // release
+        }
+    } else if (threadIdx.x == 0) {
+        while (*reinterpret_cast<volatile unsigned *>(gen_ptr) == my_gen) __nanosleep(20);
+        __threadfence();
+    }
+    my_gen++;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256, 4)
+minres_persistent_kernel(CsrView A, double *Ra, double *Rb, double *Rc, double *Wa, double *Wb, double *x,
+                         DevScalars *s, double *hist, ReduceWs ws, unsigned *gen_ptr, long long n_iters)
+{
+    if (s->done) return;
+    unsigned my_gen = *reinterpret_cast<volatile unsigned *>(gen_ptr);
+    long long rot = s->n_iter;                       // trips done so far: fixes the buffer rotation
+    double *R[3] = {Ra, Rb, Rc}, *W[2] = {Wa, Wb};
+    const int stride = (int)(gridDim.x * blockDim.x), t0 = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    const int nn = A.nrows, half = nn >> 1;
+    for (long long it = 0; it < n_iters; ++it, ++rot) {
+        const int k = (int)(rot % 3), j = (int)(rot % 2);
+        double *r2 = R[k], *r1 = R[(k + 2) % 3], *rn = R[(k + 1) % 3];
+        // phase 1: y' = A v - shift v - (beta/oldb) r1 with v = y/beta ; alfa = v.y'      (K1)
+        double acc[1] = {0.0};
+        {
+            MinGather g{r2, s, 0.0};
+            MinEpiY   e{rn, r2, r1, s, 0, 0, 0, 0};
+            g.init();
+            e.init();
+            for (int row = t0; row < nn; row += stride) {
+                const int rs = __ldg(A.rowptr + row), re = __ldg(A.rowptr + row + 1);
+                double sum = 0.0;
+                for (int q = rs; q < re; ++q)
+                    sum = __dadd_rn(sum, __dmul_rn(__ldg(A.val + q), g(__ldg(A.col + q))));
+                e(row, sum, acc);
+            }
+            MinFinAlfa f{s};
+            grid_reduce_sync<1>(acc, ws, f, gen_ptr, my_gen);
+        }
+        // phase 2: r2' = (-alfa/beta) r2 + y' ; beta'^2 = r2'.r2' ; QR step, norms, stopping tests   (K2)
+        {
+            MinBodyR2 b{rn, nullptr, r2, nullptr, 0, s, 0.0};
+            b.init();
+            acc[0] = 0.0;
+            for (int i = t0; i < half; i += stride) b.pair(i, acc);
+            if ((nn & 1) && t0 == 0) b(nn - 1, acc);
+            MinFinQR f{s, hist, 2};
+            grid_reduce_sync<1>(acc, ws, f, gen_ptr, my_gen);
+        }
+        // both written by the last CTA before it released the barrier, by nobody afterwards: uniform
+        const int stop = s->done;
+        if (stop && s->s[M_STOPNOW] != 0.0) break;     // beta < 0: the reference leaves before the w update
+        // phase 3: w = (v - oldeps w1 - delta w2)/gamma ; x += phi w                      (K3)
+        {
+            MinBodyW b{W[1 - j], x, W[j], r2, s, 0, 0, 0, 0, 0};
+            b.init();
+            for (int i = t0; i < half; i += stride) b.pair(i, nullptr);
+            if ((nn & 1) && t0 == 0) b(nn - 1, nullptr);
+        }
+        if (stop) break;
+    }
+}
+
+static int minres_persistent_iterate(kry_solver *S, int64_t n_iters)
+{
+    kry_ctx *c = S->ctx;
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        int b = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, minres_persistent_kernel, 256, 0) != cudaSuccess || b < 1) b = 1;
+        per_sm = b;
+    }
+    int64_t need = (S->n + 255) / 256;
+    if (need < 1) need = 1;
+    const int64_t cap = (int64_t)c->sm_count * per_sm;             // one resident wave: co-residency is required
+    const int grid = (int)(need < cap ? need : cap);
+    KRY_TRY(kry_ctx_ensure_partials(c, grid));
+    ReduceWs ws = kry_ws(c);
+    CsrView A = csr_view(S->A->A);
+    double *Ra = solver_vec(S, "ra"), *Rb = solver_vec(S, "rb"), *Rc = solver_vec(S, "rc");
+    double *Wa = solver_vec(S, "wa"), *Wb = solver_vec(S, "wb"), *x = solver_vec(S, "x");
+    DevScalars *ds = S->ds;
+    double *hist = S->hist;
+    unsigned *gen_ptr = c->counter + 16;                           // inside the zeroed 256-byte counter block
+    long long n = (long long)n_iters;
+#ifdef KRY_EMULATE
+    KRY_REQUIRE(emu_fibers_on, KRY_ERR_UNSUPPORTED, "minres_persistent needs the SIMT mode of the emulation");
+    auto body = [&] { minres_persistent_kernel(A, Ra, Rb, Rc, Wa, Wb, x, ds, hist, ws, gen_ptr, n); };
+    emu_launch_fibers_mode(grid, 256, &body, [](const void *k) { (*static_cast<const decltype(body) *>(k))(); }, 1);
+#else
+    void *args[] = {&A, &Ra, &Rb, &Rc, &Wa, &Wb, &x, &ds, &hist, &ws, &gen_ptr, &n};
+    KRY_CUDA(cudaLaunchCooperativeKernel((const void *)minres_persistent_kernel, dim3(grid), dim3(256), args, 0, c->stream));
+#endif
+    c->launches++;
+    S->rot += n_iters;
+    KRY_CUDA(cudaGetLastError());
     return KRY_OK;
 }
 
@@ -2025,6 +2179,8 @@ extern "C" int kry_solver_iterate(kry_solver *S, int64_t n_iters)
     kry_ctx *c = S->ctx;
     KRY_CUDA(cudaSetDevice(c->device));
     if (S->method == KRY_CG && S->one_cta) return n_iters > 0 ? cg_one_cta_iterate(S, n_iters) : KRY_OK;
+    if (S->method == KRY_MINRES && S->minres_persistent)
+        return n_iters > 0 ? minres_persistent_iterate(S, n_iters) : KRY_OK;
     int64_t left = n_iters;
     // Graph replay: not on sharded runs (NCCL in the sequence), not while per-launch
     // profiling events are being recorded, and only once the sequence ran un-captured

@@ -72,3 +72,59 @@ def test_cg_one_cta_kernel_to_convergence__simt(ctx):
             A._release()
     finally:
         ctx.set_option(L.KRY_OPT_CG_ONE_CTA, saved)
+
+
+def test_minres_persistent_kernel_follows_the_oracle_and_the_3_launch_plan__simt(ctx):
+    """KRY_OPT_MINRES_PERSISTENT (candidate): one cooperative kernel per iterate call -- a resident
+    CTA wave, the reductions carried by grid-wide barriers -- played by the SIMT emulation's
+    cooperative launch (all blocks alive at once).  To convergence and with a tiny itnlim,
+    against the oracle; against the 3-launch plan to rounding; one launch per call."""
+    import numpy as np
+    import scipy.sparse as sp
+    from oracle import krylov_ref as kr
+    from oracle.csr_ref import CsrRef
+    from pykrylov_b200 import _lib as L
+    from pykrylov_b200 import device as dev
+    rng = np.random.default_rng(8)
+    saved = ctx.get_option(L.KRY_OPT_MINRES_PERSISTENT)
+    try:
+        for n, itnlim, shift in ((700, None, 0.0), (333, 7, 0.25), (64, None, 0.0), (257, 1, 0.0)):
+            B = sp.random(n, n, density=min(1.0, 5.0 / n), random_state=int(rng.integers(1 << 30)), format="csr")
+            A0 = ((B + B.T) * 0.5 + sp.diags(rng.choice([-1.0, 1.0], size=n) * (2.0 + abs(B).sum(axis=1).max()))).tocsr()
+            A0.sort_indices()
+            M = CsrRef.from_scipy(A0)
+            rhs = M.matvec(rng.standard_normal(n))
+            lim = 5 * n if itnlim is None else itnlim
+            ref = kr.minres_solve(M, rhs, shift=shift, itnlim=lim)
+            res = {}
+            for persistent in (1, 0):
+                ctx.set_option(L.KRY_OPT_MINRES_PERSISTENT, persistent)
+                ctx.set_option(L.KRY_OPT_MINRES_FUSE, 0)
+                A = dev.DeviceCsr.from_arrays(ctx, M.shape, M.indptr, M.indices, M.data, symmetric=True)
+                S = dev.DeviceSolver(ctx, "minres", A)
+                S.setup(rhs, abstol=0.0, reltol=0.0, matvec_max=lim, shift=shift, rtol=1e-12, etol=1e-6, window=5)
+                l0 = ctx.launch_count()
+                S.iterate(3)
+                if persistent:
+                    assert ctx.launch_count() - l0 == 1
+                w3 = S.get_vector("w")
+                st = S.run(4)
+                hist = S.drain_history(st)[:, 0]
+                assert (int(st.istop), int(st.n_iter)) == (ref.istop, ref.itn), (n, persistent)
+                rh = np.array(ref.residHistory, dtype=float)
+                k = min(len(rh), 8)
+                assert len(hist) == len(rh) and np.max(np.abs(hist[:k] - rh[:k]) / rh[:k]) <= 1e-9
+                xs = S.solution()
+                assert np.max(np.abs(xs - ref.x)) <= 1e-7 * max(np.max(np.abs(ref.x)), 1e-300)
+                res[persistent] = (hist, xs, w3, st.resid_norm)
+                S._release()
+                A._release()
+            # the two plans sum their inner products over different grids: equal to rounding early
+            # on (w after 3 trips, the first history entries), to the solver's accuracy at the end
+            (h1, x1, w1, _), (h0, x0, w0, _) = res[1], res[0]
+            assert np.max(np.abs(w1 - w0)) <= 1e-11 * max(np.max(np.abs(w0)), 1e-300)
+            k = min(len(h0), 8)
+            assert np.max(np.abs(h1[:k] - h0[:k])) <= 1e-11 * np.max(np.abs(h0[:k]))
+            assert np.max(np.abs(x1 - x0)) <= 1e-7 * max(np.max(np.abs(x0)), 1e-300)
+    finally:
+        ctx.set_option(L.KRY_OPT_MINRES_PERSISTENT, saved)
