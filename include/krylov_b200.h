@@ -87,6 +87,16 @@ int kry_prof_read(kry_ctx *ctx, int64_t *samples, double *total_ms);
                                 2: 2 launches  [x += alpha p ; p = beta p - r]+SpMV+dot | r update+dot
                                 The fused forms carry the p (and x) update of a trip into the SpMV of
                                 the next one; results are bit-identical to form 0.                  */
+#define KRY_OPT_CG_ONE_CTA 6  /* 1 (default): CG on an unsharded operator whose CSR and vectors fit the shared
+                                memory of one SM runs as ONE persistent CTA -- the whole loop inside a single
+                                launch per kry_solver_iterate call (candidate; latched at kry_solver_setup) */
+#define KRY_OPT_MINRES_FUSE 7 /* 1 (default): MINRES runs 2 launches per iteration -- the w / x update of a trip
+                                (minres.py:294-297, no reduction in it) rides in the second launch of the next
+                                trip; 0: 3 launches.  Candidate; latched at kry_solver_setup.               */
+#define KRY_OPT_MINRES_PERSISTENT 8 /* 1 (default): unsharded, unpreconditioned MINRES runs as ONE cooperative
+                                persistent kernel per kry_solver_iterate call: one CTA wave, the three phases of
+                                a trip separated by two grid-wide barriers that carry the reductions -- no launch
+                                between trips.  Candidate; latched at kry_solver_setup.                        */
 #define KRY_OPT_CG_FUSE_SHARDS 5 /* 1 (default): row shards use the CG_FUSE plan too (the packed halo then
                                 carries beta p - r of the boundary entries); 0: shards keep plan 0 */
 int kry_ctx_set_option(kry_ctx *ctx, int option, int value);
@@ -154,6 +164,9 @@ int kry_csr_create_convdiff3d(kry_ctx *ctx, int64_t m, double gamma,
 #define KRY_SPMV_TMA     3   /* persistent CTAs, cp.async.bulk (TMA) multi-stage     */
 #define KRY_SPMV_ROWB8   4   /* one thread per row, loads batched 8 entries at a time */
 #define KRY_SPMV_ROWB4   5   /* one thread per row, loads batched 4 entries at a time */
+#define KRY_SPMV_ROWPF   6   /* one thread per row, row pointers loaded one trip ahead (candidate)  */
+#define KRY_SPMV_ROWPF2  7   /* ... two trips ahead, and the next trip's col/val window prefetched
+                                into L2 (candidate)                                                */
 int kry_csr_set_kernel(kry_csr *A, int kind, int tile_nnz, int threads);
 
 /* ------------------------------------------------------- hot-path kernels */
@@ -257,6 +270,16 @@ int kry_solver_setup_dev(kry_solver *S, const kry_vec *rhs, const kry_vec *guess
  * formulas and latch `done`; launches after that are no-ops.                       */
 int kry_solver_iterate(kry_solver *S, int64_t n_iters);
 int kry_solver_status_read(kry_solver *S, kry_solver_status *out);   /* synchronises */
+/* Pipelined form of the same read (candidate): `enqueue` queues a copy of the device status
+ * block into pinned host memory (slot 0 or 1) behind everything enqueued so far and returns at
+ * once; `wait` blocks until that copy has landed -- not until later work has finished -- so the
+ * host can keep one chunk of iterations in flight while it replays the history of the previous
+ * one.  kry_solver_history_nowait reads history entries on a separate copy stream for the same
+ * reason (only entries counted by a status that has been waited for are final).             */
+int kry_solver_status_enqueue(kry_solver *S, int slot);
+int kry_solver_status_wait(kry_solver *S, int slot, kry_solver_status *out);
+int kry_solver_history_nowait(kry_solver *S, int64_t first, int64_t count, double *host,
+                              int32_t *width);
 /* Per-iteration scalars recorded on device (residHistory replay, log lines):
  * `width` doubles per entry (CG: residNorm,pAp; others: residNorm).                */
 int kry_solver_history(kry_solver *S, int64_t first, int64_t count, double *host,

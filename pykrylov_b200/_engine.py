@@ -68,17 +68,40 @@ def make_solver(method, plan, context=None):
     return S
 
 
-def drive(S, check_interval, on_chunk=None):
+def drive(S, check_interval, on_chunk=None, overlap=True):
     """Enqueue `check_interval` iterations at a time until the device latches done.
-    One small D2H (status block + new history entries) per chunk."""
+    One small D2H (status block + new history entries) per chunk.
+
+    With ``overlap`` the host keeps one chunk in flight: chunk k+1 is enqueued before the
+    status snapshot of chunk k is waited for and its history replayed, so the GPU never idles
+    while Python works.  The chunk enqueued after the device latched `done` consists of no-op
+    launches.  Callers whose ``on_chunk`` reads device vectors (store_iterates / store_resids)
+    pass ``overlap=False``: they need the state of exactly the chunk they are told about."""
     st = S.status()
     if on_chunk is not None:
         on_chunk(st, S.drain_history(st))
-    while not st.done:
-        S.iterate(check_interval)
-        st = S.status()
+    if st.done:
+        return st
+    if not overlap:
+        while not st.done:
+            S.iterate(check_interval)
+            st = S.status()
+            if on_chunk is not None:
+                on_chunk(st, S.drain_history(st))
+        return st
+    slot = 0
+    S.iterate(check_interval)
+    S.status_enqueue(slot)
+    while True:
+        S.iterate(check_interval)                 # speculative: no-ops once `done` is latched
+        S.status_enqueue(1 - slot)
+        st = S.status_wait(slot)
         if on_chunk is not None:
-            on_chunk(st, S.drain_history(st))
+            on_chunk(st, S.drain_history(st, nowait=True))
+        if st.done:
+            break
+        slot = 1 - slot
+    S.status_wait(1 - slot)                       # drain the speculative chunk before state is read
     return st
 
 

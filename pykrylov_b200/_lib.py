@@ -33,9 +33,11 @@ KRY_ERR_STATE = -7
 KRY_CSR_SYMMETRIC = 1
 KRY_CSR_BUILD_TRANSPOSE = 2
 KRY_SPMV_AUTO, KRY_SPMV_ROW, KRY_SPMV_STREAM, KRY_SPMV_TMA, KRY_SPMV_ROWB8, KRY_SPMV_ROWB4 = 0, 1, 2, 3, 4, 5
+KRY_SPMV_ROWPF, KRY_SPMV_ROWPF2 = 6, 7
 KRY_CG, KRY_BICGSTAB, KRY_CGS, KRY_TFQMR, KRY_MINRES = 1, 2, 3, 4, 5
 KRY_NUM_SLOTS = 64
 KRY_OPT_L2_HINTS, KRY_OPT_GRAPHS, KRY_OPT_P2P, KRY_OPT_CG_FUSE, KRY_OPT_CG_FUSE_SHARDS = 1, 2, 3, 4, 5
+KRY_OPT_CG_ONE_CTA, KRY_OPT_MINRES_FUSE, KRY_OPT_MINRES_PERSISTENT = 6, 7, 8
 KRY_COMM_ID_BYTES = 128
 
 c_i32p = C.POINTER(C.c_int32)
@@ -123,6 +125,9 @@ PROTOTYPES = {
     "kry_solver_iterate": (C.c_int, [handle, C.c_int64]),
     "kry_solver_status_read": (C.c_int, [handle, C.POINTER(SolverStatus)]),
     "kry_solver_history": (C.c_int, [handle, C.c_int64, C.c_int64, C.c_void_p, c_i32p]),
+    "kry_solver_status_enqueue": (C.c_int, [handle, C.c_int]),
+    "kry_solver_status_wait": (C.c_int, [handle, C.c_int, C.POINTER(SolverStatus)]),
+    "kry_solver_history_nowait": (C.c_int, [handle, C.c_int64, C.c_int64, C.c_void_p, c_i32p]),
     "kry_solver_solution": (C.c_int, [handle, C.c_void_p]),
     "kry_solver_get_vector": (C.c_int, [handle, C.c_char_p, C.c_void_p]),
     "kry_solver_set_vector": (C.c_int, [handle, C.c_char_p, C.c_void_p]),

@@ -77,7 +77,7 @@ class CG(KrylovMethod):
                 self.resids.append(r if plan.precon_mode == 0 else
                                    (plan.precon_diag * r if plan.precon_mode == 1 else r / plan.precon_diag))
 
-        st = _engine.drive(S, interval, replay)
+        st = _engine.drive(S, interval, replay, overlap=not (store_resids or store_iterates))
         if not st.definite:
             self.logger.error("Coefficient operator is not positive definite")
             self.infiniteDescent = S.get_vector("p")

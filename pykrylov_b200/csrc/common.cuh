@@ -68,6 +68,7 @@ struct ReduceWs {
 struct kry_ctx {
     int          device;
     cudaStream_t stream;
+    cudaStream_t copy_stream;  // small D2H reads that must not queue behind the compute stream (lazy)
     cudaEvent_t  ev0, ev1;
     int          sm_count;
     int64_t      l2_bytes;
@@ -91,6 +92,9 @@ struct kry_ctx {
     int          use_graphs;   // 1: solver loops replay CUDA graphs of 12 iterations (default)
     int          cg_fuse;      // KRY_OPT_CG_FUSE: CG launch plan (0: 3 launches, 1/2: fused 2-launch forms)
     int          cg_fuse_shards;   // KRY_OPT_CG_FUSE_SHARDS: the plan also applies to row shards
+    int          cg_one_cta;       // KRY_OPT_CG_ONE_CTA: small problems iterate inside one CTA
+    int          minres_fuse;      // KRY_OPT_MINRES_FUSE: 2-launch MINRES plan
+    int          minres_persistent;    // KRY_OPT_MINRES_PERSISTENT: one cooperative kernel per iterate call
     // lifetime: vectors / operators / solvers hold a reference; kry_ctx_destroy releases the
     // device resources at once but the struct itself lives until the last child is destroyed,
     // so handles may be destroyed in any order (interpreter shutdown does exactly that)

@@ -68,6 +68,9 @@ extern "C" int kry_ctx_create(int device, kry_ctx **out)
     c->nranks = 1;
     c->l2_hints = 1;
     c->use_graphs = 1;
+    c->cg_one_cta = 1;
+    c->minres_fuse = 1;
+    c->minres_persistent = 1;
     c->cg_fuse = 2;        // measured on B200, 10^7-row 5-pt Laplacian: 0.222 ms/iteration against 0.233
                            // (form 1) and 0.249 (form 0) -- profiles/r1b_ab_cgfuse*.json, r1_final_bench_n1.json
     c->cg_fuse_shards = 1; // row shards use the same plan: 2 x B200, 10^8 rows: 825.7 vs 803.8 it/s with the same
@@ -144,6 +147,8 @@ extern "C" int kry_ctx_destroy(kry_ctx *c)
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    c->copy_stream = nullptr;
     c->stream = nullptr;
     c->scalars = c->partials = c->sums = nullptr;
     c->counter = nullptr;
@@ -230,10 +235,15 @@ extern "C" int kry_ctx_set_option(kry_ctx *c, int option, int value)
 {
     KRY_REQUIRE(c, KRY_ERR_INVALID, "kry_ctx_set_option: NULL context");
     KRY_REQUIRE(option == KRY_OPT_L2_HINTS || option == KRY_OPT_GRAPHS || option == KRY_OPT_P2P ||
-                    option == KRY_OPT_CG_FUSE || option == KRY_OPT_CG_FUSE_SHARDS,
+                    option == KRY_OPT_CG_FUSE || option == KRY_OPT_CG_FUSE_SHARDS ||
+                    option == KRY_OPT_CG_ONE_CTA || option == KRY_OPT_MINRES_FUSE ||
+                    option == KRY_OPT_MINRES_PERSISTENT,
                 KRY_ERR_INVALID, "kry_ctx_set_option: unknown option %d", option);
     if (option == KRY_OPT_L2_HINTS) c->l2_hints = value;
     else if (option == KRY_OPT_CG_FUSE_SHARDS) c->cg_fuse_shards = value ? 1 : 0;
+    else if (option == KRY_OPT_CG_ONE_CTA) c->cg_one_cta = value ? 1 : 0;
+    else if (option == KRY_OPT_MINRES_FUSE) c->minres_fuse = value ? 1 : 0;
+    else if (option == KRY_OPT_MINRES_PERSISTENT) c->minres_persistent = value ? 1 : 0;
     else if (option == KRY_OPT_CG_FUSE) {
         KRY_REQUIRE(value >= 0 && value <= 2, KRY_ERR_INVALID, "kry_ctx_set_option: CG_FUSE=%d not in 0..2", value);
         c->cg_fuse = value;
@@ -256,6 +266,9 @@ extern "C" int kry_ctx_get_option(kry_ctx *c, int option, int *value)
         case KRY_OPT_P2P: *value = c->p2p_on; break;
         case KRY_OPT_CG_FUSE: *value = c->cg_fuse; break;
         case KRY_OPT_CG_FUSE_SHARDS: *value = c->cg_fuse_shards; break;
+        case KRY_OPT_CG_ONE_CTA: *value = c->cg_one_cta; break;
+        case KRY_OPT_MINRES_FUSE: *value = c->minres_fuse; break;
+        case KRY_OPT_MINRES_PERSISTENT: *value = c->minres_persistent; break;
         default: kry_set_error("kry_ctx_get_option: unknown option %d", option); return KRY_ERR_INVALID;
     }
     return KRY_OK;
@@ -679,7 +692,7 @@ extern "C" int kry_csr_diagonal(const kry_csr *M, double *diag_host)
 extern "C" int kry_csr_set_kernel(kry_csr *M, int kind, int tile_nnz, int threads)
 {
     KRY_REQUIRE(M, KRY_ERR_INVALID, "kry_csr_set_kernel: NULL operator");
-    KRY_REQUIRE(kind >= KRY_SPMV_AUTO && kind <= KRY_SPMV_ROWB4, KRY_ERR_INVALID,
+    KRY_REQUIRE(kind >= KRY_SPMV_AUTO && kind <= KRY_SPMV_ROWPF2, KRY_ERR_INVALID,
                 "kry_csr_set_kernel: unknown kernel %d", kind);
     KRY_REQUIRE(tile_nnz == 0 || (tile_nnz >= 256 && tile_nnz <= 16384 && tile_nnz % 4 == 0),
                 KRY_ERR_INVALID, "kry_csr_set_kernel: tile_nnz %d not in [256,16384] / 4", tile_nnz);

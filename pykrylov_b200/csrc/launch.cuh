@@ -72,21 +72,28 @@ int spmv_launch(kry_csr *M, bool trans, Gather g, Epi epi, Fin fin, const int *d
         smem = (size_t)KRY_TMA_STAGES * cap * 12;
         if (smem > budget) kind = KRY_SPMV_ROW;
     }
-    if (kind == KRY_SPMV_ROW || kind == KRY_SPMV_ROWB8 || kind == KRY_SPMV_ROWB4) {
+    if (kind == KRY_SPMV_ROW || kind == KRY_SPMV_ROWB8 || kind == KRY_SPMV_ROWB4 || kind == KRY_SPMV_ROWPF ||
+        kind == KRY_SPMV_ROWPF2) {
         int64_t need = (m->nrows + 255) / 256;
         if (need < 1) need = 1;
         // one resident wave (8 CTAs x 256 threads per SM) measured best: 6.25 vs 5.5 TB/s with
         // 64 CTAs/SM on the 5-pt Laplacian; `threads`/32 overrides the CTAs per SM for sweeps
         int per_sm = (M->threads >= 64 && M->tile_nnz == 0) ? M->threads / 32 : 8;
-        if (kind == KRY_SPMV_ROW && per_sm == 8) {
+        if ((kind == KRY_SPMV_ROW || kind == KRY_SPMV_ROWPF || kind == KRY_SPMV_ROWPF2) && per_sm == 8) {
             // ... but never more CTAs than are really resident (an epilogue above 32 registers
             // would otherwise leave a second, partial wave)
-            static int occ = 0;              // per instantiation
+            static int occs[3] = {0, 0, 0};               // per instantiation: row, rowpf, rowpf2
+            int &occ = occs[kind == KRY_SPMV_ROW ? 0 : (kind == KRY_SPMV_ROWPF ? 1 : 2)];
             if (occ == 0) {
                 int b = 0;
-                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, spmv_row_kernel<ND, Gather, Epi, Fin>, 256, 0) !=
-                        cudaSuccess || b < 1)
-                    b = 8;
+                cudaError_t qe;
+                if (kind == KRY_SPMV_ROW)
+                    qe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, spmv_row_kernel<ND, Gather, Epi, Fin>, 256, 0);
+                else if (kind == KRY_SPMV_ROWPF)
+                    qe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, spmv_rowpf_kernel<ND, 1, Gather, Epi, Fin>, 256, 0);
+                else
+                    qe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, spmv_rowpf_kernel<ND, 2, Gather, Epi, Fin>, 256, 0);
+                if (qe != cudaSuccess || b < 1) b = 8;
                 occ = b;
             }
             if (occ < per_sm) per_sm = occ;
@@ -119,6 +126,10 @@ int spmv_launch(kry_csr *M, bool trans, Gather g, Epi epi, Fin fin, const int *d
     (void)threads;
     if (kind == KRY_SPMV_ROW)
         emu_launch<ND>(grid, 256, ws, fin, [&] { spmv_row_kernel<ND, Gather, Epi, Fin>(A, g, epi, ws, fin, done); });
+    else if (kind == KRY_SPMV_ROWPF)
+        emu_launch<ND>(grid, 256, ws, fin, [&] { spmv_rowpf_kernel<ND, 1, Gather, Epi, Fin>(A, g, epi, ws, fin, done); });
+    else if (kind == KRY_SPMV_ROWPF2)
+        emu_launch<ND>(grid, 256, ws, fin, [&] { spmv_rowpf_kernel<ND, 2, Gather, Epi, Fin>(A, g, epi, ws, fin, done); });
     else if (kind == KRY_SPMV_ROWB8)
         emu_launch<ND>(grid, 256, ws, fin, [&] { spmv_rowb_kernel<ND, 8, Gather, Epi, Fin>(A, g, epi, ws, fin, done); });
     else
@@ -126,6 +137,10 @@ int spmv_launch(kry_csr *M, bool trans, Gather g, Epi epi, Fin fin, const int *d
 #else
     if (kind == KRY_SPMV_ROW) {
         spmv_row_kernel<ND, Gather, Epi, Fin><<<grid, 256, 0, c->stream>>>(A, g, epi, ws, fin, done);
+    } else if (kind == KRY_SPMV_ROWPF) {
+        spmv_rowpf_kernel<ND, 1, Gather, Epi, Fin><<<grid, 256, 0, c->stream>>>(A, g, epi, ws, fin, done);
+    } else if (kind == KRY_SPMV_ROWPF2) {
+        spmv_rowpf_kernel<ND, 2, Gather, Epi, Fin><<<grid, 256, 0, c->stream>>>(A, g, epi, ws, fin, done);
     } else if (kind == KRY_SPMV_ROWB8) {
         spmv_rowb_kernel<ND, 8, Gather, Epi, Fin><<<grid, 256, 0, c->stream>>>(A, g, epi, ws, fin, done);
     } else if (kind == KRY_SPMV_ROWB4) {

@@ -44,6 +44,10 @@ enum {
     //            2: p was materialised into P[n_iter&1] by a trip that then stopped (curvature exit)
     //   S_XPEND  1: x += alpha * P[(n_iter-1)&1] is pending (form 2)
     S_PSTATE, S_XPEND,
+    // fused MINRES plan (KRY_OPT_MINRES_FUSE): 1 = the w / x update of trip n_iter-1 is still owed
+    M_WPEND,
+    // persistent MINRES kernel: 1 = the reference left the trip before the w / x update (beta < 0)
+    M_STOPNOW,
     S_COUNT
 };
 constexpr int KRY_NSCAL = 64;
@@ -79,6 +83,13 @@ struct kry_solver {
     bool              warm;             // at least one iteration ran un-captured
     int               cg_fuse;          // CG launch plan latched at setup (KRY_OPT_CG_FUSE)
     bool              fresh;            // fused CG: nothing pending, p sits in the next trip's source buffer
+    bool              one_cta;          // CG: the whole loop runs inside one CTA (KRY_OPT_CG_ONE_CTA)
+    int               minres_fuse;      // MINRES launch plan latched at setup (KRY_OPT_MINRES_FUSE)
+    bool              minres_persistent;    // ... or the cooperative persistent kernel (KRY_OPT_MINRES_PERSISTENT)
+    DevScalars       *snap_host[2];     // pinned status snapshots (kry_solver_status_enqueue / _wait)
+    cudaEvent_t       snap_ev[2];
+    bool              snap_pending[2];
+    size_t            one_cta_smem;     // its dynamic shared memory
 };
 
 constexpr int KRY_GRAPH_ITERS = 12;     // multiple of 6 = lcm of the MINRES buffer rotations

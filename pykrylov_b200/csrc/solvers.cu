@@ -15,6 +15,7 @@
 #include "solver.cuh"
 
 static void solver_drop_graph(kry_solver *S);
+static size_t cg_one_cta_bytes(int64_t n, int64_t nnz);
 
 // ======================================================================= CG
 // cg/cg.py:113-158.   3 launches per iteration:
@@ -368,6 +369,10 @@ static int cg_setup(kry_solver *S, int guess)
     double *x = solver_vec(S, "x"), *r = solver_vec(S, "r"), *p = solver_vec(S, "p");
     double *rhs = solver_vec(S, "rhs");
     S->cg_fuse = (S->sharded && !S->ctx->cg_fuse_shards) ? 0 : S->ctx->cg_fuse;
+    S->one_cta_smem = cg_one_cta_bytes(S->n, S->A->A.nnz);
+    S->one_cta = S->ctx->cg_one_cta && !S->sharded && !S->A->halo.active &&
+                 S->one_cta_smem + 2048 <= (size_t)S->ctx->smem_optin;
+    if (S->one_cta) S->cg_fuse = 0;     // its HBM state is that of the 3-launch plan
     S->fresh = true;
     S->rot = 0;
     CgSetupFin fin{S->ds, S->hist, guess};
@@ -428,6 +433,134 @@ static int cg_iterate(kry_solver *S)
     KRY_TRY((solver_pass<1>(S, ub, CgFinRy{S->ds, S->hist, 0}, done)));
     CgDirBody db{p, r, S->ds, 0.0, opt & 1, 0, 0};
     return vec_map_launch(S->ctx, S->n, db, done);
+}
+
+// ---- CG inside one CTA (KRY_OPT_CG_ONE_CTA): problems whose CSR and four vectors fit the
+// shared memory of one SM (BASELINE config 0: 1138bus = 90 kB).  The 3-launch plan spends
+// ~10 us per iteration there on launch and grid-reduction latency; here the whole loop of
+// cg.py:113-158 runs in one launch out of shared memory, the phases separated by
+// __syncthreads() only.  Per element and per row the arithmetic is the reference's (same
+// expressions as the multi-CTA kernels), inner products are summed by a fixed block tree, the
+// scalar recurrence and stopping tests are the same functors (CgFinAp, CgFinRy) run by thread 0
+// on the same device scalar block, so status / history / done behave exactly as before.  State
+// in HBM is that of the 3-launch plan (x current, p materialised in "p").
+constexpr int KRY_ONE_CTA_THREADS = 1024;
+
+__global__ void __launch_bounds__(KRY_ONE_CTA_THREADS, 1)
+cg_one_cta_kernel(CsrView A, double *gx, double *gr, double *gp, double *gAp, const double *pd, int pmode,
+                  DevScalars *s, double *hist, long long n_iters)
+{
+#ifdef KRY_EMULATE
+    unsigned char *smem_raw = emu_dynamic_smem;          // tests/emu: the launcher sized it
+#else
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+#endif
+    __shared__ double s_warp[1][32];
+    __shared__ double sh_scalar;
+    __shared__ int    sh_done;
+    const int n = A.nrows, tid = threadIdx.x, nt = blockDim.x;
+    if (s->done) return;
+    const int nnz = __ldg(A.rowptr + n);
+    // layout: val[nnz] | x[n] | r[n] | p[n] | Ap[n] | rowptr[n+1] | col[nnz]
+    double *val = reinterpret_cast<double *>(smem_raw);
+    double *x = val + nnz, *r = x + n, *p = r + n, *Ap = p + n;
+    int *rowptr = reinterpret_cast<int *>(Ap + n);
+    int *col = rowptr + n + 1;
+    for (int k = tid; k < nnz; k += nt) {
+        val[k] = __ldg(A.val + k);
+        col[k] = __ldg(A.col + k);
+    }
+    for (int i = tid; i <= n; i += nt) rowptr[i] = __ldg(A.rowptr + i);
+    for (int i = tid; i < n; i += nt) {
+        x[i] = gx[i];
+        r[i] = gr[i];
+        p[i] = gp[i];
+        Ap[i] = gAp[i];
+    }
+    __syncthreads();
+
+    for (long long it = 0; it < n_iters; ++it) {
+        // Ap = A p ; pAp = p.Ap ; alpha, curvature test                          cg.py:115-127
+        double acc[1] = {0.0};
+        for (int row = tid; row < n; row += nt) {
+            double sum = 0.0;
+            for (int k = rowptr[row]; k < rowptr[row + 1]; ++k)
+                sum = __dadd_rn(sum, __dmul_rn(val[k], p[col[k]]));
+            Ap[row] = sum;
+            acc[0] = __dadd_rn(acc[0], __dmul_rn(p[row], sum));
+        }
+        block_sum<1>(acc, s_warp);
+        if (tid == 0) {
+            CgFinAp{s}(acc);
+            sh_scalar = s->s[S_ALPHA];
+            sh_done = s->done;
+        }
+        __syncthreads();
+        if (sh_done) break;                     // x is left un-updated (cg.py:119-124)
+        const double alpha = sh_scalar;
+        // x += alpha p ; r += alpha Ap ; y = M r ; ry' = r.y ; beta, residNorm, loop test   cg.py:130-158
+        acc[0] = 0.0;
+        for (int i = tid; i < n; i += nt) {
+            x[i] = __dadd_rn(x[i], __dmul_rn(alpha, p[i]));
+            const double rn = __dadd_rn(r[i], __dmul_rn(alpha, Ap[i]));
+            r[i] = rn;
+            acc[0] = __dadd_rn(acc[0], __dmul_rn(rn, apply_diag(pd, pmode, i, rn)));
+        }
+        __syncthreads();                        // s_warp reuse
+        block_sum<1>(acc, s_warp);
+        if (tid == 0) {
+            CgFinRy{s, hist, 0}(acc);
+            sh_scalar = s->s[S_BETA];
+            sh_done = s->done;
+        }
+        __syncthreads();
+        const double beta = sh_scalar;
+        // p = beta p - r   (the reference updates p before it re-tests the loop condition)   cg.py:150-151
+        for (int i = tid; i < n; i += nt) p[i] = __dsub_rn(__dmul_rn(beta, p[i]), r[i]);
+        __syncthreads();
+        if (sh_done) break;
+    }
+    for (int i = tid; i < n; i += nt) {
+        gx[i] = x[i];
+        gr[i] = r[i];
+        gp[i] = p[i];
+        gAp[i] = Ap[i];
+    }
+}
+
+static size_t cg_one_cta_bytes(int64_t n, int64_t nnz)
+{
+    return (size_t)nnz * 12 + (size_t)n * 32 + (size_t)(n + 1) * 4 + 16;
+}
+
+static int cg_one_cta_iterate(kry_solver *S, int64_t n_iters)
+{
+    kry_ctx *c = S->ctx;
+#ifdef KRY_EMULATE
+    // tests/emu, SIMT mode: one block of fibers plays the CTA
+    KRY_REQUIRE(emu_fibers_on, KRY_ERR_UNSUPPORTED, "cg_one_cta needs the SIMT mode of the emulation");
+    CsrView Ae = csr_view(S->A->A);
+    double *ex = solver_vec(S, "x"), *er = solver_vec(S, "r"), *ep = solver_vec(S, "p"), *eAp = solver_vec(S, "Ap");
+    emu_set_dynamic_smem(S->one_cta_smem);
+    auto body = [&] { cg_one_cta_kernel(Ae, ex, er, ep, eAp, S->dinv, S->precon_mode, S->ds, S->hist, (long long)n_iters); };
+    emu_launch_fibers(1, KRY_ONE_CTA_THREADS, &body, [](const void *k) { (*static_cast<const decltype(body) *>(k))(); });
+    c->launches++;
+    return KRY_OK;
+#else
+    static bool attr_set = false;
+    if (!attr_set) {
+        KRY_CUDA(cudaFuncSetAttribute(cg_one_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(c->smem_optin - 1024)));
+        attr_set = true;
+    }
+    CsrView A = csr_view(S->A->A);
+    cg_one_cta_kernel<<<1, KRY_ONE_CTA_THREADS, S->one_cta_smem, c->stream>>>(
+        A, solver_vec(S, "x"), solver_vec(S, "r"), solver_vec(S, "p"), solver_vec(S, "Ap"), S->dinv,
+        S->precon_mode, S->ds, S->hist, (long long)n_iters);
+    c->launches++;
+    KRY_CUDA(cudaGetLastError());
+    return KRY_OK;
+#endif
 }
 
 // Fused forms only: bring x and p to the state the 3-launch form would hold (see
@@ -1268,10 +1401,14 @@ struct MinBodyR2Pre {         // preconditioned K2: r2' = (-alfa/beta) r2 + y' ;
 struct MinFinQR {
     DevScalars *s;
     double     *hist;
+    int         fuse;        // 2-launch plan: this launch is the last of the trip -> it latches `done`
+                             // itself and records that the w / x update of the trip is still owed
     __device__ void operator()(const double *t) const
     {
         const double eps = 2.220446049250313e-16;
         double *v = s->s;
+        if (fuse == 1) v[M_WPEND] = 0.0; // the body of this launch paid what the previous trip owed
+        if (fuse == 2) v[M_STOPNOW] = 0.0;
         s->n_iter++;
         s->n_matvec++;
         const long long itn = s->n_iter;
@@ -1282,6 +1419,7 @@ struct MinFinQR {
         if (beta < 0) {                                                      // :252-254
             s->istop = 6;
             s->done = 1;
+            if (fuse == 2) v[M_STOPNOW] = 1.0;
             return;
         }
         beta = sqrt(beta);                                                   // :255
@@ -1357,8 +1495,111 @@ struct MinFinQR {
             if (test2 <= s->rtol) s->istop = 2;
             if (test1 <= s->rtol) s->istop = 1;
         }
+        if (fuse == 1) {
+            v[M_WPEND] = 1.0;                                                // minres.py:294-297 of this trip
+            if (s->istop > 0 || itn >= s->matvec_max) s->done = 1;           // :381, :218
+            return;
+        }
+        if (fuse == 2) {             // persistent kernel: every CTA reads `done` right after this barrier, runs
+            if (s->istop > 0 || itn >= s->matvec_max) s->done = 1;   // the w / x update of the trip and leaves
+            return;
+        }
         // `done` is latched by K3 (the x update of this trip must still run)
         if (s->istop > 0 || itn >= s->matvec_max) s->skip_half = 1;          // :381, :218
+    }
+};
+
+// 2-launch plan: K2 of this trip + the w / x update the previous trip still owes.  The owed
+// update uses the previous trip's buffers (y_prev = this trip's r1, the two w buffers swapped)
+// and the scalars its MinFinQR left (this launch's finalize overwrites them only after every
+// CTA has finished its body).
+template <bool PEND>
+struct MinBodyR2W {
+    static constexpr int kMinBlocks = 4;       // 7 vectors in flight: allow 64 registers
+    double       *yn;                          // K2 part (as MinBodyR2, no preconditioner)
+    const double *r2;
+    double       *wnew, *x;                    // owed part (as MinBodyW, previous trip's roles)
+    const double *w2, *yold;
+    DevScalars   *s;
+    double        c, inv, oldeps, delta, denom, phi;
+    __device__ void init()
+    {
+        c = s->s[M_C_R2];
+        inv = s->s[M_INVBETA];
+        oldeps = s->s[M_OLDEPS];
+        delta = s->s[M_DELTA];
+        denom = s->s[M_DENOM];
+        phi = s->s[M_PHI];
+    }
+    __device__ void operator()(int i, double *acc) const
+    {
+        const double yi = __dadd_rn(__dmul_rn(c, r2[i]), yn[i]);             // :246
+        yn[i] = yi;
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(yi, yi));                       // :251
+        if constexpr (PEND) {
+            const double vi = __dmul_rn(inv, yold[i]);                       // :237 of the previous trip
+            double wi = __dsub_rn(vi, __dmul_rn(oldeps, wnew[i]));           // :296
+            wi = __dsub_rn(wi, __dmul_rn(delta, w2[i]));
+            wi = __dmul_rn(wi, denom);
+            wnew[i] = wi;
+            x[i] = __dadd_rn(x[i], __dmul_rn(phi, wi));                      // :297
+        }
+    }
+    static constexpr bool kPair = true;
+    __device__ void pair(int i2, double *acc) const
+    {
+        const double2 rv = ld2(r2, i2);
+        double2 yv = ld2(yn, i2);
+        yv.x = __dadd_rn(__dmul_rn(c, rv.x), yv.x);
+        yv.y = __dadd_rn(__dmul_rn(c, rv.y), yv.y);
+        st2(yn, i2, yv);
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(yv.x, yv.x));
+        acc[0] = __dadd_rn(acc[0], __dmul_rn(yv.y, yv.y));
+        if constexpr (PEND) {
+            const double2 yo = ld2(yold, i2), w1 = ld2(wnew, i2), wv = ld2(w2, i2);
+            double2 xv = ld2(x, i2), wn;
+            wn.x = __dmul_rn(__dsub_rn(__dsub_rn(__dmul_rn(inv, yo.x), __dmul_rn(oldeps, w1.x)), __dmul_rn(delta, wv.x)), denom);
+            wn.y = __dmul_rn(__dsub_rn(__dsub_rn(__dmul_rn(inv, yo.y), __dmul_rn(oldeps, w1.y)), __dmul_rn(delta, wv.y)), denom);
+            st2(wnew, i2, wn);
+            xv.x = __dadd_rn(xv.x, __dmul_rn(phi, wn.x));
+            xv.y = __dadd_rn(xv.y, __dmul_rn(phi, wn.y));
+            st2(x, i2, xv);
+        }
+    }
+};
+
+// Pay the owed w / x update (driven by the device flag and the device trip counter, so it
+// is right whichever launch latched `done`); afterwards the state is that of the 3-launch plan.
+struct MinSettleBody {
+    double     *R[3], *W[2], *x;
+    DevScalars *s;
+    double     *wnew;
+    const double *w2, *yold;
+    double      inv, oldeps, delta, denom, phi;
+    int         pend;
+    __device__ void init()
+    {
+        pend = (s->s[M_WPEND] != 0.0);
+        const long long t = s->n_iter - 1;              // the trip whose update is owed
+        const int k = (int)(((t % 3) + 3) % 3), j = (int)(((t % 2) + 2) % 2);
+        yold = R[k];
+        wnew = W[1 - j];
+        w2 = W[j];
+        inv = s->s[M_INVBETA];
+        oldeps = s->s[M_OLDEPS];
+        delta = s->s[M_DELTA];
+        denom = s->s[M_DENOM];
+        phi = s->s[M_PHI];
+    }
+    __device__ void operator()(int i) const
+    {
+        if (!pend) return;
+        const double vi = __dmul_rn(inv, yold[i]);
+        double wi = __dsub_rn(vi, __dmul_rn(oldeps, wnew[i]));
+        wi = __dsub_rn(wi, __dmul_rn(delta, w2[i]));
+        wi = __dmul_rn(wi, denom);
+        wnew[i] = wi;
+        x[i] = __dadd_rn(x[i], __dmul_rn(phi, wi));
     }
 };
 
@@ -1474,6 +1715,14 @@ static int minres_setup(kry_solver *S, int)
     KRY_CUDA(cudaMemsetAsync(solver_vec(S, "wa"), 0, bytes, S->ctx->stream));   // :206-207
     KRY_CUDA(cudaMemsetAsync(solver_vec(S, "wb"), 0, bytes, S->ctx->stream));
     S->rot = 0;
+    S->minres_fuse = S->ctx->minres_fuse;
+    S->minres_persistent = S->ctx->minres_persistent && !S->sharded && !S->A->halo.active && !S->precon_mode &&
+                           (S->A->kind == KRY_SPMV_AUTO || S->A->kind == KRY_SPMV_ROW) && S->A->A.max_row <= 64;
+#ifdef KRY_EMULATE
+    if (!emu_fibers_on) S->minres_persistent = false;          // the host emulation plays it in SIMT mode only
+#endif
+    if (S->minres_persistent) S->minres_fuse = 0;                // its HBM state is that of the 3-launch plan
+    S->fresh = true;
     return KRY_OK;
 }
 
@@ -1505,11 +1754,181 @@ static int minres_iterate(kry_solver *S)
     MinGather g{r2, S->ds, 0.0};
     MinEpiY e{rn, r2, r1, S->ds, 0, 0, 0, 0};
     KRY_TRY((solver_spmv<1>(S, g, e, MinFinAlfa{S->ds}, done, r2)));
+    if (S->minres_fuse) {
+        // 2 launches: the w / x update of the PREVIOUS trip rides in this trip's second launch.
+        // Previous trip (rot-1): y_prev = R[(k+2)%3] = r1, it wrote W[1-j_prev] = W[j] from w2 = W[1-j].
+        MinFinQR fin{S->ds, S->hist, 1};
+        if (S->fresh) {
+            MinBodyR2W<false> b{rn, r2, nullptr, x, nullptr, nullptr, S->ds, 0, 0, 0, 0, 0, 0};
+            KRY_TRY((solver_pass<1>(S, b, fin, done)));
+        } else {
+            MinBodyR2W<true> b{rn, r2, W[j], x, W[1 - j], r1, S->ds, 0, 0, 0, 0, 0, 0};
+            KRY_TRY((solver_pass<1>(S, b, fin, done)));
+        }
+        S->fresh = false;
+        S->rot++;
+        return KRY_OK;
+    }
     MinBodyR2 b2{rn, nullptr, r2, S->dinv, 0, S->ds, 0.0};
-    KRY_TRY((solver_pass<1>(S, b2, MinFinQR{S->ds, S->hist}, done)));
+    KRY_TRY((solver_pass<1>(S, b2, MinFinQR{S->ds, S->hist, 0}, done)));
     MinBodyW bw{W[1 - j], x, W[j], r2, S->ds, 0, 0, 0, 0, 0};
     KRY_TRY((solver_pass<1>(S, bw, MinFinW{S->ds}, done)));
     S->rot++;
+    return KRY_OK;
+}
+
+// ---- MINRES as one cooperative persistent kernel (KRY_OPT_MINRES_PERSISTENT).  At N = 10^6
+// (BASELINE config 2) a trip moves ~180 MB, i.e. ~30 us of HBM time, and three dependent launches
+// cost about as much again in launch gaps, ramp-up, tails and last-CTA finalisation.  Here one
+// CTA wave stays resident for the whole kry_solver_iterate call; the three phases of a trip are
+// the same loops and functors as the three kernels (MinGather/MinEpiY, MinBodyR2, MinBodyW), and
+// the two reductions ride in grid-wide barriers: the CTA that arrives last sums the partials in
+// index order, runs the scalar step (MinFinAlfa / MinFinQR) and releases the others.  Nothing
+// __shared__ is live across such a barrier.  Phase 3 needs no barrier before the next trip's
+// phase 1 (disjoint buffers; the next barrier orders everything else).
+template <int ND, class Fin>
+__device__ __forceinline__ void grid_reduce_sync(double (&acc)[ND], const ReduceWs &ws, Fin &fin,
+                                                 unsigned *gen_ptr, unsigned &my_gen)
+{
+    __shared__ double s_warp[ND][32];
+    __shared__ int    s_last;
+    block_sum<ND>(acc, s_warp);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int d = 0; d < ND; ++d) ws.partials[(size_t)d * ws.stride + blockIdx.x] = acc[d];
+        __threadfence();
+        const unsigned ticket = atomicAdd(ws.counter, 1u);
+        s_last = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        double tot[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            double a = 0.0;
+            const volatile double *p = ws.partials + (size_t)d * ws.stride;
+            for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) a = __dadd_rn(a, p[i]);
+            tot[d] = a;
+        }
+        __syncthreads();            // s_warp reuse
+        block_sum<ND>(tot, s_warp);
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int d = 0; d < ND; ++d) ws.sums[d] = tot[d];
+            *ws.counter = 0u;
+            fin(tot);
+            __threadfence();
+            atomicAdd(gen_ptr, 1u);                               // release
+        }
+    } else if (threadIdx.x == 0) {
+        while (*reinterpret_cast<volatile unsigned *>(gen_ptr) == my_gen) __nanosleep(20);
+        __threadfence();
+    }
+    my_gen++;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256, 4)
+minres_persistent_kernel(CsrView A, double *Ra, double *Rb, double *Rc, double *Wa, double *Wb, double *x,
+                         DevScalars *s, double *hist, ReduceWs ws, unsigned *gen_ptr, long long n_iters)
+{
+    if (s->done) return;
+    unsigned my_gen = *reinterpret_cast<volatile unsigned *>(gen_ptr);
+    long long rot = s->n_iter;                       // trips done so far: fixes the buffer rotation
+    double *R[3] = {Ra, Rb, Rc}, *W[2] = {Wa, Wb};
+    const int stride = (int)(gridDim.x * blockDim.x), t0 = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    const int nn = A.nrows, half = nn >> 1;
+    for (long long it = 0; it < n_iters; ++it, ++rot) {
+        const int k = (int)(rot % 3), j = (int)(rot % 2);
+        double *r2 = R[k], *r1 = R[(k + 2) % 3], *rn = R[(k + 1) % 3];
+        // phase 1: y' = A v - shift v - (beta/oldb) r1 with v = y/beta ; alfa = v.y'      (K1)
+        double acc[1] = {0.0};
+        {
+            MinGather g{r2, s, 0.0};
+            MinEpiY   e{rn, r2, r1, s, 0, 0, 0, 0};
+            g.init();
+            e.init();
+            for (int row = t0; row < nn; row += stride) {
+                const int rs = __ldg(A.rowptr + row), re = __ldg(A.rowptr + row + 1);
+                double sum = 0.0;
+                for (int q = rs; q < re; ++q)
+                    sum = __dadd_rn(sum, __dmul_rn(__ldg(A.val + q), g(__ldg(A.col + q))));
+                e(row, sum, acc);
+            }
+            MinFinAlfa f{s};
+            grid_reduce_sync<1>(acc, ws, f, gen_ptr, my_gen);
+        }
+        // phase 2: r2' = (-alfa/beta) r2 + y' ; beta'^2 = r2'.r2' ; QR step, norms, stopping tests   (K2)
+        {
+            MinBodyR2 b{rn, nullptr, r2, nullptr, 0, s, 0.0};
+            b.init();
+            acc[0] = 0.0;
+            for (int i = t0; i < half; i += stride) b.pair(i, acc);
+            if ((nn & 1) && t0 == 0) b(nn - 1, acc);
+            MinFinQR f{s, hist, 2};
+            grid_reduce_sync<1>(acc, ws, f, gen_ptr, my_gen);
+        }
+        // both written by the last CTA before it released the barrier, by nobody afterwards: uniform
+        const int stop = s->done;
+        if (stop && s->s[M_STOPNOW] != 0.0) break;     // beta < 0: the reference leaves before the w update
+        // phase 3: w = (v - oldeps w1 - delta w2)/gamma ; x += phi w                      (K3)
+        {
+            MinBodyW b{W[1 - j], x, W[j], r2, s, 0, 0, 0, 0, 0};
+            b.init();
+            for (int i = t0; i < half; i += stride) b.pair(i, nullptr);
+            if ((nn & 1) && t0 == 0) b(nn - 1, nullptr);
+        }
+        if (stop) break;
+    }
+}
+
+static int minres_persistent_iterate(kry_solver *S, int64_t n_iters)
+{
+    kry_ctx *c = S->ctx;
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        int b = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, minres_persistent_kernel, 256, 0) != cudaSuccess || b < 1) b = 1;
+        per_sm = b;
+    }
+    int64_t need = (S->n + 255) / 256;
+    if (need < 1) need = 1;
+    const int64_t cap = (int64_t)c->sm_count * per_sm;             // one resident wave: co-residency is required
+    const int grid = (int)(need < cap ? need : cap);
+    KRY_TRY(kry_ctx_ensure_partials(c, grid));
+    ReduceWs ws = kry_ws(c);
+    CsrView A = csr_view(S->A->A);
+    double *Ra = solver_vec(S, "ra"), *Rb = solver_vec(S, "rb"), *Rc = solver_vec(S, "rc");
+    double *Wa = solver_vec(S, "wa"), *Wb = solver_vec(S, "wb"), *x = solver_vec(S, "x");
+    DevScalars *ds = S->ds;
+    double *hist = S->hist;
+    unsigned *gen_ptr = c->counter + 16;                           // inside the zeroed 256-byte counter block
+    long long n = (long long)n_iters;
+#ifdef KRY_EMULATE
+    KRY_REQUIRE(emu_fibers_on, KRY_ERR_UNSUPPORTED, "minres_persistent needs the SIMT mode of the emulation");
+    auto body = [&] { minres_persistent_kernel(A, Ra, Rb, Rc, Wa, Wb, x, ds, hist, ws, gen_ptr, n); };
+    emu_launch_fibers_mode(grid, 256, &body, [](const void *k) { (*static_cast<const decltype(body) *>(k))(); }, 1);
+#else
+    void *args[] = {&A, &Ra, &Rb, &Rc, &Wa, &Wb, &x, &ds, &hist, &ws, &gen_ptr, &n};
+    KRY_CUDA(cudaLaunchCooperativeKernel((const void *)minres_persistent_kernel, dim3(grid), dim3(256), args, 0, c->stream));
+#endif
+    c->launches++;
+    S->rot += n_iters;
+    KRY_CUDA(cudaGetLastError());
+    return KRY_OK;
+}
+
+static int minres_settle(kry_solver *S)
+{
+    if (S->method != KRY_MINRES || !S->minres_fuse || !S->ready) return KRY_OK;
+    MinSettleBody b{{solver_vec(S, "ra"), solver_vec(S, "rb"), solver_vec(S, "rc")},
+                    {solver_vec(S, "wa"), solver_vec(S, "wb")}, solver_vec(S, "x"), S->ds,
+                    nullptr, nullptr, nullptr, 0, 0, 0, 0, 0, 0};
+    KRY_TRY(vec_map_launch(S->ctx, S->n, b, &S->ctx->never_done[0]));
+    KRY_CUDA(cudaMemsetAsync(&S->ds->s[M_WPEND], 0, sizeof(double), S->ctx->stream));
+    S->fresh = true;
+    S->warm = false;      // the next trip must run un-captured (PEND = false variant)
     return KRY_OK;
 }
 
@@ -1602,6 +2021,12 @@ extern "C" int kry_solver_destroy(kry_solver *S)
     if (!S) return KRY_OK;
     if (!S->ctx->closed) cudaStreamSynchronize(S->ctx->stream);
     solver_drop_graph(S);
+    for (int k = 0; k < 2; ++k) {
+        if (S->snap_host[k]) {
+            cudaEventDestroy(S->snap_ev[k]);
+            cudaFreeHost(S->snap_host[k]);
+        }
+    }
     cudaFree(S->slab);
     cudaFree(S->ds);
     cudaFree(S->hist);
@@ -1633,6 +2058,7 @@ static int solver_setup_common(kry_solver *S, int guess, const kry_solver_params
                 "kry_solver_setup: MINRES window %d not in [1,16]", p->window);
     solver_drop_graph(S);
     S->warm = false;
+    S->snap_pending[0] = S->snap_pending[1] = false;
     S->params = *p;
     DevScalars h;
     memset(&h, 0, sizeof(h));
@@ -1752,6 +2178,9 @@ extern "C" int kry_solver_iterate(kry_solver *S, int64_t n_iters)
                 "kry_solver_iterate: n_iters=%lld not in [0,%d)", (long long)n_iters, KRY_HIST_CAP / 2);
     kry_ctx *c = S->ctx;
     KRY_CUDA(cudaSetDevice(c->device));
+    if (S->method == KRY_CG && S->one_cta) return n_iters > 0 ? cg_one_cta_iterate(S, n_iters) : KRY_OK;
+    if (S->method == KRY_MINRES && S->minres_persistent)
+        return n_iters > 0 ? minres_persistent_iterate(S, n_iters) : KRY_OK;
     int64_t left = n_iters;
     // Graph replay: not on sharded runs (NCCL in the sequence), not while per-launch
     // profiling events are being recorded, and only once the sequence ran un-captured
@@ -1778,6 +2207,8 @@ extern "C" int kry_solver_iterate(kry_solver *S, int64_t n_iters)
     return KRY_OK;
 }
 
+static void status_decode(const kry_solver *S, const DevScalars &h, kry_solver_status *out);
+
 extern "C" int kry_solver_status_read(kry_solver *S, kry_solver_status *out)
 {
     KRY_REQUIRE(S && out, KRY_ERR_INVALID, "kry_solver_status_read: NULL argument");
@@ -1786,6 +2217,39 @@ extern "C" int kry_solver_status_read(kry_solver *S, kry_solver_status *out)
     KRY_CUDA(cudaMemcpyAsync(&h, S->ds, sizeof(h), cudaMemcpyDeviceToHost, S->ctx->stream));
     KRY_CUDA(cudaStreamSynchronize(S->ctx->stream));
     KRY_CUDA(cudaGetLastError());
+    status_decode(S, h, out);
+    return KRY_OK;
+}
+
+extern "C" int kry_solver_status_enqueue(kry_solver *S, int slot)
+{
+    KRY_REQUIRE(S && (slot == 0 || slot == 1), KRY_ERR_INVALID, "kry_solver_status_enqueue: bad argument");
+    KRY_CTX_LIVE(S->ctx, "kry_solver_status_enqueue");
+    KRY_REQUIRE(S->ready, KRY_ERR_STATE, "kry_solver_status_enqueue: call kry_solver_setup first");
+    if (!S->snap_host[slot]) {
+        KRY_CUDA(cudaMallocHost((void **)&S->snap_host[slot], sizeof(DevScalars)));
+        KRY_CUDA(cudaEventCreateWithFlags(&S->snap_ev[slot], cudaEventDisableTiming));
+    }
+    KRY_CUDA(cudaMemcpyAsync(S->snap_host[slot], S->ds, sizeof(DevScalars), cudaMemcpyDeviceToHost,
+                             S->ctx->stream));
+    KRY_CUDA(cudaEventRecord(S->snap_ev[slot], S->ctx->stream));
+    S->snap_pending[slot] = true;
+    return KRY_OK;
+}
+
+extern "C" int kry_solver_status_wait(kry_solver *S, int slot, kry_solver_status *out)
+{
+    KRY_REQUIRE(S && out && (slot == 0 || slot == 1), KRY_ERR_INVALID, "kry_solver_status_wait: bad argument");
+    KRY_CTX_LIVE(S->ctx, "kry_solver_status_wait");
+    KRY_REQUIRE(S->snap_pending[slot], KRY_ERR_STATE, "kry_solver_status_wait: nothing enqueued in slot %d", slot);
+    KRY_CUDA(cudaEventSynchronize(S->snap_ev[slot]));
+    S->snap_pending[slot] = false;
+    status_decode(S, *S->snap_host[slot], out);
+    return KRY_OK;
+}
+
+static void status_decode(const kry_solver *S, const DevScalars &h, kry_solver_status *out)
+{
     memset(out, 0, sizeof(*out));
     out->done = h.done;
     out->definite = h.definite;
@@ -1838,18 +2302,35 @@ extern "C" int kry_solver_status_read(kry_solver *S, kry_solver_status *out)
             out->aux[7] = h.s[S_RHO_NEXT];
             break;
     }
-    return KRY_OK;
 }
+
+static int solver_history_on(kry_solver *S, cudaStream_t st, int64_t first, int64_t count, double *host,
+                             int32_t *width);
 
 extern "C" int kry_solver_history(kry_solver *S, int64_t first, int64_t count, double *host,
                                   int32_t *width)
 {
     KRY_REQUIRE(S && (host || count == 0), KRY_ERR_INVALID, "kry_solver_history: NULL argument");
     KRY_CTX_LIVE(S->ctx, "kry_solver_history");
+    return solver_history_on(S, S->ctx->stream, first, count, host, width);
+}
+
+extern "C" int kry_solver_history_nowait(kry_solver *S, int64_t first, int64_t count, double *host,
+                                         int32_t *width)
+{
+    KRY_REQUIRE(S && (host || count == 0), KRY_ERR_INVALID, "kry_solver_history_nowait: NULL argument");
+    KRY_CTX_LIVE(S->ctx, "kry_solver_history_nowait");
+    kry_ctx *c = S->ctx;
+    if (!c->copy_stream) KRY_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    return solver_history_on(S, c->copy_stream, first, count, host, width);
+}
+
+static int solver_history_on(kry_solver *S, cudaStream_t st, int64_t first, int64_t count, double *host,
+                             int32_t *width)
+{
     if (width) *width = S->hist_width;
     KRY_REQUIRE(first >= 0 && count >= 0 && count <= KRY_HIST_CAP, KRY_ERR_INVALID,
                 "kry_solver_history: range [%lld,+%lld) invalid", (long long)first, (long long)count);
-    cudaStream_t st = S->ctx->stream;
     const int w = S->hist_width;
     int64_t done = 0;
     while (done < count) {      // the ring may wrap
@@ -1869,6 +2350,7 @@ extern "C" int kry_solver_solution(kry_solver *S, double *x_host)
     KRY_REQUIRE(S && x_host, KRY_ERR_INVALID, "kry_solver_solution: NULL argument");
     KRY_CTX_LIVE(S->ctx, "kry_solver_solution");
     KRY_TRY(cg_settle(S));
+    KRY_TRY(minres_settle(S));
     KRY_CUDA(cudaMemcpyAsync(x_host, solver_vec(S, "x"), (size_t)S->n * sizeof(double),
                              cudaMemcpyDeviceToHost, S->ctx->stream));
     KRY_CUDA(cudaStreamSynchronize(S->ctx->stream));
@@ -1906,6 +2388,7 @@ extern "C" int kry_solver_get_vector(kry_solver *S, const char *name, double *ho
     KRY_REQUIRE(S && name && host, KRY_ERR_INVALID, "kry_solver_get_vector: NULL argument");
     KRY_CTX_LIVE(S->ctx, "kry_solver_get_vector");
     KRY_TRY(cg_settle(S));
+    KRY_TRY(minres_settle(S));
     double *d = solver_vec_logical(S, name);
     KRY_REQUIRE(d, KRY_ERR_INVALID, "kry_solver_get_vector: no vector named '%s'", name);
     KRY_CUDA(cudaMemcpyAsync(host, d, (size_t)S->n * sizeof(double), cudaMemcpyDeviceToHost,
@@ -1919,6 +2402,7 @@ extern "C" int kry_solver_set_vector(kry_solver *S, const char *name, const doub
     KRY_REQUIRE(S && name && host, KRY_ERR_INVALID, "kry_solver_set_vector: NULL argument");
     KRY_CTX_LIVE(S->ctx, "kry_solver_set_vector");
     KRY_TRY(cg_settle(S));
+    KRY_TRY(minres_settle(S));
     double *d = solver_vec_logical(S, name);
     KRY_REQUIRE(d, KRY_ERR_INVALID, "kry_solver_set_vector: no vector named '%s'", name);
     KRY_CUDA(cudaMemcpyAsync(d, host, (size_t)S->n * sizeof(double), cudaMemcpyHostToDevice,

@@ -103,6 +103,79 @@ spmv_row_kernel(CsrView A, Gather g, Epi epi, ReduceWs ws, Fin fin, const int *d
     if constexpr (ND > 0) block_reduce_finalize<ND>(acc, ws, fin);
 }
 
+// ------------------------------------- thread per row, software-pipelined
+// Same mapping and summation order as spmv_row_kernel.  A warp-trip of that kernel is a chain
+// of three dependent memory latencies (rowptr -> col/val -> gathers); here the row pointers
+// are loaded two trips ahead (registers) and, one trip ahead, every lane asks L2 for the line
+// that holds the start of its next row (prefetch.global.L2: no register, no dependency), so
+// the next trip finds rowptr in a register and col/val in L2.
+__device__ __forceinline__ void prefetch_l2(const void *p)
+{
+#ifndef KRY_EMULATE
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
+template <int ND, int DEPTH, class Gather, class Epi, class Fin>
+__global__ void __launch_bounds__(256, epi_min_blocks<Epi>::value)
+spmv_rowpf_kernel(CsrView A, Gather g, Epi epi, ReduceWs ws, Fin fin, const int *done)
+{
+    static_assert(DEPTH == 1 || DEPTH == 2, "row pointers one or two trips ahead");
+    if (*done) return;
+    g.init();
+    epi.init();
+    double acc[ND > 0 ? ND : 1];
+#pragma unroll
+    for (int d = 0; d < (ND > 0 ? ND : 1); ++d) acc[d] = 0.0;
+    const int stride = gridDim.x * blockDim.x;      // < 2^20, rows < 2^31 - 2^20: no overflow below
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    int s = 0, e = 0, s1 = 0, e1 = 0;
+    if (row < A.nrows) {
+        s = __ldg(A.rowptr + row);
+        e = __ldg(A.rowptr + row + 1);
+    }
+    if constexpr (DEPTH == 2) {
+        if (row + stride < A.nrows) {
+            s1 = __ldg(A.rowptr + row + stride);
+            e1 = __ldg(A.rowptr + row + stride + 1);
+        }
+    }
+    while (row < A.nrows) {
+        int s2 = 0, e2 = 0;
+        if constexpr (DEPTH == 2) {
+            // trip t+1: its CSR window towards L2 now; trip t+2: its row pointers into registers
+            if (row + stride < A.nrows) {
+                prefetch_l2(A.val + s1);
+                prefetch_l2(A.col + s1);
+                if (row + 2 * stride < A.nrows) {
+                    s2 = __ldg(A.rowptr + row + 2 * stride);
+                    e2 = __ldg(A.rowptr + row + 2 * stride + 1);
+                }
+            }
+        } else {
+            // trip t+1: its row pointers into registers while this trip's loads are in flight
+            if (row + stride < A.nrows) {
+                s1 = __ldg(A.rowptr + row + stride);
+                e1 = __ldg(A.rowptr + row + stride + 1);
+            }
+        }
+        double sum = 0.0;
+        for (int k = s; k < e; ++k)
+            sum = __dadd_rn(sum, __dmul_rn(__ldg(A.val + k), g(__ldg(A.col + k))));
+        epi(row, sum, acc);
+        row += stride;
+        s = s1;
+        e = e1;
+        if constexpr (DEPTH == 2) {
+            s1 = s2;
+            e1 = e2;
+        }
+    }
+    if constexpr (ND > 0) block_reduce_finalize<ND>(acc, ws, fin);
+}
+
 // -------------------------------------------- thread per row, batched loads
 // Same mapping as spmv_row_kernel, but the loads of a row are issued in three
 // waves of independent requests -- all (col,val) pairs of a CHUNK, then all x

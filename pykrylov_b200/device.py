@@ -530,16 +530,29 @@ class DeviceSolver(object):
         call("kry_solver_status_read", self._h, C.byref(s))
         return s
 
-    def drain_history(self, status=None):
-        """New per-iteration entries since the last drain, shape (k, width)."""
+    def status_enqueue(self, slot):
+        """Queue a status snapshot behind everything enqueued so far (returns at once)."""
+        call("kry_solver_status_enqueue", self._h, int(slot))
+
+    def status_wait(self, slot):
+        """Block until snapshot `slot` has landed -- not until later work has finished."""
+        s = L.SolverStatus()
+        call("kry_solver_status_wait", self._h, int(slot), C.byref(s))
+        return s
+
+    def drain_history(self, status=None, nowait=False):
+        """New per-iteration entries since the last drain, shape (k, width).  With
+        ``nowait`` the copy runs on the side stream (entries counted by a snapshot that has
+        been waited for are final even while later iterations are still running)."""
         s = status if status is not None else self.status()
         count = s.hist_count - self._hist_read
         width = C.c_int32(0)
+        fn = "kry_solver_history_nowait" if nowait else "kry_solver_history"
         if count <= 0:
-            call("kry_solver_history", self._h, 0, 0, None, C.byref(width))
+            call(fn, self._h, 0, 0, None, C.byref(width))
             return np.empty((0, width.value))
         buf = np.empty((count, 2), dtype=np.float64)
-        call("kry_solver_history", self._h, self._hist_read, count, _ptr(buf), C.byref(width))
+        call(fn, self._h, self._hist_read, count, _ptr(buf), C.byref(width))
         self._hist_read = s.hist_count
         return buf.reshape(-1)[:count * width.value].reshape(count, width.value)
 

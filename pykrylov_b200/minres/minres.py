@@ -97,7 +97,7 @@ class Minres(KrylovMethod):
                 self.iterates.append(S.solution())
 
         interval = 1 if store_iterates else self.check_interval
-        st = _engine.drive(S, interval, replay)
+        st = _engine.drive(S, interval, replay, overlap=not store_iterates)
         istop = int(st.istop)
         if not symmetric_ok:
             istop = 7

@@ -19,7 +19,8 @@ rhs = DeviceVector(ctx, n)
 A.spmv(x, rhs)
 out = {}
 variants = []
-for kind, name in ((L.KRY_SPMV_ROW, "row"), (L.KRY_SPMV_ROWB8, "rowb8"), (L.KRY_SPMV_ROWB4, "rowb4")):
+for kind, name in ((L.KRY_SPMV_ROW, "row"), (L.KRY_SPMV_ROWPF, "rowpf"), (L.KRY_SPMV_ROWPF2, "rowpf2"),
+                   (L.KRY_SPMV_ROWB8, "rowb8"), (L.KRY_SPMV_ROWB4, "rowb4")):
     for bps in (8, 16, 32, 64):
         variants.append((kind, 0, bps * 32 if bps < 64 else 0, "%s/bps%d" % (name, bps)))
 variants += [(L.KRY_SPMV_STREAM, 4096, 512, "stream/t4096/b512"), (L.KRY_SPMV_TMA, 2048, 512, "tma/t2048/b512")]

@@ -33,7 +33,7 @@ namespace {
 constexpr size_t kFiberStack = 128 * 1024;
 struct Fiber {
     ucontext_t uc;
-    int        tid;
+    int        tid, blk;
     bool       done;
 };
 struct Block {
@@ -43,38 +43,42 @@ struct Block {
     unsigned wgen[32];
 };
 // one set per host thread: the ranks of an emulated multi-GPU run are threads of this process
-thread_local Block              g_blk;
+thread_local std::vector<Block> g_blks;
 thread_local std::vector<Fiber> g_fibers;
 thread_local std::vector<char>  g_stacks;
 thread_local ucontext_t         g_sched;
 thread_local Fiber             *g_cur = nullptr;
 thread_local const void        *g_closure = nullptr;
 thread_local void (*g_invoke)(const void *) = nullptr;
+thread_local bool               g_grid_wait = false;
 
-void release_if_complete()
+Block &cur_block() { return g_blks[(size_t)g_cur->blk]; }
+
+void release_if_complete(Block &b)
 {
-    if (g_blk.live > 0 && g_blk.arrived == g_blk.live) {
-        g_blk.arrived = 0;
-        g_blk.gen++;
+    if (b.live > 0 && b.arrived == b.live) {
+        b.arrived = 0;
+        b.gen++;
     }
 }
-void warp_release_if_complete(int w)
+void warp_release_if_complete(Block &b, int w)
 {
-    if (g_blk.wlive[w] > 0 && g_blk.warrived[w] == g_blk.wlive[w]) {
-        g_blk.warrived[w] = 0;
-        g_blk.wgen[w]++;
+    if (b.wlive[w] > 0 && b.warrived[w] == b.wlive[w]) {
+        b.warrived[w] = 0;
+        b.wgen[w]++;
     }
 }
 void fiber_main()
 {
     g_invoke(g_closure);
     Fiber *me = g_cur;
+    Block &b = g_blks[(size_t)me->blk];
     me->done = true;
-    g_blk.live--;
-    release_if_complete();
+    b.live--;
+    release_if_complete(b);
     const int w = me->tid >> 5;
-    g_blk.wlive[w]--;
-    warp_release_if_complete(w);
+    b.wlive[w]--;
+    warp_release_if_complete(b, w);
     // returning resumes uc_link = the scheduler
 }
 }  // namespace
@@ -85,16 +89,25 @@ void emu_yield()
     swapcontext(&g_cur->uc, &g_sched);
 }
 
+// a thread that spins on memory another block (or another rank) will write: tell the scheduler of
+// a cooperative launch that this block cannot advance, so that it runs the other blocks
+void emu_spin_wait()
+{
+    g_grid_wait = true;
+    emu_yield();
+}
+
 void emu_block_barrier()
 {
     if (!g_cur) {
         fprintf(stderr, "emulation: __syncthreads() reached outside the SIMT mode (kry_emu_set_fibers)\n");
         abort();
     }
-    const unsigned gen = g_blk.gen;
-    g_blk.arrived++;
-    release_if_complete();
-    while (g_blk.gen == gen) emu_yield();
+    Block &b = cur_block();
+    const unsigned gen = b.gen;
+    b.arrived++;
+    release_if_complete(b);
+    while (b.gen == gen) emu_yield();
 }
 
 void emu_warp_barrier(int w)
@@ -103,48 +116,87 @@ void emu_warp_barrier(int w)
         fprintf(stderr, "emulation: warp-level synchronisation reached outside the SIMT mode\n");
         abort();
     }
-    const unsigned gen = g_blk.wgen[w];
-    g_blk.warrived[w]++;
-    warp_release_if_complete(w);
-    while (g_blk.wgen[w] == gen) emu_yield();
+    Block &b = cur_block();
+    const unsigned gen = b.wgen[w];
+    b.warrived[w]++;
+    warp_release_if_complete(b, w);
+    while (b.wgen[w] == gen) emu_yield();
 }
 
-void emu_launch_fibers(int grid, int block, const void *closure, void (*invoke)(const void *))
+// cooperative = 0: the blocks run one after the other.  cooperative = 1 (cudaLaunchCooperativeKernel):
+// all blocks are alive at once; a block runs until all its threads have returned or it waits for
+// the other blocks (emu_spin_wait), then the next block runs.  __shared__ variables are static,
+// i.e. one copy per host thread: that is safe as long as no __shared__ value is live across a
+// grid-wide wait, which holds for the kernels of this library.
+void emu_launch_fibers_mode(int grid, int block, const void *closure, void (*invoke)(const void *), int cooperative)
 {
-    if ((int)g_fibers.size() < block) g_fibers.resize((size_t)block);
-    if (g_stacks.size() < (size_t)block * kFiberStack) g_stacks.resize((size_t)block * kFiberStack);
+    const int wave = cooperative ? grid : 1;
+    const size_t nf = (size_t)wave * block;
+    if (g_fibers.size() < nf) g_fibers.resize(nf);
+    if (g_stacks.size() < nf * kFiberStack) g_stacks.resize(nf * kFiberStack);
+    if ((int)g_blks.size() < grid) g_blks.resize((size_t)grid);
     g_closure = closure;
     g_invoke = invoke;
     gridDim = EmuDim{(unsigned)grid, 1, 1};
     blockDim = EmuDim{(unsigned)block, 1, 1};
-    for (int b = 0; b < grid; ++b) {
-        blockIdx = EmuDim{(unsigned)b, 0, 0};
-        memset(&g_blk, 0, sizeof(g_blk));
-        g_blk.live = block;
-        for (int t = 0; t < block; ++t) g_blk.wlive[t >> 5]++;
-        for (int t = 0; t < block; ++t) {
-            Fiber &f = g_fibers[(size_t)t];
-            f.tid = t;
-            f.done = false;
-            getcontext(&f.uc);
-            f.uc.uc_stack.ss_sp = g_stacks.data() + (size_t)t * kFiberStack;
-            f.uc.uc_stack.ss_size = kFiberStack;
-            f.uc.uc_link = &g_sched;
-            makecontext(&f.uc, fiber_main, 0);
-        }
-        int remaining = block;
-        while (remaining > 0) {
+    for (int b0 = 0; b0 < grid; b0 += wave) {
+        for (int bb = 0; bb < wave; ++bb) {
+            Block &B = g_blks[(size_t)(b0 + bb)];
+            memset(&B, 0, sizeof(B));
+            B.live = block;
+            for (int t = 0; t < block; ++t) B.wlive[t >> 5]++;
             for (int t = 0; t < block; ++t) {
-                Fiber &f = g_fibers[(size_t)t];
-                if (f.done) continue;
-                g_cur = &f;
-                threadIdx = EmuDim{(unsigned)t, 0, 0};
-                swapcontext(&g_sched, &f.uc);
-                if (f.done) remaining--;
+                Fiber &f = g_fibers[(size_t)bb * block + t];
+                f.tid = t;
+                f.blk = b0 + bb;
+                f.done = false;
+                getcontext(&f.uc);
+                f.uc.uc_stack.ss_sp = g_stacks.data() + ((size_t)bb * block + t) * kFiberStack;
+                f.uc.uc_stack.ss_size = kFiberStack;
+                f.uc.uc_link = &g_sched;
+                makecontext(&f.uc, fiber_main, 0);
+            }
+        }
+        int blocks_left = wave;
+        std::vector<int> left((size_t)wave, block);
+        while (blocks_left > 0) {
+            for (int bb = 0; bb < wave; ++bb) {
+                if (left[(size_t)bb] == 0) continue;
+                // run this block until it is finished or waits for the others
+                for (;;) {
+                    g_grid_wait = false;
+                    for (int t = 0; t < block; ++t) {
+                        Fiber &f = g_fibers[(size_t)bb * block + t];
+                        if (f.done) continue;
+                        g_cur = &f;
+                        threadIdx = EmuDim{(unsigned)t, 0, 0};
+                        blockIdx = EmuDim{(unsigned)(b0 + bb), 0, 0};
+                        swapcontext(&g_sched, &f.uc);
+                        if (f.done) left[(size_t)bb]--;
+                    }
+                    if (left[(size_t)bb] == 0) {
+                        blocks_left--;
+                        break;
+                    }
+                    if (g_grid_wait && wave > 1) break;          // let the other blocks run
+                }
             }
         }
         g_cur = nullptr;
     }
+}
+
+void emu_launch_fibers(int grid, int block, const void *closure, void (*invoke)(const void *))
+{
+    emu_launch_fibers_mode(grid, block, closure, invoke, 0);
+}
+
+unsigned char *emu_dynamic_smem = nullptr;
+void emu_set_dynamic_smem(size_t bytes)
+{
+    static std::vector<double> buf;                   // 8-byte aligned
+    if (buf.size() * 8 < bytes + 16) buf.resize(bytes / 8 + 4);
+    emu_dynamic_smem = reinterpret_cast<unsigned char *>(buf.data());
 }
 
 // emulation-only switch (not part of the product ABI): 1 = SIMT fibers + the genuine reduction
@@ -249,6 +301,12 @@ extern "C" int kry_ctx_create(int device, kry_ctx **out)
     c->use_graphs = 0;
     c->cg_fuse = 2;
     c->cg_fuse_shards = 1;
+#ifdef KRY_OPT_MINRES_FUSE
+    c->minres_fuse = 1;
+#endif
+#ifdef KRY_OPT_MINRES_PERSISTENT
+    c->minres_persistent = 1;
+#endif
     KRY_TRY(kry_alloc((void **)&c->scalars, KRY_NUM_SLOTS * sizeof(double)));
     KRY_TRY(kry_alloc((void **)&c->sums, 2 * KRY_MAX_DOTS * sizeof(double)));
     KRY_TRY(kry_alloc((void **)&c->counter, 256));
@@ -314,8 +372,11 @@ extern "C" int kry_ctx_set_option(kry_ctx *c, int option, int value)
 #ifdef KRY_OPT_MINRES_FUSE
         case KRY_OPT_MINRES_FUSE: c->minres_fuse = value ? 1 : 0; return KRY_OK;
 #endif
+#ifdef KRY_OPT_MINRES_PERSISTENT
+        case KRY_OPT_MINRES_PERSISTENT: c->minres_persistent = value ? 1 : 0; return KRY_OK;
+#endif
 #ifdef KRY_OPT_CG_ONE_CTA
-        case KRY_OPT_CG_ONE_CTA: return KRY_OK;               // needs shared memory: not emulated
+        case KRY_OPT_CG_ONE_CTA: c->cg_one_cta = (value && emu_fibers_on) ? 1 : 0; return KRY_OK;   // SIMT mode only
 #endif
         default: kry_set_error("kry_ctx_set_option (emulation): option %d", option); return KRY_ERR_INVALID;
     }
@@ -332,8 +393,11 @@ extern "C" int kry_ctx_get_option(kry_ctx *c, int option, int *value)
 #ifdef KRY_OPT_MINRES_FUSE
         case KRY_OPT_MINRES_FUSE: *value = c->minres_fuse; return KRY_OK;
 #endif
+#ifdef KRY_OPT_MINRES_PERSISTENT
+        case KRY_OPT_MINRES_PERSISTENT: *value = c->minres_persistent; return KRY_OK;
+#endif
 #ifdef KRY_OPT_CG_ONE_CTA
-        case KRY_OPT_CG_ONE_CTA: *value = 0; return KRY_OK;
+        case KRY_OPT_CG_ONE_CTA: *value = c->cg_one_cta; return KRY_OK;
 #endif
         default: kry_set_error("kry_ctx_get_option (emulation): option %d", option); return KRY_ERR_INVALID;
     }

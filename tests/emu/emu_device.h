@@ -63,7 +63,8 @@ static inline void __syncthreads() { emu_block_barrier(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu_warp_barrier((int)(threadIdx.x >> 5)); }
 static inline void __threadfence() {}
 static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
-static inline void __nanosleep(unsigned) { emu_yield(); }
+void emu_spin_wait();
+static inline void __nanosleep(unsigned) { emu_spin_wait(); }
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { const unsigned o = *p; *p = o + v; return o; }
 static inline int atomicMax(int *p, int v) { const int o = *p; if (v > o) *p = v; return o; }
 
@@ -102,9 +103,14 @@ static inline void block_reduce_finalize(double (&acc)[ND], const ReduceWs &ws, 
     emu_reduced = 1;
 }
 
+// ---- dynamic shared memory of a launch (extern __shared__ in CUDA)
+extern unsigned char *emu_dynamic_smem;
+void emu_set_dynamic_smem(size_t bytes);
+
 // ---- launchers
 void emu_p2p_allreduce(const ReduceWs &ws, double *tot, int nd);
 void emu_launch_fibers(int grid, int block, const void *kernel_closure, void (*invoke)(const void *));
+void emu_launch_fibers_mode(int grid, int block, const void *kernel_closure, void (*invoke)(const void *), int cooperative);
 
 template <int ND, class Ws, class Fin, class Kernel>
 static inline void emu_launch(int grid, int block, const Ws &ws, Fin fin, Kernel kernel)

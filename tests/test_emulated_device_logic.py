@@ -22,7 +22,7 @@ import test_gpu_lls as GL
 import test_gpu_parity as GP
 
 # fixtures the collected tests ask for
-from test_gpu_parity import cg_form          # noqa: F401
+from test_gpu_parity import cg_form, minres_plan          # noqa: F401
 from test_gpu_lls import gold                # noqa: F401
 
 
@@ -36,6 +36,7 @@ def _emulable(name):
     skip = ("fullsize",                   # 10^7-row operators: minutes on one host thread
             "gallery_equals_oracle",      # would test emu_context.cpp's generators, not the product
             "handles_can_be_destroyed",   # creates its own Context on cuda:0
+            "one_cta_loop",               # shared memory + __syncthreads(): CUDA only
             "lsqr_rectangular")           # its 1e-3 bar on Anorm/Acond (rounding-chaotic after convergence,
                                           # see the test) is calibrated to the GPU's reduction tree
     return name.startswith("test_") and not any(s in name for s in skip)

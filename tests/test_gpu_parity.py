@@ -78,7 +78,8 @@ def fixtures():
 
 
 KERNELS = [("row", 1, 0, 0), ("stream", 2, 4096, 256), ("stream_small", 2, 512, 64),
-           ("tma", 3, 2048, 256), ("tma_small", 3, 256, 128)]
+           ("tma", 3, 2048, 256), ("tma_small", 3, 256, 128),
+           ("rowpf", 6, 0, 0), ("rowpf2", 7, 0, 0)]     # software-pipelined row kernels (candidates)
 
 
 # ============================================================== integer work
@@ -209,14 +210,17 @@ def test_reduction_is_deterministic(ctx):
 
 
 # ==================================================== single-step solver parity
-@pytest.fixture(params=[0, 1, 2], ids=["cg3launch", "cgfuse1", "cgfuse2"])
+@pytest.fixture(params=[(0, 0), (1, 0), (2, 0), (2, 1)], ids=["cg3launch", "cgfuse1", "cgfuse2", "cg1cta"])
 def cg_form(ctx, request):
-    """Every CG test runs under the three launch plans (KRY_OPT_CG_FUSE): the 3-launch
-    form and the two fused 2-launch forms must be indistinguishable from outside."""
-    default = ctx.get_option(L().KRY_OPT_CG_FUSE)
-    ctx.set_option(L().KRY_OPT_CG_FUSE, request.param)
+    """Every CG test runs under the three multi-CTA launch plans (KRY_OPT_CG_FUSE: the 3-launch
+    form and the two fused 2-launch forms) and with the one-CTA loop for problems that fit one SM
+    (KRY_OPT_CG_ONE_CTA); all of them must be indistinguishable from outside."""
+    d_fuse, d_one = ctx.get_option(L().KRY_OPT_CG_FUSE), ctx.get_option(L().KRY_OPT_CG_ONE_CTA)
+    ctx.set_option(L().KRY_OPT_CG_FUSE, request.param[0])
+    ctx.set_option(L().KRY_OPT_CG_ONE_CTA, request.param[1])
     yield request.param
-    ctx.set_option(L().KRY_OPT_CG_FUSE, default)
+    ctx.set_option(L().KRY_OPT_CG_FUSE, d_fuse)
+    ctx.set_option(L().KRY_OPT_CG_ONE_CTA, d_one)
 
 
 def cg_case(name):
@@ -386,8 +390,17 @@ def minres_case():
     return Sm, Sm.matvec(np.ones(Sm.shape[0]))
 
 
+@pytest.fixture(params=[0, 1], ids=["minres3launch", "minres2launch"])
+def minres_plan(ctx, request):
+    """MINRES tests run under both launch plans (KRY_OPT_MINRES_FUSE)."""
+    default = ctx.get_option(L().KRY_OPT_MINRES_FUSE)
+    ctx.set_option(L().KRY_OPT_MINRES_FUSE, request.param)
+    yield request.param
+    ctx.set_option(L().KRY_OPT_MINRES_FUSE, default)
+
+
 @pytest.mark.parametrize("shift", [0.0, 0.5])
-def test_minres_single_step_from_identical_state(ctx, shift):
+def test_minres_single_step_from_identical_state(ctx, shift, minres_plan):
     M, rhs = minres_case()
     A = upload(ctx, M, symmetric=True)
     st = kr.minres_start(M, rhs, shift=shift)
@@ -519,7 +532,7 @@ def test_short_runs_reproduce_doc_tables(ctx, golden):
         assert "%8.2e" % (np.linalg.norm(ks.bestSolution - e) / np.sqrt(n)) == err
 
 
-def test_minres_public_api(ctx, golden, capsys):
+def test_minres_public_api(ctx, golden, capsys, minres_plan):
     from pykrylov_b200.linop import csr_operator
     from pykrylov_b200.minres import Minres
     M, rhs = minres_case()
@@ -620,6 +633,8 @@ def test_cg_fused_forms_are_bit_identical_to_the_3_launch_form(ctx, name, precon
     d = np.abs(M.to_scipy().diagonal()) + 1.0
     A = upload(ctx, M, symmetric=True)
     default = ctx.get_option(L().KRY_OPT_CG_FUSE)
+    one_cta = ctx.get_option(L().KRY_OPT_CG_ONE_CTA)
+    ctx.set_option(L().KRY_OPT_CG_ONE_CTA, 0)           # this test is about the multi-CTA plans
     out = {}
     try:
         for form in (0, 1, 2):
@@ -638,6 +653,7 @@ def test_cg_fused_forms_are_bit_identical_to_the_3_launch_form(ctx, name, precon
             S._release()
     finally:
         ctx.set_option(L().KRY_OPT_CG_FUSE, default)
+        ctx.set_option(L().KRY_OPT_CG_ONE_CTA, one_cta)
     for form in (1, 2):
         for a, b in zip(out[0][:-1], out[form][:-1]):
             assert a[:4] == b[:4], (form, a[:4], b[:4])
@@ -803,6 +819,106 @@ def test_large_results_come_back_in_pooled_pinned_memory(ctx):
     assert result_pool.hits == hits + 1 and np.array_equal(b, np.arange(n))
     small = ctx.vector(np.ones(10)).download()
     assert small.base is None
+
+
+def test_cg_one_cta_loop_matches_oracle_and_counts_one_launch_per_call(ctx, golden):
+    """KRY_OPT_CG_ONE_CTA: 1138bus (90 kB) iterates inside one CTA -- one launch per
+    kry_solver_iterate call, same history as the oracle within the per-step bar."""
+    M = fixtures()["1138bus"]
+    n = M.shape[0]
+    rhs = M.matvec(np.ones(n))
+    A = upload(ctx, M, symmetric=True)
+    saved = ctx.get_option(L().KRY_OPT_CG_ONE_CTA)
+    ctx.set_option(L().KRY_OPT_CG_ONE_CTA, 1)
+    try:
+        S = dev().DeviceSolver(ctx, "cg", A)
+        S.setup(rhs, matvec_max=2 * n)
+        l0 = ctx.launch_count()
+        S.iterate(40)
+        assert ctx.launch_count() - l0 == 1
+        st = S.status()
+        ref = kr.cg_solve(M, rhs, matvec_max=40)
+        hist = S.drain_history(st)[:, 0]
+        assert st.n_matvec == 40 and rel(hist[:41], ref.residHistory[:41]) <= 1e-9
+        st = S.run(200)
+        full = kr.cg_solve(M, rhs)
+        assert abs(st.n_matvec - full.nMatvec) <= 0.01 * full.nMatvec       # cond ~ 1e7: SURVEY.md section 6
+        x = S.solution()
+        assert abs(np.linalg.norm(rhs - M.matvec(x)) - np.linalg.norm(rhs - M.matvec(full.x))) <= RTOL_FINAL * np.linalg.norm(rhs)
+    finally:
+        ctx.set_option(L().KRY_OPT_CG_ONE_CTA, saved)
+
+
+def test_pipelined_host_drive_gives_the_same_results(ctx):
+    """_engine.drive(overlap=True) keeps one chunk in flight (status snapshots through
+    kry_solver_status_enqueue/_wait, history on the copy stream); results, histories and
+    counters must not depend on it or on the check interval."""
+    import pykrylov_b200._engine as eng
+    from pykrylov_b200.linop import csr_operator
+    from pykrylov_b200.cg import CG
+    from pykrylov_b200.bicgstab import BiCGSTAB
+    from pykrylov_b200.minres import Minres
+    M = load_mtx(mtx("1138bus"))
+    op = csr_operator(M.shape, M.indptr, M.indices, M.data, symmetric=True, context=ctx)
+    rhs = M.matvec(np.ones(M.shape[0]))
+    N = load_mtx(mtx("jpwh_991"))
+    nop = csr_operator(N.shape, N.indptr, N.indices, N.data, context=ctx)
+    nrhs = N.matvec(np.random.default_rng(3).standard_normal(N.shape[0]))
+    real = eng.drive
+    out = {}
+    try:
+        for overlap in (False, True):
+            eng.drive = (lambda S, k, cb=None, overlap=True, _o=overlap: real(S, k, cb, overlap=_o and overlap))
+            for interval in (7, 64):
+                cg = CG(op, check_interval=interval)
+                cg.solve(rhs)
+                bi = BiCGSTAB(nop, reltol=1e-8, check_interval=interval)
+                bi.solve(nrhs, matvec_max=2 * N.shape[0])
+                mr = Minres(op, check_interval=interval)
+                mr.solve(rhs, show=False, check=False, itnlim=300)
+                out[(overlap, interval)] = (cg.nMatvec, tuple(cg.residHistory), cg.bestSolution.copy(),
+                                            bi.nMatvec, tuple(bi.residHistory), bi.bestSolution.copy(),
+                                            mr.itn, mr.istop, tuple(mr.residHistory), mr.x.copy())
+    finally:
+        eng.drive = real
+    base = out[(False, 7)]
+    for key, val in out.items():
+        for a, b in zip(base, val):
+            assert (np.array_equal(a, b) if isinstance(a, np.ndarray) else a == b), key
+
+
+def test_minres_2_launch_plan_is_bit_identical_to_the_3_launch_plan(ctx):
+    """KRY_OPT_MINRES_FUSE only moves the w / x update of a trip into the next trip's second
+    launch: x, w, w2, r1, r2, every scalar and the history are the same bits, read mid-run
+    (which settles what is owed) or at the end, through graph replays or single launches."""
+    S0 = fixtures()["jpwh_991"].to_scipy()
+    M = CsrRef.from_scipy(((S0 + S0.T) * 0.5).tocsr())
+    n = M.shape[0]
+    rhs = M.matvec(np.ones(n))
+    A = upload(ctx, M, symmetric=True)
+    default = ctx.get_option(L().KRY_OPT_MINRES_FUSE)
+    out = {}
+    try:
+        for plan in (0, 1):
+            ctx.set_option(L().KRY_OPT_MINRES_FUSE, plan)
+            S = dev().DeviceSolver(ctx, "minres", A)
+            S.setup(rhs, matvec_max=10 ** 6, rtol=0.0, etol=0.0, window=5)
+            snaps = []
+            for chunk in (1, 2, 40, 3, 31):
+                S.iterate(chunk)
+                st = S.status()
+                snaps.append((st.n_iter, st.resid_norm, tuple(st.aux[:13])) +
+                             tuple(S.get_vector(v) for v in ("x", "w", "w2", "r1", "r2")))
+            snaps.append(S.drain_history())
+            out[plan] = snaps
+            S._release()
+    finally:
+        ctx.set_option(L().KRY_OPT_MINRES_FUSE, default)
+    for a, b in zip(out[0][:-1], out[1][:-1]):
+        assert a[:3] == b[:3], (a[:3], b[:3])
+        for u, v in zip(a[3:], b[3:]):
+            assert np.array_equal(u, v, equal_nan=True)
+    assert np.array_equal(out[0][-1], out[1][-1], equal_nan=True)
 
 
 @pytest.mark.parametrize("pmode", [1, 2])
