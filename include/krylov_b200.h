@@ -99,6 +99,11 @@ int kry_prof_read(kry_ctx *ctx, int64_t *samples, double *total_ms);
                                 between trips.  Candidate; latched at kry_solver_setup.                        */
 #define KRY_OPT_CG_FUSE_SHARDS 5 /* 1 (default): row shards use the CG_FUSE plan too (the packed halo then
                                 carries beta p - r of the boundary entries); 0: shards keep plan 0 */
+#define KRY_OPT_HALO_P2P 9     /* sharded runs with KRY_OPT_P2P on: the SpMV launch itself writes this rank's
+                                boundary entries into the peers' halo tails over NVLink peer memory (CUDA IPC)
+                                and waits for the peers' flags only when it reaches its boundary rows, which it
+                                processes last -- no pack launch, no ncclAllGather.  0: pack kernel + one
+                                ncclAllGather ahead of the SpMV.  Must be set identically on every rank.       */
 int kry_ctx_set_option(kry_ctx *ctx, int option, int value);
 int kry_ctx_get_option(kry_ctx *ctx, int option, int *value);
 

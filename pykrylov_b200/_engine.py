@@ -32,9 +32,33 @@ def _diag_precon(precon, n):
     d = getattr(precon, "diag", None)
     if d is not None and not hasattr(precon, "device_csr") and callable(precon):
         d = np.asarray(d)
-        if d.dtype == np.float64 and d.shape == (n,):
+        if d.dtype == np.float64 and d.shape == (n,) and _divides_by_diag(precon, d):
             return d, 2                      # y = r ./ d   (examples/bmark.py:14-22)
     return None
+
+
+def _divides_by_diag(precon, d):
+    """A callable with a ``.diag`` is only *assumed* to compute ``r / diag`` (bmark.py's
+    DiagonalPrec); scaled Jacobi, a stored inverse diagonal or SSOR carry a ``.diag`` too.  So
+    the device fast path is taken only after the callable has reproduced ``probe / diag`` to
+    the bit on a random probe (IEEE division is correctly rounded: any honest ``r / diag``
+    matches exactly); anything else stays an opaque callable and goes through the host bridge.
+    The verdict is remembered per (object, diagonal buffer)."""
+    key = (d.__array_interface__["data"][0], d.shape[0])
+    seen = getattr(precon, "_kry_diag_probe", None)
+    if seen is not None and seen[0] == key:
+        return seen[1]
+    probe = np.random.default_rng(20251017).standard_normal(d.shape[0])
+    try:
+        with np.errstate(all="ignore"):
+            ok = bool(np.array_equal(np.asarray(precon(probe)), probe / d, equal_nan=True))
+    except Exception:                        # noqa: BLE001 -- not callable that way: opaque
+        ok = False
+    try:
+        precon._kry_diag_probe = (key, ok)
+    except Exception:                        # noqa: BLE001 -- __slots__ etc.: probe again next time
+        pass
+    return ok
 
 
 def resolve(op, precon, n):
@@ -45,6 +69,17 @@ def resolve(op, precon, n):
     if pd is None:
         return None
     return DevicePlan(csr, pd[0], pd[1])
+
+
+def global_size(op, n):
+    """Problem size the default iteration caps (2n, 5n) are derived from: the reference uses the
+    system size; on a row shard that is the global row count, the same on every rank -- caps
+    derived from the local slice would differ by rank and the ranks would latch `done` at
+    different trips (and then wait for each other in the collectives forever)."""
+    csr = getattr(op, "device_csr", None)
+    if csr is not None and getattr(csr, "sharded", False):
+        return int(csr.n_global)
+    return n
 
 
 def check_real(op, rhs):

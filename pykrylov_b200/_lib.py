@@ -37,7 +37,7 @@ KRY_SPMV_ROWPF, KRY_SPMV_ROWPF2 = 6, 7
 KRY_CG, KRY_BICGSTAB, KRY_CGS, KRY_TFQMR, KRY_MINRES = 1, 2, 3, 4, 5
 KRY_NUM_SLOTS = 64
 KRY_OPT_L2_HINTS, KRY_OPT_GRAPHS, KRY_OPT_P2P, KRY_OPT_CG_FUSE, KRY_OPT_CG_FUSE_SHARDS = 1, 2, 3, 4, 5
-KRY_OPT_CG_ONE_CTA, KRY_OPT_MINRES_FUSE, KRY_OPT_MINRES_PERSISTENT = 6, 7, 8
+KRY_OPT_CG_ONE_CTA, KRY_OPT_MINRES_FUSE, KRY_OPT_MINRES_PERSISTENT, KRY_OPT_HALO_P2P = 6, 7, 8, 9
 KRY_COMM_ID_BYTES = 128
 
 c_i32p = C.POINTER(C.c_int32)

@@ -27,7 +27,7 @@ class BiCGSTAB(KrylovMethod):
         n = rhs.shape[0]
         result_type = _engine.check_real(self.op, rhs)
         guess = kwargs.get("guess", None)
-        matvec_max = kwargs.get("matvec_max", 2 * n)
+        matvec_max = kwargs.get("matvec_max", 2 * _engine.global_size(self.op, n))
         plan = _engine.resolve(self.op, self.precon, n)
         if plan is None:       # closure operator / opaque preconditioner: host-driven loop on device vectors
             from .. import _bridged

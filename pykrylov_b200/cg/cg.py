@@ -44,7 +44,7 @@ class CG(KrylovMethod):
 
         result_type = _engine.check_real(self.op, rhs)
         guess = kwargs.get("guess", None)
-        matvec_max = kwargs.get("matvec_max", 2 * n)
+        matvec_max = kwargs.get("matvec_max", 2 * _engine.global_size(self.op, n))
         plan = _engine.resolve(self.op, self.precon, n)
         if plan is None:
             return self._solve_bridged(rhs, guess, matvec_max, check_curvature,

@@ -78,6 +78,7 @@ struct kry_ctx {
     double      *sums;
     unsigned    *counter;
     int          partial_stride;
+    int          partials_gen; // bumped whenever `partials` is reallocated (kry_ctx_ensure_partials)
     int         *never_done;   // device int == 0: "done" flag of the stand-alone ops
     void        *flush_buf;
     size_t       flush_bytes;
@@ -92,6 +93,7 @@ struct kry_ctx {
     int          use_graphs;   // 1: solver loops replay CUDA graphs of 12 iterations (default)
     int          cg_fuse;      // KRY_OPT_CG_FUSE: CG launch plan (0: 3 launches, 1/2: fused 2-launch forms)
     int          cg_fuse_shards;   // KRY_OPT_CG_FUSE_SHARDS: the plan also applies to row shards
+    int          halo_p2p;         // KRY_OPT_HALO_P2P: halo entries travel through peer memory from inside the SpMV launch
     int          cg_one_cta;       // KRY_OPT_CG_ONE_CTA: small problems iterate inside one CTA
     int          minres_fuse;      // KRY_OPT_MINRES_FUSE: 2-launch MINRES plan
     int          minres_persistent;    // KRY_OPT_MINRES_PERSISTENT: one cooperative kernel per iterate call

@@ -101,6 +101,7 @@ int kry_ctx_ensure_partials(kry_ctx *c, int nblocks)
     c->partials = nullptr;
     KRY_TRY(kry_alloc((void **)&c->partials, (size_t)KRY_MAX_DOTS * stride * sizeof(double)));
     c->partial_stride = stride;
+    c->partials_gen++;      // captured graphs have the old pointer / stride baked in: solvers re-capture
     return KRY_OK;
 }
 
@@ -237,13 +238,14 @@ extern "C" int kry_ctx_set_option(kry_ctx *c, int option, int value)
     KRY_REQUIRE(option == KRY_OPT_L2_HINTS || option == KRY_OPT_GRAPHS || option == KRY_OPT_P2P ||
                     option == KRY_OPT_CG_FUSE || option == KRY_OPT_CG_FUSE_SHARDS ||
                     option == KRY_OPT_CG_ONE_CTA || option == KRY_OPT_MINRES_FUSE ||
-                    option == KRY_OPT_MINRES_PERSISTENT,
+                    option == KRY_OPT_MINRES_PERSISTENT || option == KRY_OPT_HALO_P2P,
                 KRY_ERR_INVALID, "kry_ctx_set_option: unknown option %d", option);
     if (option == KRY_OPT_L2_HINTS) c->l2_hints = value;
     else if (option == KRY_OPT_CG_FUSE_SHARDS) c->cg_fuse_shards = value ? 1 : 0;
     else if (option == KRY_OPT_CG_ONE_CTA) c->cg_one_cta = value ? 1 : 0;
     else if (option == KRY_OPT_MINRES_FUSE) c->minres_fuse = value ? 1 : 0;
     else if (option == KRY_OPT_MINRES_PERSISTENT) c->minres_persistent = value ? 1 : 0;
+    else if (option == KRY_OPT_HALO_P2P) c->halo_p2p = value ? 1 : 0;
     else if (option == KRY_OPT_CG_FUSE) {
         KRY_REQUIRE(value >= 0 && value <= 2, KRY_ERR_INVALID, "kry_ctx_set_option: CG_FUSE=%d not in 0..2", value);
         c->cg_fuse = value;
@@ -269,6 +271,7 @@ extern "C" int kry_ctx_get_option(kry_ctx *c, int option, int *value)
         case KRY_OPT_CG_ONE_CTA: *value = c->cg_one_cta; break;
         case KRY_OPT_MINRES_FUSE: *value = c->minres_fuse; break;
         case KRY_OPT_MINRES_PERSISTENT: *value = c->minres_persistent; break;
+        case KRY_OPT_HALO_P2P: *value = c->halo_p2p; break;
         default: kry_set_error("kry_ctx_get_option: unknown option %d", option); return KRY_ERR_INVALID;
     }
     return KRY_OK;
@@ -520,6 +523,36 @@ int csr_build_partition(kry_ctx *c, CsrDev &m, int tile_nnz)
     return KRY_OK;
 }
 
+// One pass over an uploaded CSR: row pointers must not decrease and every column index
+// must address the input vector -- a malformed matrix would otherwise read out of bounds in
+// every SpMV.  bad[0] counts offending rows, bad[1] offending entries.
+__global__ void csr_validate_kernel(const int *rowptr, const int *col, int nrows, int ncols, int nnz, int *bad)
+{
+    const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    int br = 0, bc = 0;
+    for (int i = t0; i < nrows; i += stride) br += (rowptr[i] > rowptr[i + 1]) || rowptr[i] < 0;
+    for (int k = t0; k < nnz; k += stride) bc += (col[k] < 0 || col[k] >= ncols);
+    if (br) atomicAdd(bad, br);
+    if (bc) atomicAdd(bad + 1, bc);
+}
+
+static int csr_validate(kry_ctx *c, const CsrDev &m)
+{
+    int *d_bad = (int *)c->counter + 12;    // scratch inside the 256-byte counter block
+    KRY_CUDA(cudaMemsetAsync(d_bad, 0, 2 * sizeof(int), c->stream));
+    csr_validate_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(m.rowptr, m.col, (int)m.nrows, (int)m.ncols,
+                                                              (int)m.nnz, d_bad);
+    c->launches++;
+    KRY_CUDA(cudaGetLastError());
+    int h[2] = {0, 0};
+    KRY_CUDA(cudaMemcpyAsync(h, d_bad, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    KRY_CUDA(cudaStreamSynchronize(c->stream));
+    KRY_REQUIRE(h[0] == 0, KRY_ERR_INVALID, "kry_csr_create: rowptr decreases at %d row(s)", h[0]);
+    KRY_REQUIRE(h[1] == 0, KRY_ERR_INVALID, "kry_csr_create: %d column index(es) outside [0, %lld)", h[1],
+                (long long)m.ncols);
+    return KRY_OK;
+}
+
 static int csr_finish(kry_ctx *c, CsrDev &m)
 {
     int *d_max = (int *)c->counter + 8;     // scratch inside the 256-byte counter block
@@ -584,6 +617,7 @@ extern "C" int kry_csr_create(kry_ctx *c, int64_t nrows, int64_t ncols, int64_t 
             rc = KRY_ERR_CUDA;
         }
     }
+    if (rc == KRY_OK) rc = csr_validate(c, M->A);
     if (rc == KRY_OK) rc = csr_finish(c, M->A);
     if (rc == KRY_OK && (flags & KRY_CSR_BUILD_TRANSPOSE) && !(flags & KRY_CSR_SYMMETRIC)) {
         rc = csr_build_transpose_dev(c, M->A, M->T);

@@ -80,6 +80,7 @@ struct kry_solver {
     // CUDA-graph replay of KRY_GRAPH_ITERS iterations (launch-latency bound problems)
     cudaGraphExec_t   graph_exec;
     int64_t           graph_launches;   // kernel launches inside one replay
+    uint64_t          graph_key;        // solver_graph_key() the graph was captured under
     bool              warm;             // at least one iteration ran un-captured
     int               cg_fuse;          // CG launch plan latched at setup (KRY_OPT_CG_FUSE)
     bool              fresh;            // fused CG: nothing pending, p sits in the next trip's source buffer

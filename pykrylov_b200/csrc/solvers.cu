@@ -115,6 +115,8 @@ struct CgFinRy {
     DevScalars *s;
     double     *hist;
     int         fuse;        // fused forms: the p (and x) update of this trip is now owed
+    int         late;        // 3-launch plan: K3 (p = beta p - r) still runs in the trip that meets the
+                             // stopping test and latches `done` itself (CgFinDir), as cg.py:149-151 does
     __device__ void operator()(const double *t) const
     {
         const double ry_next = t[0];
@@ -126,7 +128,21 @@ struct CgFinRy {
         s->resid = resid;
         s->n_iter++;
         hist_push(s, hist, 2, resid, s->s[S_PAP]);                   // cg.py:155-158
-        if (!(resid > s->threshold && s->n_matvec < s->matvec_max)) s->done = 1;   // cg.py:113
+        if (!(resid > s->threshold && s->n_matvec < s->matvec_max)) {              // cg.py:113
+            if (late) s->skip_half = 1;
+            else s->done = 1;
+        }
+    }
+};
+
+struct CgFinDir {                 // 3-launch plan, after K3: the loop condition of cg.py:113 is re-tested here
+    DevScalars *s;
+    __device__ void operator()(const double *) const
+    {
+        if (s->skip_half) {
+            s->skip_half = 0;
+            s->done = 1;
+        }
     }
 };
 
@@ -143,12 +159,12 @@ struct CgDirBody {
         ef = l2_policy_evict_first();
         el = l2_policy_evict_last();
     }
-    __device__ void operator()(int i) const
+    __device__ void operator()(int i, double *) const
     {
         p[i] = __dsub_rn(__dmul_rn(beta, p[i]), r[i]);               // cg.py:150-151
     }
     static constexpr bool kPair = true;
-    __device__ void pair(int i2) const
+    __device__ void pair(int i2, double *) const
     {
         double2 pv, rv;
         if (hints) {
@@ -420,7 +436,7 @@ static int cg_iterate(kry_solver *S)
         KRY_TRY(rc);
         S->fresh = false;
         S->rot++;
-        CgFinRy fin{S->ds, S->hist, S->cg_fuse};
+        CgFinRy fin{S->ds, S->hist, S->cg_fuse, 0};
         if (xlag) {
             CgUpdateRBody ub{r, Ap, S->dinv, S->precon_mode, S->ds, 0.0, opt & 1, 0, 0};
             return solver_pass<1>(S, ub, fin, done);
@@ -430,9 +446,11 @@ static int cg_iterate(kry_solver *S)
     }
     KRY_TRY((solver_spmv<1>(S, GatherPlain{p}, CgEpiAp{Ap, p, (opt & 4) ? 1 : 0, 0}, CgFinAp{S->ds}, done, p)));
     CgUpdateBody ub{x, r, p, Ap, S->dinv, S->precon_mode, S->ds, 0.0, opt & 1, 0, 0};
-    KRY_TRY((solver_pass<1>(S, ub, CgFinRy{S->ds, S->hist, 0}, done)));
+    KRY_TRY((solver_pass<1>(S, ub, CgFinRy{S->ds, S->hist, 0, 1}, done)));
+    // K3 carries no inner product; its finalize only latches `done` (every rank holds the same
+    // flag, so there is nothing to all-reduce on shards)
     CgDirBody db{p, r, S->ds, 0.0, opt & 1, 0, 0};
-    return vec_map_launch(S->ctx, S->n, db, done);
+    return vec_pass_launch<1>(S->ctx, S->n, db, CgFinDir{S->ds}, done, 0);
 }
 
 // ---- CG inside one CTA (KRY_OPT_CG_ONE_CTA): problems whose CSR and four vectors fit the
@@ -509,7 +527,7 @@ cg_one_cta_kernel(CsrView A, double *gx, double *gr, double *gp, double *gAp, co
         __syncthreads();                        // s_warp reuse
         block_sum<1>(acc, s_warp);
         if (tid == 0) {
-            CgFinRy{s, hist, 0}(acc);
+            CgFinRy{s, hist, 0, 0}(acc);
             sh_scalar = s->s[S_BETA];
             sh_done = s->done;
         }
@@ -2056,8 +2074,7 @@ static int solver_setup_common(kry_solver *S, int guess, const kry_solver_params
     KRY_REQUIRE(p, KRY_ERR_INVALID, "kry_solver_setup: NULL params");
     KRY_REQUIRE(S->method != KRY_MINRES || (p->window >= 1 && p->window <= 16), KRY_ERR_INVALID,
                 "kry_solver_setup: MINRES window %d not in [1,16]", p->window);
-    solver_drop_graph(S);
-    S->warm = false;
+    S->warm = false;      // (a captured graph survives: see solver_graph_key)
     S->snap_pending[0] = S->snap_pending[1] = false;
     S->params = *p;
     DevScalars h;
@@ -2142,6 +2159,26 @@ static void solver_drop_graph(kry_solver *S)
     S->graph_launches = 0;
 }
 
+// Everything besides the solver's own (fixed) buffers that a captured launch sequence has baked
+// into its kernel arguments and grid sizes.  A graph is kept across kry_solver_setup calls --
+// re-instantiating it costs more than a small solve -- and dropped only when this key changes.
+static uint64_t solver_graph_key(const kry_solver *S)
+{
+    const kry_ctx *c = S->ctx;
+    uint64_t k = 1469598103934665603ull;
+    auto mix = [&k](uint64_t v) { k = (k ^ v) * 1099511628211ull; };
+    mix((uint64_t)c->partials_gen);
+    mix((uint64_t)c->l2_hints);
+    mix((uint64_t)S->precon_mode);
+    mix((uint64_t)S->cg_fuse);
+    mix((uint64_t)S->minres_fuse);
+    mix((uint64_t)S->A->kind);
+    mix((uint64_t)S->A->tile_nnz);
+    mix((uint64_t)S->A->threads);
+    mix((uint64_t)(uintptr_t)S->A->A.rowblk);
+    return k;
+}
+
 // Capture KRY_GRAPH_ITERS iterations of the (static) launch sequence into a graph.
 static int solver_capture_graph(kry_solver *S)
 {
@@ -2163,6 +2200,7 @@ static int solver_capture_graph(kry_solver *S)
         KRY_CUDA(e);
         return KRY_ERR_CUDA;
     }
+    S->graph_key = solver_graph_key(S);
     e = cudaGraphInstantiate(&S->graph_exec, graph, 0);
     cudaGraphDestroy(graph);
     KRY_CUDA(e);
@@ -2192,6 +2230,7 @@ extern "C" int kry_solver_iterate(kry_solver *S, int64_t n_iters)
             S->warm = true;
             --left;
         }
+        if (S->graph_exec && S->graph_key != solver_graph_key(S)) solver_drop_graph(S);
         if (!S->graph_exec && left >= KRY_GRAPH_ITERS) KRY_TRY(solver_capture_graph(S));
         while (S->graph_exec && left >= KRY_GRAPH_ITERS) {
             KRY_CUDA(cudaGraphLaunch(S->graph_exec, c->stream));

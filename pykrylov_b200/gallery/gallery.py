@@ -67,3 +67,24 @@ def poisson2d_csr_arrays(grid):
     vals = np.broadcast_to(np.array([-1.0, -1.0, 4.0, -1.0, -1.0]), cols.shape)
     indptr = np.concatenate([[0], np.cumsum(keep.sum(axis=1))]).astype(np.int32)
     return indptr, cols[keep].astype(np.int32), np.ascontiguousarray(vals[keep])
+
+
+def kron_sym_jpwh(mtx_path, k=1009):
+    """BASELINE config 3: A = kron(I_k, S) with S = (B + B^T)/2 and B the
+    Matrix Market file at ``mtx_path`` (examples/jpwh_991.mtx).  Returns host CSR arrays
+    ((n, n), indptr[int32], indices[int32], data) with sorted columns; k = 1009 gives
+    n = 999 919, nnz = 6 404 123."""
+    from ..mmio import read_mtx, coo_to_csr
+    (m, _), ip, ix, dv, _ = read_mtx(mtx_path)
+    rows = np.repeat(np.arange(m, dtype=np.int64), np.diff(ip))
+    cols = ix.astype(np.int64)
+    # (B + B^T) * 0.5: coincident entries are summed first, then halved (scipy's expression order)
+    sip, six, sdv = coo_to_csr(m, np.concatenate([rows, cols]), np.concatenate([cols, rows]),
+                               np.concatenate([dv, dv]))
+    sdv = sdv * 0.5
+    nnz1 = len(sdv)
+    k = int(k)
+    indptr = (np.arange(k, dtype=np.int64)[:, None] * nnz1 + sip[None, :-1].astype(np.int64)).reshape(-1)
+    indptr = np.concatenate([indptr, [k * nnz1]]).astype(np.int32)
+    indices = (np.arange(k, dtype=np.int64)[:, None] * m + six[None, :].astype(np.int64)).reshape(-1).astype(np.int32)
+    return (k * m, k * m), indptr, indices, np.tile(sdv, k)

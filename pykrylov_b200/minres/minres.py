@@ -58,7 +58,7 @@ class Minres(KrylovMethod):
         shift = kwargs.get("shift", 0.0)
         show = kwargs.get("show", True)
         check = kwargs.get("check", True)
-        itnlim = kwargs.get("itnlim", 5 * n)
+        itnlim = kwargs.get("itnlim", 5 * _engine.global_size(A, n))
         rtol = kwargs.get("rtol", 1.0e-12)
         etol = kwargs.get("etol", 1.0e-6)
         store_iterates = kwargs.get("store_iterates", False)

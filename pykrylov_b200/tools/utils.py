@@ -20,12 +20,19 @@ def check_symmetric(op, repeats=10):
     if nrow != ncol:
         return False
     eps = machine_epsilon()
+    # Row-sharded device operator (SPMD: local slice in, local slice out): the two inner
+    # products are partial sums that only mean something after a sum over the ranks -- and
+    # every rank must reach the same verdict, or some would iterate while others do not.
+    csr = getattr(op, "device_csr", None)
+    reduce = csr.ctx.allreduce if (csr is not None and getattr(csr, "sharded", False)) else None
     np.random.seed(1)
     for _ in range(repeats):
         x = np.random.random(ncol)
         w = op * x
         s = np.dot(w, w)
         t = np.dot(x, op * w)
+        if reduce is not None:
+            s, t = (float(v) for v in reduce([s, t]))
         if abs(s - t) > (s + eps) * eps ** (1.0 / 3):
             return False
     return True

@@ -365,6 +365,7 @@ extern "C" int kry_ctx_set_option(kry_ctx *c, int option, int value)
             c->cg_fuse = value;
             return KRY_OK;
         case KRY_OPT_CG_FUSE_SHARDS: c->cg_fuse_shards = value ? 1 : 0; return KRY_OK;
+        case KRY_OPT_HALO_P2P: c->halo_p2p = value ? 1 : 0; return KRY_OK;
         case KRY_OPT_P2P:
             KRY_REQUIRE(!value || c->p2p_inbox, KRY_ERR_STATE, "peer-memory all-reduce was not set up");
             c->p2p_on = value ? 1 : 0;
@@ -390,6 +391,7 @@ extern "C" int kry_ctx_get_option(kry_ctx *c, int option, int *value)
         case KRY_OPT_P2P: *value = c->p2p_on; return KRY_OK;
         case KRY_OPT_CG_FUSE: *value = c->cg_fuse; return KRY_OK;
         case KRY_OPT_CG_FUSE_SHARDS: *value = c->cg_fuse_shards; return KRY_OK;
+        case KRY_OPT_HALO_P2P: *value = c->halo_p2p; return KRY_OK;
 #ifdef KRY_OPT_MINRES_FUSE
         case KRY_OPT_MINRES_FUSE: *value = c->minres_fuse; return KRY_OK;
 #endif

@@ -241,3 +241,32 @@ def test_sharded_preconditioned_minres_follows_the_oracle(emu_ctx, world):
         return True
 
     assert all(run_ranks(world, worker))
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_hardware_worker_sections_on_emulated_ranks(emu_ctx, world):
+    """tests/multi_gpu_worker.py -- what `pytest -m gpu` runs on 2, 4 and 8 real GPUs -- section by
+    section on emulated ranks: the hardware test's own logic is exercised in the CPU suite, and a
+    rank that would hang in a collective on the box hangs (and is reported) here first."""
+    from pykrylov_b200 import _lib as L
+    from pykrylov_b200 import device as dev
+    import multi_gpu_worker as W
+    uid = C.create_string_buffer(L.KRY_COMM_ID_BYTES)
+    L.call("kry_comm_unique_id", uid)
+
+    def worker(rank):
+        ctx = dev.Context(0)
+        ctx.comm_init(world, rank, uid.raw)
+        lines = []
+        try:
+            W.section_cg_stencil(ctx, rank, world, lines.append)
+            W.section_cg_irregular(ctx, rank, world, lines.append)
+            W.section_other_loops(ctx, rank, world, lines.append)
+            W.section_public_api(ctx, rank, world, lines.append)
+            ctx.barrier()
+        finally:
+            ctx.close()
+        return lines
+
+    out = run_ranks(world, worker, timeout=900)
+    assert all(len(o) >= 8 for o in out)

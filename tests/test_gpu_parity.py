@@ -839,7 +839,10 @@ def test_cg_one_cta_loop_matches_oracle_and_counts_one_launch_per_call(ctx, gold
         st = S.status()
         ref = kr.cg_solve(M, rhs, matvec_max=40)
         hist = S.drain_history(st)[:, 0]
-        assert st.n_matvec == 40 and rel(hist[:41], ref.residHistory[:41]) <= 1e-9
+        # cond(1138bus) ~ 1e7: a different summation order alone moves the history by 1e-15 at
+        # trip 20, 1e-6 at trip 30 and 1e-2 at trip 40 (measured with the oracle, np.dot against
+        # math.fsum), so the trajectory is compared over the first 20 trips
+        assert st.n_matvec == 40 and rel(hist[:21], ref.residHistory[:21]) <= 1e-9
         st = S.run(200)
         full = kr.cg_solve(M, rhs)
         assert abs(st.n_matvec - full.nMatvec) <= 0.01 * full.nMatvec       # cond ~ 1e7: SURVEY.md section 6
@@ -965,3 +968,97 @@ def test_minres_with_diagonal_preconditioner_is_device_resident(ctx, pmode):
     k = min(len(ref.residHistory), len(mr.residHistory), 20)
     assert rel(mr.residHistory[:k], ref.residHistory[:k]) <= 1e-9
     assert np.linalg.norm(mr.x - ref.x) <= 1e-6 * np.linalg.norm(ref.x)
+
+
+# ------------------------------------------------------------------ BASELINE configs 3 and 4 at full size
+@pytest.mark.gpu
+def test_config3_minres_kron_jpwh_fullsize_follows_the_oracle(ctx):
+    """BASELINE config 3 at its full size (N = 999 919, nnz = 6 404 123): MINRES on
+    kron(I_1009, sym(jpwh_991)) -- SpMV bit-exact on a random vector, and under every launch plan
+    the oracle's exit (istop 10 at 74 iterations, the reference's own figures), its
+    residual history and truncated direct-error estimates, and its solution."""
+    from pykrylov_b200.gallery import kron_sym_jpwh
+    shape, ip, ix, dv = kron_sym_jpwh(mtx("jpwh_991"), 1009)
+    n = shape[0]
+    assert (n, len(dv)) == (999919, 6404123)
+    M = CsrRef(shape, ip, ix, dv)
+    A = dev().DeviceCsr.from_arrays(ctx, shape, ip, ix, dv, symmetric=True)
+    v = np.random.default_rng(5).standard_normal(n)
+    assert np.array_equal(A.matvec(v), M.matvec(v))
+    rhs = M.matvec(np.ones(n))
+    ref = kr.minres_solve(M, rhs)
+    assert (ref.istop, ref.itn) == (10, 74)
+    rh = np.array(ref.residHistory)
+    de = np.array(ref.dir_errors_window)
+    bnorm = np.linalg.norm(rhs)
+
+    def oracle_residual_after(itn):
+        st = kr.minres_start(M, rhs)
+        while st.itn < itn:
+            kr.minres_step(M, st)
+        return np.linalg.norm(rhs - M.matvec(st.x))
+
+    # How far the trajectory can be followed.  The Lanczos recurrence loses orthogonality on this
+    # operator: re-running the ORACLE with nothing changed but the summation order of its inner
+    # products (reversed, or in chunks of 991) moves its own history by 1e-10 at trip 40, 1e-6 at
+    # trip 45, 1e-3 at trip 49 and 1-8 % at the exit, where the truncated direct-error estimate sits
+    # within 1.5 % of etol one trip before the exit (DESIGN.md section 3).  So: per-entry agreement
+    # over the first 30 trips, the oracle's exit reason, and its exit trip +- 1.
+    saved = [ctx.get_option(o) for o in (L().KRY_OPT_MINRES_PERSISTENT, L().KRY_OPT_MINRES_FUSE)]
+    runs = {}
+    try:
+        for name, pers, fuse in (("3-launch", 0, 0), ("2-launch", 0, 1), ("persistent", 1, 0)):
+            ctx.set_option(L().KRY_OPT_MINRES_PERSISTENT, pers)
+            ctx.set_option(L().KRY_OPT_MINRES_FUSE, fuse)
+            S = dev().DeviceSolver(ctx, "minres", A)
+            S.setup(rhs, abstol=0.0, reltol=0.0, matvec_max=5 * n, rtol=1e-12, etol=1e-6, window=5)
+            st = S.run(16)
+            h = S.drain_history(st)
+            itn = int(st.n_iter)
+            assert int(st.istop) == ref.istop and abs(itn - ref.itn) <= 1, (name, st.istop, itn)
+            assert len(h) == itn and rel(h[:30, 0], rh[:30]) <= 1e-10, (name, rel(h[:30, 0], rh[:30]))
+            d = h[:, 1][~np.isnan(h[:, 1])]
+            assert len(d) == itn - 5 and rel(d[:25], de[:25]) <= 1e-10, name
+            x = S.solution()
+            res = np.linalg.norm(rhs - M.matvec(x))
+            assert abs(res - oracle_residual_after(itn)) <= RTOL_FINAL * bnorm, name     # final residual bar
+            assert np.max(np.abs(x - 1.0)) <= 1e-4                                       # exact solution: ones
+            runs[name] = (h.copy(), x.copy())
+            S._release()
+    finally:
+        ctx.set_option(L().KRY_OPT_MINRES_PERSISTENT, saved[0])
+        ctx.set_option(L().KRY_OPT_MINRES_FUSE, saved[1])
+    # the 2-launch plan only moves the w / x update between launches
+    assert rel(runs["2-launch"][0][:30, 0], runs["3-launch"][0][:30, 0]) <= 1e-12
+
+
+@pytest.mark.gpu
+def test_config4_bicgstab_convdiff_215_fullsize_follows_the_oracle(ctx):
+    """BASELINE config 4 at its full size (7-point convection-diffusion, grid 215^3, N = 9 938 375,
+    nnz = 69 291 275): the device-generated operator equals the oracle's CSR, A x and A^T x are
+    bit-exact on a random vector, and the first Bi-CGSTAB iterations follow the oracle."""
+    m = 215
+    n = m ** 3
+    ip, ix, dv = kr.convdiff3d_csr(m)
+    assert (n, len(dv)) == (9938375, 69291275)
+    M = CsrRef((n, n), ip, ix, dv)
+    A = dev().DeviceCsr.convdiff3d(ctx, m, 0.5, build_transpose=True)
+    dip, dix, ddv = A.download()
+    assert np.array_equal(dip, ip) and np.array_equal(dix, ix) and np.array_equal(ddv, dv)
+    del dip, dix, ddv
+    v = np.random.default_rng(6).standard_normal(n)
+    assert np.array_equal(A.matvec(v), M.matvec(v))
+    assert np.array_equal(A.matvec(v, trans=True), M.rmatvec(v))
+    rhs = M.matvec(np.ones(n))
+    ref = kr.bicgstab_solve(M, rhs, reltol=1e-8, matvec_max=10)
+    rh = np.array(ref.residHistory)
+    S = dev().DeviceSolver(ctx, "bicgstab", A)
+    S.setup(rhs, abstol=1e-8, reltol=1e-8, matvec_max=10)
+    st = S.run(8)
+    h = S.drain_history(st)[:, 0]
+    assert st.n_matvec == ref.nMatvec == 10
+    assert len(h) == len(rh) and np.max(np.abs(h - rh) / rh) <= 1e-10, np.max(np.abs(h - rh) / rh)
+    x = S.solution()
+    assert np.max(np.abs(x - ref.x)) <= 1e-10 * np.max(np.abs(ref.x))
+    S._release()
+    A._release()
