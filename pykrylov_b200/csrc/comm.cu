@@ -17,7 +17,7 @@
 #include <algorithm>
 #include <vector>
 
-#include "common.cuh"
+#include "solver.cuh"
 
 namespace {
 
@@ -367,6 +367,21 @@ __global__ void remap_cols_kernel(int *col, int nnz, int lo, int hi, const int *
     }
 }
 
+// edge[0] = 1 + last row of the first half that touches a halo column (c >= n_local),
+// edge[1] = first such row of the second half
+__global__ void halo_rows_kernel(const int *rowptr, const int *col, int nrows, int *edge)
+{
+    const int stride = gridDim.x * blockDim.x, half = nrows / 2;
+    for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < nrows; row += stride) {
+        bool touches = false;
+        for (int k = rowptr[row]; k < rowptr[row + 1] && !touches; ++k) touches = col[k] >= nrows;
+        if (touches) {
+            if (row < half) atomicMax(edge, row + 1);
+            else atomicMin(edge + 1, row);
+        }
+    }
+}
+
 extern "C" int kry_csr_shard_finalize(kry_csr *M, int64_t n_global, int64_t row_begin)
 {
     KRY_REQUIRE(M, KRY_ERR_INVALID, "kry_csr_shard_finalize: NULL operator");
@@ -521,6 +536,130 @@ extern "C" int kry_csr_shard_finalize(kry_csr *M, int64_t n_global, int64_t row_
         KRY_CUDA(cudaStreamSynchronize(st));
     }
     M->A.ncols = n_local + (int64_t)P * max_send;
+
+    // peer-memory halo (KRY_OPT_HALO_P2P): readers of my boundary entries, owners of my halo columns
+    h.n_to = h.n_from = 0;
+    for (int q = 0; q < P && P <= KRY_MAX_RANKS; ++q) {
+        if (q == me) continue;
+        const int *lst = all_need.data() + (size_t)q * need_pad.size();
+        bool reads_me = false;
+        for (int64_t i = 0; i < counts[q] && !reads_me; ++i) reads_me = lst[i] >= lo && lst[i] < hi;
+        if (reads_me) h.to_rank[h.n_to++] = q;
+        bool i_read = false;
+        for (size_t i = 0; i < need.size() && !i_read; ++i)
+            i_read = need[i] >= ranges[2 * q] && need[i] < ranges[2 * q + 1];
+        if (i_read) h.from_rank[h.n_from++] = q;
+    }
+    // rows that touch halo columns: [0, lo_rows) and [hi_begin, n) -- for a banded operator two thin
+    // slabs at the ends of the shard; the fused launch waits for the peers only there
+    h.lo_rows = 0;
+    h.hi_begin = (int)n_local;
+    if (n_local > 0 && nnz > 0) {
+        int *d_edge = nullptr;
+        KRY_TRY(kry_alloc((void **)&d_edge, 256));
+        const int init[2] = {0, (int)n_local};
+        KRY_CUDA(cudaMemcpyAsync(d_edge, init, sizeof(init), cudaMemcpyHostToDevice, st));
+#ifdef KRY_EMULATE
+        emu_launch<0>(c->sm_count * 8, 256, ReduceWs(), NoFin(), [&] {
+            halo_rows_kernel(M->A.rowptr, M->A.col, (int)n_local, d_edge); });
+#else
+        halo_rows_kernel<<<c->sm_count * 8, 256, 0, st>>>(M->A.rowptr, M->A.col, (int)n_local, d_edge);
+#endif
+        c->launches++;
+        int edge[2] = {0, 0};
+        KRY_CUDA(cudaMemcpyAsync(edge, d_edge, sizeof(edge), cudaMemcpyDeviceToHost, st));
+        KRY_CUDA(cudaStreamSynchronize(st));
+        cudaFree(d_edge);
+        h.lo_rows = edge[0];
+        h.hi_begin = edge[1];
+    }
     h.active = true;
     return KRY_OK;
+}
+
+// ------------------------------------------------- peer-memory halo: solver linkage
+// Collective over the ranks (every rank creates its solvers in the same order).  Each rank exports
+// its solver slab through CUDA IPC together with the layout of its vectors; every rank then
+// builds, per gathered vector, the table of remote tail slots its boundary entries go to and of
+// the flag words it signals / waits on.  Any failure on any rank leaves every rank on the
+// pack + ncclAllGather exchange.
+struct SlabInfo {
+    cudaIpcMemHandle_t handle;
+    int64_t            n_local, max_send, total;
+    int64_t            voff[16];      // offset of vector i in the slab, in doubles
+};
+
+int kry_halo_link(kry_solver *S)
+{
+    kry_ctx *c = S->ctx;
+    const HaloPlan &hp = S->A->halo;
+    const int P = c->nranks, me = c->rank;
+    S->halo_linked = false;
+    if (!S->sharded || !c->p2p_inbox || P > KRY_MAX_RANKS) return KRY_OK;
+    KRY_CUDA(cudaSetDevice(c->device));
+    const double magic = 424242.0 + me;
+    KRY_CUDA(cudaMemcpyAsync(S->slab + S->slab_doubles, &magic, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    KRY_CUDA(cudaStreamSynchronize(c->stream));
+    SlabInfo mine;
+    memset(&mine, 0, sizeof(mine));
+    int ok = cudaIpcGetMemHandle(&mine.handle, S->slab) == cudaSuccess;
+    cudaGetLastError();
+    mine.n_local = S->n;
+    mine.max_send = hp.max_send;
+    mine.total = S->slab_doubles;
+    for (int i = 0; i < S->nvecs; ++i) mine.voff[i] = S->vecs[i].d - S->slab;
+    std::vector<SlabInfo> all((size_t)P);
+    KRY_TRY(kry_comm_allgather_host(c, &mine, all.data(), sizeof(mine)));
+    for (int k = 0; k < hp.n_to && ok; ++k) {
+        const int q = hp.to_rank[k];
+        void *ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, all[q].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            ok = 0;
+            break;
+        }
+        S->peer_slab[q] = ptr;
+        double seen = 0.0;                      // does the mapping address rank q's slab?
+        if (cudaMemcpy(&seen, (double *)ptr + all[q].total, sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess ||
+            seen != 424242.0 + q || all[q].max_send != hp.max_send) {
+            cudaGetLastError();
+            ok = 0;
+        }
+    }
+    double mm[2] = {ok ? 1.0 : 0.0, ok ? -1.0 : 0.0};
+    KRY_TRY(kry_comm_allreduce_host(c, mm, 2, 1));            // max(ok), max(-ok) = -min(ok)
+    if (-mm[1] < 1.0) {
+        kry_halo_unlink(S);
+        return KRY_OK;                                        // every rank stays on the NCCL exchange
+    }
+    std::vector<HaloTable> tbl((size_t)S->nvecs);
+    memset(tbl.data(), 0, tbl.size() * sizeof(HaloTable));
+    unsigned long long *my_flags = reinterpret_cast<unsigned long long *>(c->p2p_inbox + KRY_HALO_FLAG_OFFSET);
+    for (int i = 0; i < S->nvecs; ++i) {
+        HaloTable &T = tbl[(size_t)i];
+        T.n_to = hp.n_to;
+        T.n_from = hp.n_from;
+        for (int k = 0; k < hp.n_to; ++k) {
+            const int q = hp.to_rank[k];
+            T.to_tail[k] = (double *)S->peer_slab[q] + all[q].voff[i] + all[q].n_local + (int64_t)me * hp.max_send;
+            T.to_flag[k] = reinterpret_cast<unsigned long long *>((double *)c->p2p_peer_ptr[q] + KRY_HALO_FLAG_OFFSET) + 8 * me;
+        }
+        for (int k = 0; k < hp.n_from; ++k) T.from_flag[k] = my_flags + 8 * hp.from_rank[k];
+    }
+    KRY_TRY(kry_alloc((void **)&S->halo_tbl, tbl.size() * sizeof(HaloTable)));
+    KRY_CUDA(cudaMemcpy(S->halo_tbl, tbl.data(), tbl.size() * sizeof(HaloTable), cudaMemcpyHostToDevice));
+    S->halo_linked = true;
+    return KRY_OK;
+}
+
+void kry_halo_unlink(kry_solver *S)
+{
+    for (int q = 0; q < KRY_MAX_RANKS; ++q) {
+        if (S->peer_slab[q]) cudaIpcCloseMemHandle(S->peer_slab[q]);
+        S->peer_slab[q] = nullptr;
+    }
+    if (S->halo_tbl) cudaFree(S->halo_tbl);
+    S->halo_tbl = nullptr;
+    S->halo_linked = false;
+    cudaGetLastError();
 }

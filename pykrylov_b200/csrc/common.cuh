@@ -50,6 +50,8 @@ void kry_set_error(const char *fmt, ...);
 
 // ---------------------------------------------------------------- handles
 constexpr int KRY_MAX_DOTS = 4;
+constexpr int KRY_MAX_RANKS = 16;   // one NVSwitch domain
+constexpr int KRY_HALO_FLAG_OFFSET = 1024;   // doubles into the inbox allocation: flag of source rank q at +8q
 
 struct ReduceWs {
     double   *partials;   // [KRY_MAX_DOTS][stride] one partial per CTA
@@ -89,6 +91,7 @@ struct kry_ctx {
     double            **p2p_peers_dev;
     unsigned long long *p2p_seq;
     void               *p2p_peer_ptr[16];
+    unsigned long long  halo_seq;  // tag of the last fused halo exchange (host counter, same on every rank)
     int          l2_hints;     // bit 0: CG vector kernels use L2 eviction-priority hints (default 1)
     int          use_graphs;   // 1: solver loops replay CUDA graphs of 12 iterations (default)
     int          cg_fuse;      // KRY_OPT_CG_FUSE: CG launch plan (0: 3 launches, 1/2: fused 2-launch forms)
@@ -128,6 +131,32 @@ struct HaloPlan {                // 1-D row sharding
     int      max_send = 0;       // padded per-rank slot in the all-gather
     int     *send_idx = nullptr; // local indices to pack
     double  *send_buf = nullptr; // [max_send]
+    // peer-memory halo (KRY_OPT_HALO_P2P): who reads my boundary entries, whose entries I read,
+    // and the row order that puts the rows touching halo columns last
+    int      n_to = 0, n_from = 0;
+    int      to_rank[KRY_MAX_RANKS], from_rank[KRY_MAX_RANKS];
+    int      lo_rows = 0;        // rows [0, lo_rows) and [hi_begin, nrows) may touch halo columns,
+    int      hi_begin = 0;       // the rows in between do not
+};
+
+// Per gathered vector of a solver (device memory): where this rank's boundary entries land in
+// each reader's copy of that vector, and the arrival flags (one 64-bit tag per directed pair of
+// ranks, living in the IPC-mapped inbox allocation of the reader).
+struct HaloTable {
+    int                       n_to, n_from;
+    double                   *to_tail[KRY_MAX_RANKS];     // reader q's tail slot for my entries
+    unsigned long long       *to_flag[KRY_MAX_RANKS];     // reader q's flag word for me
+    const unsigned long long *from_flag[KRY_MAX_RANKS];   // my flag words for the ranks I read from
+};
+
+struct HaloArgs {                // by value into the sharded SpMV launch
+    const HaloTable   *tbl;
+    const int         *send_idx;
+    int                n_send, push_ctas;
+    unsigned          *ticket;   // self-resetting retirement ticket of the push CTAs
+    unsigned long long tag;      // monotonic per context, identical on every rank
+    int                lo_rows, hi_begin;
+    int                skip_push;   // tests/emu fast mode only: the launcher has played the push
 };
 
 struct kry_csr {

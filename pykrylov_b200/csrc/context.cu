@@ -75,6 +75,8 @@ extern "C" int kry_ctx_create(int device, kry_ctx **out)
                            // (form 1) and 0.249 (form 0) -- profiles/r1b_ab_cgfuse*.json, r1_final_bench_n1.json
     c->cg_fuse_shards = 1; // row shards use the same plan: 2 x B200, 10^8 rows: 825.7 vs 803.8 it/s with the same
                            // residual bits (profiles/r1e_*); 2-8 emulated ranks: tests/test_emulated_multi_rank.py
+    c->halo_p2p = 1;       // row shards: boundary entries travel through peer memory from inside the SpMV launch
+                           // (takes effect where the CUDA IPC mappings of kry_comm_init / kry_halo_link succeeded)
     KRY_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     KRY_CUDA(cudaEventCreate(&c->ev0));
     KRY_CUDA(cudaEventCreate(&c->ev1));

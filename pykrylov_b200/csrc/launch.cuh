@@ -164,6 +164,85 @@ int spmv_launch(kry_csr *M, bool trans, Gather g, Epi epi, Fin fin, const int *d
     return KRY_OK;
 }
 
+// Row shards, KRY_OPT_HALO_P2P: the halo exchange rides in the SpMV launch (spmv.cuh,
+// spmv_row_shard_kernel).  `tbl` is the device table of the gathered vector (solver.cuh); the
+// fused inner products are all-reduced in-kernel over the same peer mapping.  Every rank issues
+// the same sequence of these launches, so the host-side tag counter agrees everywhere.
+static inline bool spmv_shard_fusable(const kry_csr *M)
+{
+    int kind = M->kind;
+    if (kind == KRY_SPMV_AUTO) kind = (M->A.max_row <= 64) ? KRY_SPMV_ROW : KRY_SPMV_STREAM;
+    return kind == KRY_SPMV_ROW && M->ctx->p2p_on && M->ctx->halo_p2p && M->halo.active;
+}
+
+template <int ND, class Gather, class Epi, class Fin>
+int spmv_shard_launch(kry_csr *M, Gather g, Epi epi, Fin fin, const int *done, const HaloTable *tbl)
+{
+    static_assert(ND > 0, "the in-kernel all-reduce at the end of the launch is what orders the exchanges");
+    kry_ctx *c = M->ctx;
+    CsrDev *m = &M->A;
+    const HaloPlan &hp = M->halo;
+    int64_t need = (m->nrows + 255) / 256;
+    if (need < 1) need = 1;
+    static int occ = 0;              // per instantiation
+    if (occ == 0) {
+        int b = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, spmv_row_shard_kernel<ND, Gather, Epi, Fin>, 256, 0) !=
+                cudaSuccess || b < 1)
+            b = 8;
+        occ = b < 8 ? b : 8;
+    }
+    const int64_t capg = (int64_t)c->sm_count * occ;       // one resident wave: the push CTAs and the
+    const int grid = (int)(need < capg ? need : capg);     // waiting CTAs must be co-resident
+    KRY_TRY(kry_ctx_ensure_partials(c, grid));
+    ReduceWs ws = kry_ws(c);
+    ws.defer = 0;
+    ws.p2p = 1;
+    CsrView A = csr_view(*m);
+    HaloArgs h;
+    h.tbl = tbl;
+    h.send_idx = hp.send_idx;
+    h.n_send = hp.n_send;
+    h.push_ctas = (hp.n_send + 255) / 256;
+    if (h.push_ctas > grid) h.push_ctas = grid;
+    h.ticket = c->counter + 24;                             // inside the zeroed 256-byte counter block
+    h.tag = ++c->halo_seq;
+    h.lo_rows = hp.lo_rows;
+    h.hi_begin = hp.hi_begin;
+    h.skip_push = 0;
+    const bool prof = c->prof_ev && c->prof_n < c->prof_cap;
+    if (prof) KRY_CUDA(cudaEventRecord(c->prof_ev[2 * c->prof_n], c->stream));
+#ifdef KRY_EMULATE
+    if (emu_fibers_on) {
+        // SIMT mode: all blocks alive at once (a block that waits for a peer's flag must not keep
+        // this rank's later push blocks from running)
+        auto body = [&] { spmv_row_shard_kernel<ND, Gather, Epi, Fin>(A, g, epi, ws, fin, done, h); };
+        emu_launch_fibers_mode(grid, 256, &body, [](const void *k) { (*static_cast<const decltype(body) *>(k))(); }, 1);
+    } else {
+        // fast mode plays the threads one after the other: the push (all of it, then the flags) is
+        // played first by the launcher with the kernel's own device function
+        if (!*done) {
+            Gather g0 = g;
+            g0.init();
+            gridDim = EmuDim{(unsigned)grid, 1, 1};
+            blockDim = EmuDim{256, 1, 1};
+            emu_halo_push_all(h, g0);
+        }
+        h.skip_push = 1;
+        emu_launch<ND>(grid, 256, ws, fin, [&] { spmv_row_shard_kernel<ND, Gather, Epi, Fin>(A, g, epi, ws, fin, done, h); });
+    }
+#else
+    spmv_row_shard_kernel<ND, Gather, Epi, Fin><<<grid, 256, 0, c->stream>>>(A, g, epi, ws, fin, done, h);
+#endif
+    if (prof) {
+        KRY_CUDA(cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], c->stream));
+        c->prof_n++;
+    }
+    c->launches++;
+    KRY_CUDA(cudaGetLastError());
+    return KRY_OK;
+}
+
 template <int ND, class Body, class Fin>
 int vec_pass_launch(kry_ctx *c, int64_t n, Body body, Fin fin, const int *done, int defer)
 {

@@ -77,6 +77,12 @@ struct kry_solver {
     kry_solver_params params;
     bool              ready;
     bool              sharded;
+    // peer-memory halo (KRY_OPT_HALO_P2P, comm.cu kry_halo_link): the peers' solver slabs are mapped
+    // through CUDA IPC; halo_tbl[i] says where vector i's boundary entries land in each reader
+    bool              halo_linked;
+    HaloTable        *halo_tbl;                 // device, one per vector of the solver
+    void             *peer_slab[KRY_MAX_RANKS];
+    int64_t           slab_doubles;             // vectors + preconditioner diagonal (a magic word sits behind)
     // CUDA-graph replay of KRY_GRAPH_ITERS iterations (launch-latency bound problems)
     cudaGraphExec_t   graph_exec;
     int64_t           graph_launches;   // kernel launches inside one replay
@@ -103,6 +109,17 @@ static inline double *solver_vec(kry_solver *S, const char *name)
 }
 
 int kry_allreduce_sums(kry_ctx *c, int n);
+int kry_halo_link(kry_solver *S);       // comm.cu: collective over the ranks, at kry_solver_create
+void kry_halo_unlink(kry_solver *S);
+
+// table of the gathered vector `x_dev`, or nullptr when the fused exchange does not apply
+static inline const HaloTable *solver_halo_table(kry_solver *S, const double *x_dev)
+{
+    if (!S->halo_linked || !spmv_shard_fusable(S->A)) return nullptr;
+    for (int i = 0; i < S->nvecs; ++i)
+        if (S->vecs[i].d == x_dev) return S->halo_tbl + i;
+    return nullptr;
+}
 
 #if defined(__CUDACC__) || defined(KRY_EMULATE)
 // append one history entry (width doubles)
@@ -120,7 +137,12 @@ template <int ND, class Gather, class Epi, class Fin>
 int solver_spmv(kry_solver *S, Gather g, Epi e, Fin f, const int *done, double *x_dev)
 {
     if (S->sharded) {
-        if (x_dev) KRY_TRY(kry_halo_exchange(S->A, x_dev));     // nullptr: the caller did the exchange
+        if (x_dev) {
+            // halo exchange fused into the launch (peer-memory stores + flags), or pack + ncclAllGather
+            if (const HaloTable *tbl = solver_halo_table(S, x_dev))
+                return spmv_shard_launch<ND>(S->A, HaloGather<Gather>{g, (int)S->n}, e, f, done, tbl);
+            KRY_TRY(kry_halo_exchange(S->A, x_dev));
+        }                                                       // nullptr: the caller did the exchange
         if (S->ctx->p2p_on) return spmv_launch<ND>(S->A, false, g, e, f, done, 2);   // in-kernel all-reduce
         KRY_TRY((spmv_launch<ND>(S->A, false, g, e, f, done, 1)));
         KRY_TRY(kry_allreduce_sums(S->ctx, ND));

@@ -201,16 +201,24 @@ struct CgGatherDir {
     __device__ void   init() { beta = s->s[S_BETA]; }
     __device__ double operator()(int c) const
     {
+        if constexpr (SHARD) {
+            if (c >= n_local) return __ldcg(p_old + c);     // halo entry: may have been written by a peer
+        }                                                   // GPU during this launch -- read at the L2
         const double po = __ldg(p_old + c);
         if constexpr (PEND) {
-            if constexpr (SHARD) {
-                if (c >= n_local) return po;
-            }
             return __dsub_rn(__dmul_rn(beta, po), __ldg(r + c));                   // cg.py:150-151
         } else {
             return po;
         }
     }
+    // what this rank publishes for its boundary entry j (spmv_row_shard_kernel): the updated
+    // direction, same two rounded operations as everywhere else
+    __device__ double boundary(int j) const
+    {
+        if constexpr (PEND) return __dsub_rn(__dmul_rn(beta, p_old[j]), r[j]);
+        else return p_old[j];
+    }
+    __device__ double halo(int c) const { return __ldcg(p_old + c); }
 };
 
 template <bool PEND, bool XLAG>
@@ -407,8 +415,10 @@ static int cg_fused_spmv(kry_solver *S, double *p_old, double *p_new, int opt)
     CgEpiFused<PEND, XLAG> e{Ap, p_new, x, p_old, r, S->ds, opt & 5, 0.0, 0.0, 0, 0};
     if (S->sharded) {
         // boundary entries of p travel already updated; the local ones are updated in the gather
-        KRY_TRY(kry_halo_exchange_dir(S->A, p_old, PEND ? r : nullptr, PEND ? &S->ds->s[S_BETA] : nullptr));
         CgGatherDir<PEND, true> g{p_old, r, S->ds, 0.0, (int)S->n};
+        if (const HaloTable *tbl = solver_halo_table(S, p_old))      // exchange fused into the launch
+            return spmv_shard_launch<1>(S->A, g, e, CgFinApFused{S->ds}, &S->ds->done, tbl);
+        KRY_TRY(kry_halo_exchange_dir(S->A, p_old, PEND ? r : nullptr, PEND ? &S->ds->s[S_BETA] : nullptr));
         return solver_spmv<1>(S, g, e, CgFinApFused{S->ds}, &S->ds->done, nullptr);
     }
     CgGatherDir<PEND> g{p_old, r, S->ds, 0.0, 0};
@@ -1336,6 +1346,8 @@ struct MinGather {            // x[c] * (1/beta): v = s*y with s = 1.0/beta, min
     double        inv;
     __device__ void   init() { inv = 1.0 / s->s[M_BETA]; }
     __device__ double operator()(int c) const { return __dmul_rn(inv, __ldg(y + c)); }
+    __device__ double boundary(int j) const { return y[j]; }
+    __device__ double halo(int c) const { return __dmul_rn(inv, __ldcg(y + c)); }
 };
 
 struct MinEpiY {
@@ -2007,7 +2019,12 @@ extern "C" int kry_solver_create(kry_ctx *c, kry_method method, kry_csr *A, kry_
     int64_t total = 0;
     for (int i = 0; i < nv; ++i) total += pad(specs[i].gathered ? S->ncap : n);
     total += pad(n);   // preconditioner diagonal
-    int rc = kry_alloc((void **)&S->slab, (size_t)total * sizeof(double));
+    S->slab_doubles = total;
+    // shards: the slab is mapped into the peers (kry_halo_link) -- it gets a driver allocation of its
+    // own (>= 4 MiB, never a sub-allocation) and a magic word behind the vectors to verify the mapping
+    size_t slab_bytes = (size_t)(total + 32) * sizeof(double);
+    if (S->sharded && slab_bytes < ((size_t)4 << 20)) slab_bytes = (size_t)4 << 20;
+    int rc = kry_alloc((void **)&S->slab, slab_bytes);
     if (rc == KRY_OK) rc = kry_alloc((void **)&S->ds, sizeof(DevScalars));
     if (rc == KRY_OK)
         rc = kry_alloc((void **)&S->hist, (size_t)KRY_HIST_CAP * S->hist_width * sizeof(double));
@@ -2030,6 +2047,14 @@ extern "C" int kry_solver_create(kry_ctx *c, kry_method method, kry_csr *A, kry_
     S->dinv = S->slab + off;
     S->precon_mode = 0;
     kry_ctx_retain(c);
+    if (S->sharded && c->p2p_inbox) {
+        // best effort and collective: without the mapping the pack + ncclAllGather exchange stays in use
+        rc = kry_halo_link(S);
+        if (rc != KRY_OK) {
+            kry_solver_destroy(S);
+            return rc;
+        }
+    }
     *out = S;
     return KRY_OK;
 }
@@ -2045,6 +2070,7 @@ extern "C" int kry_solver_destroy(kry_solver *S)
             cudaFreeHost(S->snap_host[k]);
         }
     }
+    kry_halo_unlink(S);
     cudaFree(S->slab);
     cudaFree(S->ds);
     cudaFree(S->hist);

@@ -47,10 +47,19 @@ static inline CsrView csr_view(const CsrDev &m)
 
 #if defined(__CUDACC__) || defined(KRY_EMULATE)
 
+// Besides operator()(col) every gather functor states, for the sharded launch with the halo
+// exchange fused in (spmv_row_shard_kernel):
+//   boundary(j)  what this rank publishes for its local entry j -- the raw vector entry, such
+//                that the reader's halo(c) of the column it lands in gives operator()'s value;
+//   halo(c)      operator() for a halo column (c >= n_local): the entry was written by a peer
+//                GPU while this kernel may already be running, so it is read at the L2
+//                (ld.global.cg), never through the non-coherent L1 path of __ldg.
 struct GatherPlain {
     const double *x;
     __device__ void   init() {}
     __device__ double operator()(int c) const { return __ldg(x + c); }
+    __device__ double boundary(int j) const { return x[j]; }
+    __device__ double halo(int c) const { return __ldcg(x + c); }
 };
 
 // x[c] * s with s read from device memory (MINRES: v = (1/beta) * y on the fly)
@@ -60,6 +69,18 @@ struct GatherScaled {
     double        s;
     __device__ void   init() { s = *s_ptr; }
     __device__ double operator()(int c) const { return __dmul_rn(s, __ldg(x + c)); }
+    __device__ double boundary(int j) const { return x[j]; }
+    __device__ double halo(int c) const { return __dmul_rn(s, __ldcg(x + c)); }
+};
+
+// Halo-aware view of a gather for row shards: columns below n_local are this rank's own entries.
+template <class G>
+struct HaloGather {
+    G   g;
+    int n_local;
+    __device__ void   init() { g.init(); }
+    __device__ double operator()(int c) const { return c < n_local ? g(c) : g.halo(c); }
+    __device__ double boundary(int j) const { return g.boundary(j); }
 };
 
 // ------------------------------------------------------------ thread per row
@@ -172,6 +193,120 @@ spmv_rowpf_kernel(CsrView A, Gather g, Epi epi, ReduceWs ws, Fin fin, const int 
             s1 = s2;
             e1 = e2;
         }
+    }
+    if constexpr (ND > 0) block_reduce_finalize<ND>(acc, ws, fin);
+}
+
+// ------------------------------------- thread per row, halo exchange fused in
+// Row shards with KRY_OPT_HALO_P2P: ONE launch does the exchange of the boundary entries and
+// the SpMV (+ epilogue + fused inner products + in-kernel all-reduce).
+//   1. The first `push_ctas` CTAs store this rank's boundary entries g.boundary(send_idx[i])
+//      straight into the halo tails of the ranks that read them, over NVLink peer memory
+//      (CUDA IPC mapping of the readers' solver slabs); the CTA that finishes the push last
+//      publishes the launch's tag in every reader's flag word (system-scope fence in between).
+//   2. All CTAs walk their rows exactly as spmv_row_kernel does.  Rows that may touch a halo
+//      column sit in the first lo_rows and from hi_begin on (found at kry_csr_shard_finalize;
+//      for a banded operator: two thin slabs): the interior of the shard is multiplied while
+//      the peers' entries are in flight.
+//   3. A thread waits, right before the first such row it owns, until every rank it reads from
+//      has published this tag; halo columns are then read at the L2 (Gather::halo).
+// Ordering argument (why a tail is never overwritten while it is still being read, and why no
+// wait can be circular): DESIGN.md section 6.  No pack launch, no ncclAllGather.
+__device__ __forceinline__ unsigned long long ld_flag(const unsigned long long *p)
+{
+    return *reinterpret_cast<const volatile unsigned long long *>(p);
+}
+
+template <class Gather>
+__device__ __forceinline__ void halo_push_entries(const HaloArgs &h, const Gather &g)
+{
+    const HaloTable *T = h.tbl;
+    const int n_to = T->n_to;
+    // the LAST push_ctas CTAs publish (the first ones own the leading boundary rows and wait first)
+    for (int i = (gridDim.x - 1 - blockIdx.x) * blockDim.x + threadIdx.x; i < h.n_send; i += h.push_ctas * blockDim.x) {
+        const double v = g.boundary(__ldg(h.send_idx + i));
+        for (int q = 0; q < n_to; ++q) T->to_tail[q][i] = v;
+    }
+}
+
+__device__ __forceinline__ void halo_publish(const HaloArgs &h)
+{
+    const HaloTable *T = h.tbl;
+    __threadfence_system();
+    for (int q = 0; q < T->n_to; ++q)
+        *reinterpret_cast<volatile unsigned long long *>(T->to_flag[q]) = h.tag;
+}
+
+template <class Gather>
+__device__ __forceinline__ void halo_push(const HaloArgs &h, const Gather &g)
+{
+    if ((int)(gridDim.x - 1 - blockIdx.x) >= h.push_ctas) return;
+    halo_push_entries(h, g);
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned ticket = atomicAdd(h.ticket, 1u);
+        if (ticket == (unsigned)h.push_ctas - 1u) {
+            *h.ticket = 0u;
+            halo_publish(h);
+        }
+    }
+}
+
+#ifdef KRY_EMULATE
+// tests/emu, fast mode (threads played one after the other): the launcher plays the whole push
+// -- every entry, then the flags -- before the row loops
+template <class Gather>
+static inline void emu_halo_push_all(const HaloArgs &h, const Gather &g)
+{
+    for (int b = 0; b < h.push_ctas; ++b)
+        for (int t = 0; t < 256; ++t) {
+            blockIdx = EmuDim{gridDim.x - 1 - (unsigned)b, 0, 0};
+            threadIdx = EmuDim{(unsigned)t, 0, 0};
+            halo_push_entries(h, g);
+        }
+    if (h.push_ctas > 0) halo_publish(h);
+}
+#endif
+
+__device__ __forceinline__ void halo_wait(const HaloArgs &h)
+{
+    const HaloTable *T = h.tbl;
+    for (int q = 0; q < T->n_from; ++q)
+        while (ld_flag(T->from_flag[q]) < h.tag) __nanosleep(20);
+    __threadfence_system();
+}
+
+template <int ND, class Gather, class Epi, class Fin>
+__global__ void __launch_bounds__(256, epi_min_blocks<Epi>::value)
+spmv_row_shard_kernel(CsrView A, Gather g, Epi epi, ReduceWs ws, Fin fin, const int *done, HaloArgs h)
+{
+    if (*done) return;
+    g.init();
+    epi.init();
+    if (!h.skip_push) halo_push(h, g);
+    double acc[ND > 0 ? ND : 1];
+#pragma unroll
+    for (int d = 0; d < (ND > 0 ? ND : 1); ++d) acc[d] = 0.0;
+    const int stride = gridDim.x * blockDim.x;
+    auto one_row = [&](int row) {
+        const int s = __ldg(A.rowptr + row), e = __ldg(A.rowptr + row + 1);
+        double sum = 0.0;
+        for (int k = s; k < e; ++k)
+            sum = __dadd_rn(sum, __dmul_rn(__ldg(A.val + k), g(__ldg(A.col + k))));
+        epi(row, sum, acc);
+    };
+    // same row -> thread mapping and the same order as spmv_row_kernel, so the fused inner
+    // products are the same bits whichever way the halo travelled; a thread waits for the peers'
+    // entries right before the first row it owns that may touch a halo column
+    const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    int row = t0;
+    const int hi = h.hi_begin < A.nrows ? h.hi_begin : A.nrows;
+    if (row < h.lo_rows && row < A.nrows) halo_wait(h);
+    for (; row < hi; row += stride) one_row(row);
+    if (row < A.nrows) {
+        if (t0 >= h.lo_rows) halo_wait(h);
+        for (; row < A.nrows; row += stride) one_row(row);
     }
     if constexpr (ND > 0) block_reduce_finalize<ND>(acc, ws, fin);
 }

@@ -301,6 +301,7 @@ extern "C" int kry_ctx_create(int device, kry_ctx **out)
     c->use_graphs = 0;
     c->cg_fuse = 2;
     c->cg_fuse_shards = 1;
+    c->halo_p2p = 1;
 #ifdef KRY_OPT_MINRES_FUSE
     c->minres_fuse = 1;
 #endif

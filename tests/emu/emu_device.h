@@ -32,6 +32,8 @@ static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __ddiv_rn(double a, double b) { return a / b; }
 template <class T>
 static inline T __ldg(const T *p) { return *p; }
+template <class T>
+static inline T __ldcg(const T *p) { return *reinterpret_cast<const volatile T *>(p); }
 
 // ---- L2 hint helpers of common.cuh: plain accesses
 static inline uint64_t l2_policy_evict_first() { return 0; }
@@ -67,6 +69,7 @@ void emu_spin_wait();
 static inline void __nanosleep(unsigned) { emu_spin_wait(); }
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { const unsigned o = *p; *p = o + v; return o; }
 static inline int atomicMax(int *p, int v) { const int o = *p; if (v > o) *p = v; return o; }
+static inline int atomicMin(int *p, int v) { const int o = *p; if (v < o) *p = v; return o; }
 
 template <class T>
 static inline T __shfl_xor_sync(unsigned, T v, int lane_mask)

@@ -101,7 +101,7 @@ def _sharded_cg(L, world):
                     assert np.max(np.abs(xs - ref.x[lo:hi])) <= 1e-9
                     same = ctx.allgather_bytes(np.array([st.resid_norm]).tobytes())
                     assert len(set(same)) == 1                       # identical scalars on every rank
-                    runs[(p2p, fuse_shards, form)] = (hist.copy(), xs.copy(), S.get_vector("r"))
+                    runs[(p2p, fuse_shards, form)] = (hist.copy(), xs.copy(), S.get_vector("r"), S.get_vector("p"))
             base = runs[(1, 0, 0)]
             for key, val in runs.items():                            # plans / reduce paths: same bits
                 for a, b in zip(base, val):
@@ -121,6 +121,19 @@ def _sharded_cg(L, world):
             assert np.array_equal(x5, S0.solution()) and np.array_equal(p5, S0.get_vector("p"))
             S0.iterate(4)
             assert np.array_equal(S.solution(), S0.solution()) and np.array_equal(S.get_vector("p"), S0.get_vector("p"))
+            # the halo exchange rides in the SpMV launch (KRY_OPT_HALO_P2P): 2 launches per trip,
+            # against pack kernel + ncclAllGather + 2 launches with the option off
+            per_trip = {}
+            for halo_p2p in (1, 0):
+                ctx.set_option(L.KRY_OPT_CG_FUSE_SHARDS, 1)
+                ctx.set_option(L.KRY_OPT_HALO_P2P, halo_p2p)
+                S.setup(rhs[lo:hi], matvec_max=2 * n)
+                S.iterate(2)
+                l0 = ctx.launch_count()
+                S.iterate(4)
+                per_trip[halo_p2p] = (ctx.launch_count() - l0) / 4
+            assert per_trip == {1: 2, 0: 3}, per_trip
+            ctx.set_option(L.KRY_OPT_HALO_P2P, 1)
             res["max_send"] = A.shape[1] - A.shape[0]
             ctx.barrier()
         finally:
