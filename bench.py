@@ -355,6 +355,12 @@ def main_ours(args):
     ms_prof, _, prof, S2, _ = time_device_resident(ctx, A, rhs, args.steps, args.warmup, profile=True)
     S2._release()
     value = args.steps / (ms / 1e3)
+    if os.environ.get("KRY_HALO_TRACE") and world > 1:
+        t = ctx.halo_trace()
+        print("[halo trace rank %d] launches %d: publish-entry %.1f us | waiting warps/launch %.0f: spin %.2f us, "
+              "fence %.2f us, wait starts %.1f us after entry, latest end %.1f us after entry"
+              % (rank, t[1], t[0] / max(t[1], 1) / 1e3, t[4] / max(t[1], 1), t[2] / max(t[4], 1) / 1e3,
+                 t[3] / max(t[4], 1) / 1e3, t[6] / max(t[4], 1) / 1e3, t[5] / 1e3), file=sys.stderr)
 
     # roofline of the dominant kernel (fused SpMV+dot), from per-launch CUDA events
     peak, peak_src = measured_peak()

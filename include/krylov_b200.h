@@ -66,6 +66,12 @@ int kry_timer_stop(kry_ctx *ctx, double *elapsed_ms); /* synchronises           
 int kry_flush_l2(kry_ctx *ctx);
 /* Number of kernels this library has launched on this context so far.               */
 int kry_launch_count(kry_ctx *ctx, int64_t *count);
+/* Diagnostics of the halo exchange fused into the sharded SpMV launch: with KRY_HALO_TRACE set in
+ * the environment when the context is created, the kernels accumulate %globaltimer intervals (ns):
+ * out[0] sum over launches of (flags published - kernel entry), out[1] launches, out[2] sum of the
+ * spin time and out[3] of the fence time over waiting warps, out[4] waiting warps, out[5] max
+ * (end of wait - kernel entry), out[6] sum (start of wait - kernel entry).  Reading resets them. */
+int kry_halo_trace_read(kry_ctx *ctx, uint64_t *out16);
 /* Per-kernel device timing of the dominant kernel (the fused SpMV+dot of the solver
  * loops): when enabled, every such launch is bracketed by a CUDA event pair on the
  * context's stream (up to max_samples launches; 0 disables).  kry_prof_read

@@ -82,6 +82,7 @@ PROTOTYPES = {
     "kry_timer_stop": (C.c_int, [handle, c_f64p]),
     "kry_flush_l2": (C.c_int, [handle]),
     "kry_launch_count": (C.c_int, [handle, c_i64p]),
+    "kry_halo_trace_read": (C.c_int, [handle, C.POINTER(C.c_uint64)]),
     "kry_ctx_set_option": (C.c_int, [handle, C.c_int, C.c_int]),
     "kry_ctx_get_option": (C.c_int, [handle, C.c_int, C.POINTER(C.c_int)]),
     "kry_prof_enable": (C.c_int, [handle, C.c_int]),

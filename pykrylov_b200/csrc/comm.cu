@@ -550,10 +550,10 @@ extern "C" int kry_csr_shard_finalize(kry_csr *M, int64_t n_global, int64_t row_
             i_read = need[i] >= ranges[2 * q] && need[i] < ranges[2 * q + 1];
         if (i_read) h.from_rank[h.n_from++] = q;
     }
-    // rows that touch halo columns: [0, lo_rows) and [hi_begin, n) -- for a banded operator two thin
-    // slabs at the ends of the shard; the fused launch waits for the peers only there
-    h.lo_rows = 0;
-    h.hi_begin = (int)n_local;
+    // rows that touch halo columns: for a banded operator two thin slabs at the ends of the shard; the
+    // sharded launch walks the rows in between first (rot / v_wait) and waits for the peers only then
+    h.rot = 0;
+    h.v_wait = (int)n_local;
     if (n_local > 0 && nnz > 0) {
         int *d_edge = nullptr;
         KRY_TRY(kry_alloc((void **)&d_edge, 256));
@@ -570,8 +570,11 @@ extern "C" int kry_csr_shard_finalize(kry_csr *M, int64_t n_global, int64_t row_
         KRY_CUDA(cudaMemcpyAsync(edge, d_edge, sizeof(edge), cudaMemcpyDeviceToHost, st));
         KRY_CUDA(cudaStreamSynchronize(st));
         cudaFree(d_edge);
-        h.lo_rows = edge[0];
-        h.hi_begin = edge[1];
+        // lo = edge[0] leading and n - edge[1] trailing rows may touch halo columns: the launch walks
+        // rows [lo, edge[1]) first, then the trailing and (wrapped around) the leading slab
+        h.rot = edge[0];
+        h.v_wait = edge[1] - edge[0];
+        if (h.v_wait < 0) { h.rot = 0; h.v_wait = 0; }
     }
     h.active = true;
     return KRY_OK;

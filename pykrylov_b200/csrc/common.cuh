@@ -91,6 +91,7 @@ struct kry_ctx {
     double            **p2p_peers_dev;
     unsigned long long *p2p_seq;
     void               *p2p_peer_ptr[16];
+    unsigned long long *halo_trace; // device [16], KRY_HALO_TRACE only
     unsigned long long  halo_seq;  // tag of the last fused halo exchange (host counter, same on every rank)
     int          l2_hints;     // bit 0: CG vector kernels use L2 eviction-priority hints (default 1)
     int          use_graphs;   // 1: solver loops replay CUDA graphs of 12 iterations (default)
@@ -135,8 +136,8 @@ struct HaloPlan {                // 1-D row sharding
     // and the row order that puts the rows touching halo columns last
     int      n_to = 0, n_from = 0;
     int      to_rank[KRY_MAX_RANKS], from_rank[KRY_MAX_RANKS];
-    int      lo_rows = 0;        // rows [0, lo_rows) and [hi_begin, nrows) may touch halo columns,
-    int      hi_begin = 0;       // the rows in between do not
+    int      rot = 0;            // virtual row v maps to row (v + rot) mod nrows ...
+    int      v_wait = 0;         // ... and only rows with v >= v_wait may touch halo columns
 };
 
 // Per gathered vector of a solver (device memory): where this rank's boundary entries land in
@@ -155,8 +156,10 @@ struct HaloArgs {                // by value into the sharded SpMV launch
     int                n_send, push_ctas;
     unsigned          *ticket;   // self-resetting retirement ticket of the push CTAs
     unsigned long long tag;      // monotonic per context, identical on every rank
-    int                lo_rows, hi_begin;
-    int                skip_push;   // tests/emu fast mode only: the launcher has played the push
+    int                rot, v_wait;
+    int                skip_push;   // bit 0: no push (the entries travelled by ncclAllGather, or tests/emu played
+                                    // the push in the launcher); bit 1: no wait
+    unsigned long long *trace;      // optional (KRY_HALO_TRACE): in-kernel %globaltimer statistics, see kry_halo_trace_read
 };
 
 struct kry_csr {

@@ -88,6 +88,10 @@ extern "C" int kry_ctx_create(int device, kry_ctx **out)
     KRY_TRY(kry_alloc((void **)&c->never_done, 256));
     KRY_CUDA(cudaMemsetAsync(c->never_done, 0, 256, c->stream));
     KRY_TRY(kry_ctx_ensure_partials(c, 16384));
+    if (getenv("KRY_HALO_TRACE")) {
+        KRY_TRY(kry_alloc((void **)&c->halo_trace, 16 * sizeof(uint64_t)));
+        KRY_CUDA(cudaMemset(c->halo_trace, 0, 16 * sizeof(uint64_t)));
+    }
     KRY_CUDA(cudaStreamSynchronize(c->stream));
     *out = c;
     return KRY_OK;
@@ -224,6 +228,19 @@ extern "C" int kry_flush_l2(kry_ctx *c)
     flush_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>((double *)c->flush_buf,
                                                          c->flush_bytes / 8, 1.0);
     KRY_CUDA(cudaGetLastError());
+    return KRY_OK;
+}
+
+// Diagnostics of the fused halo exchange (env KRY_HALO_TRACE=1 at context creation): sums of
+// in-kernel %globaltimer intervals since the last read -- see spmv.cuh halo_push / halo_wait.
+extern "C" int kry_halo_trace_read(kry_ctx *c, uint64_t *out16)
+{
+    KRY_REQUIRE(c && out16, KRY_ERR_INVALID, "kry_halo_trace_read: NULL argument");
+    memset(out16, 0, 16 * sizeof(uint64_t));
+    if (!c->halo_trace) return KRY_OK;
+    KRY_CUDA(cudaStreamSynchronize(c->stream));
+    KRY_CUDA(cudaMemcpy(out16, c->halo_trace, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    KRY_CUDA(cudaMemset(c->halo_trace, 0, 16 * sizeof(uint64_t)));
     return KRY_OK;
 }
 

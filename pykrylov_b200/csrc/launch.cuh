@@ -1,6 +1,8 @@
 // launch.cuh -- host-side launch helpers shared by ops.cu and the solvers.
 #pragma once
 
+#include <stdlib.h>
+
 #include "spmv.cuh"
 
 constexpr int KRY_DEFAULT_TILE    = 4096;
@@ -168,15 +170,22 @@ int spmv_launch(kry_csr *M, bool trans, Gather g, Epi epi, Fin fin, const int *d
 // spmv_row_shard_kernel).  `tbl` is the device table of the gathered vector (solver.cuh); the
 // fused inner products are all-reduced in-kernel over the same peer mapping.  Every rank issues
 // the same sequence of these launches, so the host-side tag counter agrees everywhere.
-static inline bool spmv_shard_fusable(const kry_csr *M)
+static inline bool spmv_shard_row_kind(const kry_csr *M)
 {
     int kind = M->kind;
     if (kind == KRY_SPMV_AUTO) kind = (M->A.max_row <= 64) ? KRY_SPMV_ROW : KRY_SPMV_STREAM;
-    return kind == KRY_SPMV_ROW && M->ctx->p2p_on && M->ctx->halo_p2p && M->halo.active;
+    return kind == KRY_SPMV_ROW && M->halo.active;
+}
+static inline bool spmv_shard_fusable(const kry_csr *M)
+{
+    return spmv_shard_row_kind(M) && M->ctx->p2p_on && M->ctx->halo_p2p;
 }
 
+// tbl != nullptr: exchange fused into the launch (needs the in-kernel all-reduce, defer = 2);
+// tbl == nullptr: the halo tail was filled before the launch (pack kernel + ncclAllGather) -- same
+// kernel, same row order, push and wait switched off.  defer as in spmv_launch.
 template <int ND, class Gather, class Epi, class Fin>
-int spmv_shard_launch(kry_csr *M, Gather g, Epi epi, Fin fin, const int *done, const HaloTable *tbl)
+int spmv_shard_launch(kry_csr *M, Gather g, Epi epi, Fin fin, const int *done, const HaloTable *tbl, int defer)
 {
     static_assert(ND > 0, "the in-kernel all-reduce at the end of the launch is what orders the exchanges");
     kry_ctx *c = M->ctx;
@@ -196,8 +205,8 @@ int spmv_shard_launch(kry_csr *M, Gather g, Epi epi, Fin fin, const int *done, c
     const int grid = (int)(need < capg ? need : capg);     // waiting CTAs must be co-resident
     KRY_TRY(kry_ctx_ensure_partials(c, grid));
     ReduceWs ws = kry_ws(c);
-    ws.defer = 0;
-    ws.p2p = 1;
+    ws.defer = (defer == 1);
+    ws.p2p = (defer == 2);
     CsrView A = csr_view(*m);
     HaloArgs h;
     h.tbl = tbl;
@@ -206,10 +215,12 @@ int spmv_shard_launch(kry_csr *M, Gather g, Epi epi, Fin fin, const int *done, c
     h.push_ctas = (hp.n_send + 255) / 256;
     if (h.push_ctas > grid) h.push_ctas = grid;
     h.ticket = c->counter + 24;                             // inside the zeroed 256-byte counter block
-    h.tag = ++c->halo_seq;
-    h.lo_rows = hp.lo_rows;
-    h.hi_begin = hp.hi_begin;
-    h.skip_push = 0;
+    h.tag = tbl ? ++c->halo_seq : 0ull;
+    h.rot = hp.rot;
+    h.v_wait = hp.v_wait;
+    h.skip_push = tbl ? 0 : 3;
+    h.trace = tbl ? c->halo_trace : nullptr;
+    KRY_REQUIRE(!tbl || defer == 2, KRY_ERR_STATE, "fused halo exchange without the in-kernel all-reduce");
     const bool prof = c->prof_ev && c->prof_n < c->prof_cap;
     if (prof) KRY_CUDA(cudaEventRecord(c->prof_ev[2 * c->prof_n], c->stream));
 #ifdef KRY_EMULATE
@@ -221,14 +232,14 @@ int spmv_shard_launch(kry_csr *M, Gather g, Epi epi, Fin fin, const int *done, c
     } else {
         // fast mode plays the threads one after the other: the push (all of it, then the flags) is
         // played first by the launcher with the kernel's own device function
-        if (!*done) {
+        if (!*done && tbl) {
             Gather g0 = g;
             g0.init();
             gridDim = EmuDim{(unsigned)grid, 1, 1};
             blockDim = EmuDim{256, 1, 1};
             emu_halo_push_all(h, g0);
         }
-        h.skip_push = 1;
+        h.skip_push |= 1;
         emu_launch<ND>(grid, 256, ws, fin, [&] { spmv_row_shard_kernel<ND, Gather, Epi, Fin>(A, g, epi, ws, fin, done, h); });
     }
 #else

@@ -133,16 +133,28 @@ __device__ __forceinline__ void hist_push(DevScalars *s, double *hist, int width
 #endif
 
 // Launch wrappers that route the fused reduction through NCCL on sharded runs.
+// Row shards (thread-per-row kernel): one kernel and one row order for every way the halo and
+// the scalars can travel; `tbl` non-null = halo exchange fused into the launch.
+template <int ND, class Gather, class Epi, class Fin>
+int solver_spmv_shard(kry_solver *S, Gather g, Epi e, Fin f, const int *done, const HaloTable *tbl)
+{
+    if (S->ctx->p2p_on) return spmv_shard_launch<ND>(S->A, g, e, f, done, tbl, 2);     // in-kernel all-reduce
+    KRY_TRY((spmv_shard_launch<ND>(S->A, g, e, f, done, nullptr, 1)));
+    KRY_TRY(kry_allreduce_sums(S->ctx, ND));
+    return finalize_launch(S->ctx, f, done);
+}
+
 template <int ND, class Gather, class Epi, class Fin>
 int solver_spmv(kry_solver *S, Gather g, Epi e, Fin f, const int *done, double *x_dev)
 {
     if (S->sharded) {
-        if (x_dev) {
+        if (spmv_shard_row_kind(S->A)) {
             // halo exchange fused into the launch (peer-memory stores + flags), or pack + ncclAllGather
-            if (const HaloTable *tbl = solver_halo_table(S, x_dev))
-                return spmv_shard_launch<ND>(S->A, HaloGather<Gather>{g, (int)S->n}, e, f, done, tbl);
-            KRY_TRY(kry_halo_exchange(S->A, x_dev));
-        }                                                       // nullptr: the caller did the exchange
+            const HaloTable *tbl = x_dev ? solver_halo_table(S, x_dev) : nullptr;
+            if (!tbl && x_dev) KRY_TRY(kry_halo_exchange(S->A, x_dev));     // x_dev == nullptr: the caller did it
+            return solver_spmv_shard<ND>(S, HaloGather<Gather>{g, (int)S->n}, e, f, done, tbl);
+        }
+        if (x_dev) KRY_TRY(kry_halo_exchange(S->A, x_dev));
         if (S->ctx->p2p_on) return spmv_launch<ND>(S->A, false, g, e, f, done, 2);   // in-kernel all-reduce
         KRY_TRY((spmv_launch<ND>(S->A, false, g, e, f, done, 1)));
         KRY_TRY(kry_allreduce_sums(S->ctx, ND));

@@ -416,9 +416,9 @@ static int cg_fused_spmv(kry_solver *S, double *p_old, double *p_new, int opt)
     if (S->sharded) {
         // boundary entries of p travel already updated; the local ones are updated in the gather
         CgGatherDir<PEND, true> g{p_old, r, S->ds, 0.0, (int)S->n};
-        if (const HaloTable *tbl = solver_halo_table(S, p_old))      // exchange fused into the launch
-            return spmv_shard_launch<1>(S->A, g, e, CgFinApFused{S->ds}, &S->ds->done, tbl);
-        KRY_TRY(kry_halo_exchange_dir(S->A, p_old, PEND ? r : nullptr, PEND ? &S->ds->s[S_BETA] : nullptr));
+        const HaloTable *tbl = solver_halo_table(S, p_old);          // non-null: exchange fused into the launch
+        if (!tbl) KRY_TRY(kry_halo_exchange_dir(S->A, p_old, PEND ? r : nullptr, PEND ? &S->ds->s[S_BETA] : nullptr));
+        if (spmv_shard_row_kind(S->A)) return solver_spmv_shard<1>(S, g, e, CgFinApFused{S->ds}, &S->ds->done, tbl);
         return solver_spmv<1>(S, g, e, CgFinApFused{S->ds}, &S->ds->done, nullptr);
     }
     CgGatherDir<PEND> g{p_old, r, S->ds, 0.0, 0};

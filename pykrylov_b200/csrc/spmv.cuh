@@ -204,14 +204,33 @@ spmv_rowpf_kernel(CsrView A, Gather g, Epi epi, ReduceWs ws, Fin fin, const int 
 //      straight into the halo tails of the ranks that read them, over NVLink peer memory
 //      (CUDA IPC mapping of the readers' solver slabs); the CTA that finishes the push last
 //      publishes the launch's tag in every reader's flag word (system-scope fence in between).
-//   2. All CTAs walk their rows exactly as spmv_row_kernel does.  Rows that may touch a halo
-//      column sit in the first lo_rows and from hi_begin on (found at kry_csr_shard_finalize;
-//      for a banded operator: two thin slabs): the interior of the shard is multiplied while
-//      the peers' entries are in flight.
-//   3. A thread waits, right before the first such row it owns, until every rank it reads from
-//      has published this tag; halo columns are then read at the L2 (Gather::halo).
+//   2. All CTAs walk the rows in the rotated order v -> (v + rot) mod nrows, which puts the rows
+//      that may touch halo columns last (HaloPlan::rot / v_wait, found at kry_csr_shard_finalize;
+//      for a banded operator they are two thin slabs at the ends of the shard): the interior is
+//      multiplied while the peers' entries are in flight, and every CTA stays in step with its
+//      neighbours (measured: a CTA that stalls 25 us at the start of the launch falls four trips
+//      behind the wave, out of the L2 window the others share, and never catches up -- the launch
+//      then takes 12 % longer; profiles/r2e_*).
+//   3. A thread that reaches v >= v_wait first waits until every rank it reads from has
+//      published this tag; halo columns are then read at the L2 (Gather::halo).
+// Every sharded row launch uses this kernel and this row order -- also when the entries travelled
+// by pack kernel + ncclAllGather (skip bits set) -- so the fused inner products are the same
+// bits whichever way the halo travelled.
 // Ordering argument (why a tail is never overwritten while it is still being read, and why no
 // wait can be circular): DESIGN.md section 6.  No pack launch, no ncclAllGather.
+#ifndef KRY_EMULATE
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#else
+static inline unsigned long long global_ns() { return 0; }
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
+static inline unsigned long long atomicMax(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; if (v > o) *p = v; return o; }
+#endif
+
 __device__ __forceinline__ unsigned long long ld_flag(const unsigned long long *p)
 {
     return *reinterpret_cast<const volatile unsigned long long *>(p);
@@ -238,7 +257,7 @@ __device__ __forceinline__ void halo_publish(const HaloArgs &h)
 }
 
 template <class Gather>
-__device__ __forceinline__ void halo_push(const HaloArgs &h, const Gather &g)
+__device__ __forceinline__ void halo_push(const HaloArgs &h, const Gather &g, const unsigned long long &t_entry)
 {
     if ((int)(gridDim.x - 1 - blockIdx.x) >= h.push_ctas) return;
     halo_push_entries(h, g);
@@ -249,6 +268,10 @@ __device__ __forceinline__ void halo_push(const HaloArgs &h, const Gather &g)
         if (ticket == (unsigned)h.push_ctas - 1u) {
             *h.ticket = 0u;
             halo_publish(h);
+            if (h.trace) {                       // [0] sum of (publish - this CTA's entry), [1] launches
+                atomicAdd(h.trace + 0, global_ns() - t_entry);
+                atomicAdd(h.trace + 1, 1ull);
+            }
         }
     }
 }
@@ -269,12 +292,24 @@ static inline void emu_halo_push_all(const HaloArgs &h, const Gather &g)
 }
 #endif
 
-__device__ __forceinline__ void halo_wait(const HaloArgs &h)
+__device__ __forceinline__ void halo_wait(const HaloArgs &h, const unsigned long long &t_entry)
 {
     const HaloTable *T = h.tbl;
+    unsigned long long t0 = 0;
+    if (h.trace) t0 = global_ns();
     for (int q = 0; q < T->n_from; ++q)
         while (ld_flag(T->from_flag[q]) < h.tag) __nanosleep(20);
+    unsigned long long t1 = 0;
+    if (h.trace) t1 = global_ns();
     __threadfence_system();
+    if (h.trace && (threadIdx.x & 31) == 0) {    // per waiting warp: [2] sum spin, [3] sum fence, [4] warps,
+        const unsigned long long t2 = global_ns();   // [5] max (end of wait - entry), [6] sum (start of wait - entry)
+        atomicAdd(h.trace + 2, t1 - t0);
+        atomicAdd(h.trace + 3, t2 - t1);
+        atomicAdd(h.trace + 4, 1ull);
+        atomicMax(h.trace + 5, t2 - t_entry);
+        atomicAdd(h.trace + 6, t0 - t_entry);
+    }
 }
 
 template <int ND, class Gather, class Epi, class Fin>
@@ -284,29 +319,31 @@ spmv_row_shard_kernel(CsrView A, Gather g, Epi epi, ReduceWs ws, Fin fin, const 
     if (*done) return;
     g.init();
     epi.init();
-    if (!h.skip_push) halo_push(h, g);
+    __shared__ unsigned long long t_entry;      // KRY_HALO_TRACE only (shared: no register across the row loops)
+    if (h.trace) {
+        if (threadIdx.x == 0) t_entry = global_ns();
+        __syncthreads();
+    }
+    if (!(h.skip_push & 1)) halo_push(h, g, t_entry);
     double acc[ND > 0 ? ND : 1];
 #pragma unroll
     for (int d = 0; d < (ND > 0 ? ND : 1); ++d) acc[d] = 0.0;
     const int stride = gridDim.x * blockDim.x;
-    auto one_row = [&](int row) {
+    auto one_row = [&](int v) {
+        int row = v + h.rot;
+        if (row >= A.nrows) row -= A.nrows;
         const int s = __ldg(A.rowptr + row), e = __ldg(A.rowptr + row + 1);
         double sum = 0.0;
         for (int k = s; k < e; ++k)
             sum = __dadd_rn(sum, __dmul_rn(__ldg(A.val + k), g(__ldg(A.col + k))));
         epi(row, sum, acc);
     };
-    // same row -> thread mapping and the same order as spmv_row_kernel, so the fused inner
-    // products are the same bits whichever way the halo travelled; a thread waits for the peers'
-    // entries right before the first row it owns that may touch a halo column
-    const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
-    int row = t0;
-    const int hi = h.hi_begin < A.nrows ? h.hi_begin : A.nrows;
-    if (row < h.lo_rows && row < A.nrows) halo_wait(h);
-    for (; row < hi; row += stride) one_row(row);
-    if (row < A.nrows) {
-        if (t0 >= h.lo_rows) halo_wait(h);
-        for (; row < A.nrows; row += stride) one_row(row);
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v_int = h.v_wait < A.nrows ? h.v_wait : A.nrows;
+    for (; v < v_int; v += stride) one_row(v);            // interior: no halo column in these rows
+    if (v < A.nrows) {
+        if (!(h.skip_push & 2)) halo_wait(h, t_entry);    // the peers' boundary entries have landed
+        for (; v < A.nrows; v += stride) one_row(v);
     }
     if constexpr (ND > 0) block_reduce_finalize<ND>(acc, ws, fin);
 }

@@ -179,6 +179,12 @@ class Context(object):
         call("kry_launch_count", self._h, C.byref(n))
         return n.value
 
+    def halo_trace(self):
+        """KRY_HALO_TRACE diagnostics (kry_halo_trace_read); zeros unless tracing is on."""
+        out = (C.c_uint64 * 16)()
+        call("kry_halo_trace_read", self._h, out)
+        return [int(v) for v in out]
+
     def set_option(self, option, value):
         call("kry_ctx_set_option", self._h, int(option), int(value))
 

@@ -351,6 +351,7 @@ extern "C" int kry_timer_stop(kry_ctx *, double *ms)
 }
 extern "C" int kry_flush_l2(kry_ctx *) { return KRY_OK; }
 extern "C" int kry_launch_count(kry_ctx *c, int64_t *n) { *n = c->launches; return KRY_OK; }
+extern "C" int kry_halo_trace_read(kry_ctx *, uint64_t *out16) { memset(out16, 0, 16 * sizeof(uint64_t)); return KRY_OK; }
 extern "C" int kry_prof_enable(kry_ctx *, int) { return KRY_OK; }
 extern "C" int kry_prof_read(kry_ctx *, int64_t *n, double *ms) { *n = 0; *ms = 0.0; return KRY_OK; }
 extern "C" int kry_host_alloc(int64_t bytes, void **out) { *out = malloc(bytes > 0 ? bytes : 1); return *out ? KRY_OK : KRY_ERR_NOMEM; }
