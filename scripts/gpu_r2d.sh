@@ -25,6 +25,6 @@ PY
 }
 run_bench halo1
 run_bench halo0 --halo-p2p 0 --no-single
-run_bench halo1_again --no-single
+[ "$N" -lt 8 ] && run_bench halo1_again --no-single
 run_bench nccl_allreduce --halo-p2p 0 --nccl-allreduce --no-single
 KRY_HALO_TRACE=1 run_bench halo1_trace --no-single; grep "halo trace" gpurun_out/r2d_bench_n${N}_halo1_trace.err
