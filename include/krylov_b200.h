@@ -145,6 +145,24 @@ int kry_vec_copy(kry_vec *dst, const kry_vec *src);
 int kry_csr_create(kry_ctx *ctx, int64_t nrows, int64_t ncols, int64_t nnz,
                    const int32_t *rowptr, const int32_t *col, const double *val,
                    uint32_t flags, kry_csr **out);
+/* Operator from coordinate triplets, assembled on the device (replaces the Python loop of the
+ * reference's CoordLinearOperator, linop/linop.py:638-685).  Inside every CSR row the entries keep
+ * the order in which that loop accumulates them, so SpMV row sums are its sums bit for bit.
+ * flags: KRY_CSR_SYMMETRIC = the triplets are one triangle (the mirror images are generated);
+ * KRY_CSR_BUILD_TRANSPOSE = also assemble A^T from the triplets in the accumulation order of the
+ * reference's matvec_transp (linop.py:666-681).  Out-of-range coordinates -> KRY_ERR_INVALID.   */
+int kry_csr_create_coo(kry_ctx *ctx, int64_t nrows, int64_t ncols, int64_t nnz,
+                       const int32_t *rows, const int32_t *cols, const double *vals,
+                       uint32_t flags, kry_csr **out);
+/* Operator algebra that stays in HBM (reference linop.py:307-345, 378-410 builds host closures):
+ * C = alpha*A [+ beta*B] [+ gamma*diag(d)] as a new CSR; per row the scaled entries of A, then of B,
+ * then the diagonal entry.  B and diag_host may be NULL.  A + sigma*I and A +- D equal the
+ * reference's two-product expression bit for bit; alpha*A and A + B to rounding (one fused row sum
+ * instead of two products).  flags: KRY_CSR_SYMMETRIC if the result is symmetric.                */
+int kry_csr_combine(kry_ctx *ctx, const kry_csr *A, double alpha, const kry_csr *B, double beta,
+                    const double *diag_host, double gamma, uint32_t flags, kry_csr **out);
+/* Dense row-major copy (LinearOperator.to_array, linop.py:256-269), scattered on the device. */
+int kry_csr_to_dense(const kry_csr *A, double *dense_host);
 int kry_csr_destroy(kry_csr *A);
 int kry_csr_shape(const kry_csr *A, int64_t *nrows, int64_t *ncols, int64_t *nnz);
 /* Copy the device CSR back (integer-parity tests: device-built == scipy).           */

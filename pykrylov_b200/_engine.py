@@ -176,6 +176,11 @@ class HostBridge(object):
             csr.spmv(x_vec, out_vec, trans=trans)
             op._nMatvec += 1
             return out_vec
+        chain = getattr(op, "device_apply", None)
+        if chain is not None:                       # product of device operators: SpMVs back to back in HBM
+            chain(x_vec, out_vec, trans=trans)
+            op._nMatvec += 1
+            return out_vec
         y = (op.T if trans else op) * x_vec.download()
         out_vec.upload(np.asarray(y, dtype=np.float64))
         return out_vec

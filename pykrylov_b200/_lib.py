@@ -109,6 +109,11 @@ PROTOTYPES = {
                                            C.POINTER(handle)]),
     "kry_csr_create_poisson2d": (C.c_int, [handle, C.c_int64, C.c_int64, C.c_int64, C.c_uint32,
                                            C.POINTER(handle)]),
+    "kry_csr_create_coo": (C.c_int, [handle, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_uint32, C.POINTER(handle)]),
+    "kry_csr_combine": (C.c_int, [handle, handle, C.c_double, handle, C.c_double, C.c_void_p, C.c_double,
+                                  C.c_uint32, C.POINTER(handle)]),
+    "kry_csr_to_dense": (C.c_int, [handle, C.c_void_p]),
     "kry_csr_create_convdiff3d": (C.c_int, [handle, C.c_int64, C.c_double, C.c_int64, C.c_int64,
                                             C.c_uint32, C.POINTER(handle)]),
     "kry_csr_set_kernel": (C.c_int, [handle, C.c_int, C.c_int, C.c_int]),

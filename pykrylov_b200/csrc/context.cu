@@ -475,7 +475,7 @@ extern "C" int kry_scalars_write(kry_ctx *c, int first, int count, const double 
 }
 
 // --------------------------------------------------------------------- CSR
-static void csr_dev_free(CsrDev &m)
+void csr_dev_free(CsrDev &m)
 {
     cudaFree(m.rowptr);
     cudaFree(m.col);
@@ -484,7 +484,7 @@ static void csr_dev_free(CsrDev &m)
     m = CsrDev();
 }
 
-static int csr_dev_alloc(CsrDev &m, int64_t nrows, int64_t ncols, int64_t nnz)
+int csr_dev_alloc(CsrDev &m, int64_t nrows, int64_t ncols, int64_t nnz)
 {
     m.nrows = nrows;
     m.ncols = ncols;
@@ -555,7 +555,7 @@ __global__ void csr_validate_kernel(const int *rowptr, const int *col, int nrows
     if (bc) atomicAdd(bad + 1, bc);
 }
 
-static int csr_validate(kry_ctx *c, const CsrDev &m)
+int csr_validate(kry_ctx *c, const CsrDev &m)
 {
     int *d_bad = (int *)c->counter + 12;    // scratch inside the 256-byte counter block
     KRY_CUDA(cudaMemsetAsync(d_bad, 0, 2 * sizeof(int), c->stream));
@@ -572,7 +572,7 @@ static int csr_validate(kry_ctx *c, const CsrDev &m)
     return KRY_OK;
 }
 
-static int csr_finish(kry_ctx *c, CsrDev &m)
+int csr_finish(kry_ctx *c, CsrDev &m)
 {
     int *d_max = (int *)c->counter + 8;     // scratch inside the 256-byte counter block
     KRY_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), c->stream));
@@ -590,7 +590,7 @@ static int csr_finish(kry_ctx *c, CsrDev &m)
 
 int csr_build_transpose_dev(kry_ctx *c, const CsrDev &A, CsrDev &T);
 
-static int check_sizes(int64_t nrows, int64_t ncols, int64_t nnz)
+int check_sizes(int64_t nrows, int64_t ncols, int64_t nnz)
 {
     KRY_REQUIRE(nrows >= 0 && ncols >= 0 && nnz >= 0, KRY_ERR_INVALID,
                 "csr: negative size (%lld x %lld, nnz %lld)", (long long)nrows,

@@ -364,6 +364,41 @@ class DeviceCsr(object):
         return cls(ctx, h, symmetric)
 
     @classmethod
+    def from_coo(cls, ctx, shape, rows, cols, vals, symmetric=False, build_transpose=False):
+        """Assembled on the device from coordinate triplets (``kry_csr_create_coo``): inside a row
+        the entries keep their arrival order; ``symmetric`` expands one stored triangle."""
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        cols = np.ascontiguousarray(cols, dtype=np.int32)
+        vals = _f64(vals)
+        if not (rows.shape == cols.shape == vals.shape and rows.ndim == 1):
+            raise ValueError("rows, cols and vals must be 1-d arrays of the same length")
+        flags = (L.KRY_CSR_SYMMETRIC if symmetric else 0) | (L.KRY_CSR_BUILD_TRANSPOSE if build_transpose else 0)
+        h = L.handle()
+        call("kry_csr_create_coo", ctx._h, int(shape[0]), int(shape[1]), int(vals.shape[0]),
+             _ptr(rows), _ptr(cols), _ptr(vals), flags, C.byref(h))
+        return cls(ctx, h, symmetric)
+
+    def combine(self, alpha=1.0, other=None, beta=1.0, diag=None, gamma=1.0, symmetric=None):
+        """alpha*self [+ beta*other] [+ gamma*diag(d)] as a new operator in HBM (``kry_csr_combine``)."""
+        if symmetric is None:
+            symmetric = self.symmetric and (other is None or other.symmetric)
+        d = None
+        if diag is not None:
+            d = _f64(diag)
+            if d.shape != (self.shape[0],):
+                raise ValueError("diagonal has the wrong size")
+        h = L.handle()
+        call("kry_csr_combine", self.ctx._h, self._h, float(alpha), other._h if other is not None else None,
+             float(beta), _ptr(d) if d is not None else None, float(gamma),
+             L.KRY_CSR_SYMMETRIC if symmetric else 0, C.byref(h))
+        return DeviceCsr(self.ctx, h, symmetric)
+
+    def to_dense(self):
+        out = np.empty(self.shape, dtype=np.float64)
+        call("kry_csr_to_dense", self._h, _ptr(out))
+        return out
+
+    @classmethod
     def poisson1d(cls, ctx, n, row_begin=0, row_end=-1):
         h = L.handle()
         call("kry_csr_create_poisson1d", ctx._h, int(n), int(row_begin), int(row_end), 0, C.byref(h))

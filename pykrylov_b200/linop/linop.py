@@ -260,6 +260,10 @@ class LinearOperator(BaseLinearOperator):
             raise ValueError("Cannot add")
         if self.shape != other.shape:
             raise ShapeError("Cannot add")
+        if isinstance(other, CsrLinearOperator) and not isinstance(self, CsrLinearOperator):
+            dev = other._device_combine_reversed(self, sign)        # D +- A with A in HBM
+            if dev is not None:
+                return dev
         return LinearOperator(self.nargin, self.nargout,
                               matvec=lambda v: self(v) + sign * other(v),
                               matvec_transp=lambda v: self.T(v) + sign * other.T(v),
@@ -309,6 +313,14 @@ class IdentityOperator(LinearOperator):
         _drop(kwargs, "symmetric", "hermitian", "matvec")
         super(IdentityOperator, self).__init__(nargin, nargin, matvec=lambda x: x,
                                                symmetric=True, hermitian=True, **kwargs)
+
+    def _times_scalar(self, alpha):
+        # sigma * I as a diagonal operator: the same values as the reference's closure
+        # (sigma * x either way) in a form the device operator algebra can take in (A + sigma*I)
+        if alpha != 0 and isinstance(alpha, (int, float, np.integer, np.floating)) \
+                and not _is_complex(self.dtype):
+            return DiagonalOperator(np.full(self.nargin, float(alpha)))
+        return super(IdentityOperator, self)._times_scalar(alpha)
 
 
 class DiagonalOperator(LinearOperator):
@@ -439,6 +451,127 @@ class CsrLinearOperator(LinearOperator):
     def diagonal(self):
         return self.device_csr.diagonal()
 
+    # -- operator algebra that stays in HBM (reference linop.py:307-345, 378-410 builds host
+    #    closures; a closure handed to a solver would leave the device loop and cross PCIe at every
+    #    product).  The combined operator is a new CSR: per row the (scaled) entries of the first
+    #    operand, then those of the second, then a diagonal term.  A +- sigma*I, A +- D and -A equal
+    #    the reference's expression bit for bit (the appended entry is added last, like the second
+    #    summand; negation is exact); alpha*A and A + B differ from it by rounding only (one row
+    #    sum instead of alpha*(sum) / two sums).
+    def _algebra_ok(self):
+        return not getattr(self.device_csr, "sharded", False)
+
+    @staticmethod
+    def _diag_of(op):
+        """Real fp64 diagonal of an Identity / Diagonal operator, else None."""
+        if isinstance(op, IdentityOperator) and not _is_complex(op.dtype):
+            return np.ones(op.nargin)
+        if isinstance(op, DiagonalOperator):
+            d = np.asarray(op.diag)
+            if d.dtype == np.float64:
+                return d
+        return None
+
+    def _times_scalar(self, alpha):
+        if alpha == 0 or not self._algebra_ok() or not isinstance(alpha, (int, float, np.integer, np.floating)):
+            return super(CsrLinearOperator, self)._times_scalar(alpha)
+        return CsrLinearOperator(self.device_csr.combine(alpha=float(alpha)))
+
+    def _combine(self, other, sign):
+        if not isinstance(other, BaseLinearOperator):
+            raise ValueError("Cannot add")
+        if self.shape != other.shape:
+            raise ShapeError("Cannot add")
+        if self._algebra_ok():
+            if isinstance(other, CsrLinearOperator) and other._algebra_ok() \
+                    and other.device_csr.ctx is self.device_csr.ctx:
+                return CsrLinearOperator(self.device_csr.combine(1.0, other.device_csr, float(sign)))
+            d = self._diag_of(other)
+            if d is not None:
+                return CsrLinearOperator(self.device_csr.combine(1.0, diag=d, gamma=float(sign), symmetric=self.symmetric))
+        return super(CsrLinearOperator, self)._combine(other, sign)
+
+    def _device_combine_reversed(self, left, sign):
+        """left +- self for an Identity / Diagonal `left`: (+-1)*self + diag(d)."""
+        d = self._diag_of(left)
+        if d is None or not self._algebra_ok():
+            return None
+        return CsrLinearOperator(self.device_csr.combine(float(sign), diag=d, gamma=1.0, symmetric=self.symmetric))
+
+    def _times_operator(self, other):
+        if self.nargin != other.nargout:
+            raise ShapeError("Cannot multiply operators together")
+        if isinstance(other, (CsrLinearOperator, DeviceChainOperator)) and self._algebra_ok():
+            return DeviceChainOperator(DeviceChainOperator.links(self) + DeviceChainOperator.links(other))
+        return super(CsrLinearOperator, self)._times_operator(other)
+
+    def to_array(self):
+        "Dense matrix of the operator, scattered on the device (one D2H instead of ncol products)."
+        if not self._algebra_ok():
+            return super(CsrLinearOperator, self).to_array()
+        return self.device_csr.to_dense()
+
+    full = to_array
+
+
+class DeviceChainOperator(LinearOperator):
+    """Product A_1 A_2 ... A_k of operators that live in HBM: ``op * x`` uploads x once, applies
+    the CUDA SpMVs back to back on device vectors and downloads the result once (the reference
+    composes host closures, linop.py:320-331).  Solvers run it through the host-callback bridge
+    without leaving the device (``device_apply``)."""
+
+    @staticmethod
+    def links(op):
+        return list(op._links) if isinstance(op, DeviceChainOperator) else [op.device_csr]
+
+    def __init__(self, links):
+        self._links = list(links)
+        ctx = links[0].ctx
+        if any(m.ctx is not ctx for m in links):
+            raise ValueError("operators of a product must live on the same device context")
+        nargout, nargin = links[0].shape[0], links[-1].shape[1]
+
+        def run(x, trans):
+            from ..device import DeviceVector
+            xv = DeviceVector(ctx, x.shape[0]).upload(x)
+            out = self.device_apply(xv, None, trans=trans)
+            return out.download()
+
+        def matvec(x):
+            if x.shape != (nargin,):
+                raise ShapeError("Input has shape %s instead of (%d,)" % (str(x.shape), nargin))
+            return run(x, False)
+
+        def matvec_transp(y):
+            if y.shape != (nargout,):
+                raise ShapeError("Input has shape %s instead of (%d,)" % (str(y.shape), nargout))
+            return run(y, True)
+
+        super(DeviceChainOperator, self).__init__(nargin, nargout, matvec=matvec, matvec_transp=matvec_transp,
+                                                  symmetric=False, hermitian=False, dtype=np.float64)
+
+    def device_apply(self, x_vec, out_vec=None, trans=False):
+        """out = (A_1 ... A_k) x, or its transpose applied to x, on device vectors."""
+        from ..device import DeviceVector
+        order = self._links if trans else self._links[::-1]
+        cur = x_vec
+        for i, m in enumerate(order):
+            if trans and not m.symmetric:
+                m.build_transpose()
+            n_out = m.shape[1] if trans else m.shape[0]
+            dst = out_vec if (i == len(order) - 1 and out_vec is not None) else DeviceVector(m.ctx, n_out)
+            m.spmv(cur, dst, trans=trans)
+            cur = dst
+        return cur
+
+    def _times_operator(self, other):
+        if self.nargin != other.nargout:
+            raise ShapeError("Cannot multiply operators together")
+        if isinstance(other, (CsrLinearOperator, DeviceChainOperator)) and \
+                not (isinstance(other, CsrLinearOperator) and not other._algebra_ok()):
+            return DeviceChainOperator(self._links + DeviceChainOperator.links(other))
+        return super(DeviceChainOperator, self)._times_operator(other)
+
 
 def csr_operator(shape, indptr, indices, data, symmetric=False, context=None):
     """Device operator from host CSR arrays (int32/int64 indices, fp64 values)."""
@@ -489,15 +622,26 @@ def CoordLinearOperator(vals, rows, cols, nargin=0, nargout=0, symmetric=False, 
         nargout = rows.max()          # (sic) linop.py:647
     nargin, nargout = int(nargin), int(nargout)
     rows_i, cols_i = np.asarray(rows).astype(np.int64), np.asarray(cols).astype(np.int64)
+    vals = np.asarray(vals)
+    if vals.dtype == np.float64:
+        # assembled in HBM (csrc/assemble.cu): stable sort of the triplets by row, symmetric
+        # expansion and the range check all run on the device; A^T comes from the same triplets
+        # in the order of the reference's matvec_transp
+        from ..device import DeviceCsr, default_context
+        from .._lib import KrylovDeviceError, KRY_ERR_INVALID
+        ctx = context or default_context()
+        try:
+            csr = DeviceCsr.from_coo(ctx, (nargout, nargin), rows_i, cols_i, vals, symmetric=symmetric,
+                                     build_transpose=not symmetric)
+        except KrylovDeviceError as exc:
+            if exc.status == KRY_ERR_INVALID:
+                raise IndexError("coordinate index out of bounds for a (%d,%d) operator" % (nargout, nargin))
+            raise
+        return CsrLinearOperator(csr)
     if len(vals) and (rows_i.min() < 0 or cols_i.min() < 0 or rows_i.max() >= nargout
                       or cols_i.max() >= nargin
                       or (symmetric and (rows_i.max() >= nargin or cols_i.max() >= nargout))):
         raise IndexError("coordinate index out of bounds for a (%d,%d) operator" % (nargout, nargin))
-    vals = np.asarray(vals)
-    if vals.dtype == np.float64:
-        indptr, c, v = _coo_to_csr_in_arrival_order(vals, rows_i, cols_i, nargout, symmetric)
-        op = csr_operator((nargout, nargin), indptr, c, v, symmetric=symmetric, context=context)
-        return op
 
     def scatter(n_in, n_out, out_idx, in_idx):
         def fun(x):

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <chrono>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -550,6 +551,78 @@ extern "C" int kry_csr_create(kry_ctx *c, int64_t nrows, int64_t ncols, int64_t 
     return new_csr(c, flags, nrows, ncols, rp, cc, vv, out);
 }
 
+// host stand-ins of csrc/assemble.cu (same orders: arrival order inside a row; A, then B, then diagonal)
+static void coo_rows(int64_t nrows, int64_t nnz, const int32_t *rows, const int32_t *cols, const double *vals, int sym,
+                     std::vector<int> &rp, std::vector<int> &cc, std::vector<double> &vv)
+{
+    std::vector<std::vector<std::pair<int, double>>> R((size_t)nrows);
+    for (int64_t k = 0; k < nnz; ++k) {
+        R[(size_t)rows[k]].push_back({cols[k], vals[k]});
+        if (sym && rows[k] != cols[k]) R[(size_t)cols[k]].push_back({rows[k], vals[k]});
+    }
+    rp.assign((size_t)nrows + 1, 0);
+    cc.clear();
+    vv.clear();
+    for (int64_t i = 0; i < nrows; ++i) {
+        for (auto &e : R[(size_t)i]) { cc.push_back(e.first); vv.push_back(e.second); }
+        rp[(size_t)i + 1] = (int)cc.size();
+    }
+}
+
+extern "C" int kry_csr_create_coo(kry_ctx *c, int64_t nrows, int64_t ncols, int64_t nnz, const int32_t *rows,
+                                  const int32_t *cols, const double *vals, uint32_t flags, kry_csr **out)
+{
+    KRY_REQUIRE(c && out && (nnz == 0 || (rows && cols && vals)), KRY_ERR_INVALID, "kry_csr_create_coo: NULL argument");
+    const int sym = (flags & KRY_CSR_SYMMETRIC) ? 1 : 0;
+    int bad = 0;
+    for (int64_t k = 0; k < nnz; ++k)
+        bad += !(rows[k] >= 0 && rows[k] < nrows && cols[k] >= 0 && cols[k] < ncols &&
+                 (!sym || (rows[k] < ncols && cols[k] < nrows)));
+    KRY_REQUIRE(bad == 0, KRY_ERR_INVALID, "kry_csr_create_coo: %d coordinate(s) outside a (%lld, %lld) operator", bad,
+                (long long)nrows, (long long)ncols);
+    std::vector<int> rp, cc;
+    std::vector<double> vv;
+    coo_rows(nrows, nnz, rows, cols, vals, sym, rp, cc, vv);
+    KRY_TRY(new_csr(c, flags & KRY_CSR_SYMMETRIC, nrows, ncols, rp, cc, vv, out));
+    if ((flags & KRY_CSR_BUILD_TRANSPOSE) && !sym) {
+        coo_rows(ncols, nnz, cols, rows, vals, 0, rp, cc, vv);
+        kry_csr *T = nullptr;
+        KRY_TRY(new_csr(c, 0, ncols, nrows, rp, cc, vv, &T));
+        (*out)->T = T->A;
+        (*out)->has_T = true;
+        T->A = CsrDev();
+        kry_csr_destroy(T);
+    }
+    return KRY_OK;
+}
+
+extern "C" int kry_csr_combine(kry_ctx *c, const kry_csr *A, double alpha, const kry_csr *B, double beta,
+                               const double *diag, double gamma, uint32_t flags, kry_csr **out)
+{
+    KRY_REQUIRE(c && A && out, KRY_ERR_INVALID, "kry_csr_combine: NULL argument");
+    KRY_REQUIRE(!B || (B->A.nrows == A->A.nrows && B->A.ncols == A->A.ncols), KRY_ERR_SHAPE, "kry_csr_combine: shapes differ");
+    KRY_REQUIRE(!diag || A->A.nrows == A->A.ncols, KRY_ERR_SHAPE, "kry_csr_combine: diagonal term on a rectangular operator");
+    std::vector<int> rp((size_t)A->A.nrows + 1, 0), cc;
+    std::vector<double> vv;
+    for (int64_t i = 0; i < A->A.nrows; ++i) {
+        for (int k = A->A.rowptr[i]; k < A->A.rowptr[i + 1]; ++k) { cc.push_back(A->A.col[k]); vv.push_back(alpha * A->A.val[k]); }
+        if (B)
+            for (int k = B->A.rowptr[i]; k < B->A.rowptr[i + 1]; ++k) { cc.push_back(B->A.col[k]); vv.push_back(beta * B->A.val[k]); }
+        if (diag) { cc.push_back((int)i); vv.push_back(gamma * diag[i]); }
+        rp[(size_t)i + 1] = (int)cc.size();
+    }
+    return new_csr(c, flags & KRY_CSR_SYMMETRIC, A->A.nrows, A->A.ncols, rp, cc, vv, out);
+}
+
+extern "C" int kry_csr_to_dense(const kry_csr *A, double *dense)
+{
+    KRY_REQUIRE(A && dense, KRY_ERR_INVALID, "kry_csr_to_dense: NULL argument");
+    memset(dense, 0, (size_t)(A->A.nrows * A->A.ncols) * sizeof(double));
+    for (int64_t i = 0; i < A->A.nrows; ++i)
+        for (int k = A->A.rowptr[i]; k < A->A.rowptr[i + 1]; ++k) dense[i * A->A.ncols + A->A.col[k]] += A->A.val[k];
+    return KRY_OK;
+}
+
 extern "C" int kry_csr_destroy(kry_csr *M)
 {
     if (!M) return KRY_OK;
@@ -811,22 +884,31 @@ void emu_p2p_allreduce(const ReduceWs &ws, double *tot, int nd)
 {
     const unsigned long long seq = *ws.seq + 1ull;
     *ws.seq = seq;
+    const unsigned long long tag = (seq & 0xffffffffull) << 32;
     const size_t slot = (size_t)(seq & 1ull) * ws.nranks;
     for (int q = 0; q < ws.nranks; ++q) {
-        volatile double *dst = ws.peers[q] + (slot + ws.rank) * 8;
-        for (int d = 0; d < nd; ++d) dst[d] = tot[d];
-        __atomic_thread_fence(__ATOMIC_SEQ_CST);
-        *reinterpret_cast<volatile unsigned long long *>(dst + 7) = seq;
+        volatile unsigned long long *dst = reinterpret_cast<volatile unsigned long long *>(ws.peers[q] + (slot + ws.rank) * 8);
+        for (int d = 0; d < nd; ++d) {
+            unsigned long long bits;
+            memcpy(&bits, &tot[d], 8);
+            __atomic_store_n(const_cast<unsigned long long *>(dst + 2 * d), tag | (bits & 0xffffffffull), __ATOMIC_RELEASE);
+            __atomic_store_n(const_cast<unsigned long long *>(dst + 2 * d + 1), tag | (bits >> 32), __ATOMIC_RELEASE);
+        }
     }
+    double in[KRY_MAX_RANKS][EMU_MAX_DOTS];
     for (int q = 0; q < ws.nranks; ++q) {
-        volatile unsigned long long *flag = reinterpret_cast<volatile unsigned long long *>(ws.inbox + (slot + q) * 8 + 7);
-        while (*flag != seq) sched_yield();
+        const unsigned long long *src = reinterpret_cast<const unsigned long long *>(ws.inbox + (slot + q) * 8);
+        for (int d = 0; d < nd; ++d) {
+            unsigned long long lo, hi;
+            while (((lo = __atomic_load_n(src + 2 * d, __ATOMIC_ACQUIRE)) & 0xffffffff00000000ull) != tag) sched_yield();
+            while (((hi = __atomic_load_n(src + 2 * d + 1, __ATOMIC_ACQUIRE)) & 0xffffffff00000000ull) != tag) sched_yield();
+            const unsigned long long bits = (hi << 32) | (lo & 0xffffffffull);
+            memcpy(&in[q][d], &bits, 8);
+        }
     }
-    __atomic_thread_fence(__ATOMIC_SEQ_CST);
-    const volatile double *in = ws.inbox + slot * 8;
     for (int d = 0; d < nd; ++d) {
         double a = 0.0;
-        for (int q = 0; q < ws.nranks; ++q) a = a + in[q * 8 + d];
+        for (int q = 0; q < ws.nranks; ++q) a = a + in[q][d];
         tot[d] = a;
     }
 }

@@ -32,6 +32,8 @@ static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __ddiv_rn(double a, double b) { return a / b; }
 template <class T>
 static inline T __ldg(const T *p) { return *p; }
+static inline long long __double_as_longlong(double d) { long long v; memcpy(&v, &d, 8); return v; }
+static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
 template <class T>
 static inline T __ldcg(const T *p) { return *reinterpret_cast<const volatile T *>(p); }
 

@@ -1062,3 +1062,135 @@ def test_config4_bicgstab_convdiff_215_fullsize_follows_the_oracle(ctx):
     assert np.max(np.abs(x - ref.x)) <= 1e-10 * np.max(np.abs(ref.x))
     S._release()
     A._release()
+
+
+# ------------------------------------------------------------------ device-side assembly and operator algebra
+def _reference_coo_matvec(vals, rows, cols, nargout, x, symmetric):
+    """linop/linop.py:647-664 restated (the reference's Python loop)."""
+    y = np.zeros(nargout)
+    for k in range(len(vals)):
+        y[rows[k]] += vals[k] * x[cols[k]]
+        if symmetric and rows[k] != cols[k]:
+            y[cols[k]] += vals[k] * x[rows[k]]
+    return y
+
+
+@pytest.mark.parametrize("symmetric", [False, True])
+def test_coord_operator_is_assembled_on_the_device_in_the_reference_order(ctx, symmetric):
+    """CoordLinearOperator (linop.py:638-685): COO -> CSR runs in HBM (stable sort by row, symmetric
+    expansion, range check); inside a row the entries keep the reference loop's accumulation order,
+    so A x and A^T y equal that loop bit for bit -- duplicates, empty rows and all."""
+    from pykrylov_b200.linop import CoordLinearOperator, CsrLinearOperator
+    rng = np.random.default_rng(12)
+    m, n = (60, 60) if symmetric else (50, 70)
+    nnz = 900
+    rows = rng.integers(0, m, nnz)
+    cols = rng.integers(0, n, nnz)
+    if symmetric:
+        rows, cols = np.maximum(rows, cols), np.minimum(rows, cols)       # one triangle (with diagonal entries)
+    rows[rows == 7] = 8                                                  # an empty row
+    vals = rng.standard_normal(nnz)
+    op = CoordLinearOperator(vals, rows, cols, nargin=n, nargout=m, symmetric=symmetric, context=ctx)
+    assert isinstance(op, CsrLinearOperator) and op.shape == (m, n) and op.symmetric == symmetric
+    ip, ix, dv = op.device_csr.download()
+    # the CSR itself: per row, entries in arrival order (entry k before its mirror image of a later k)
+    want = [[] for _ in range(m)]
+    for k in range(nnz):
+        want[rows[k]].append((cols[k], vals[k]))
+        if symmetric and rows[k] != cols[k]:
+            want[cols[k]].append((rows[k], vals[k]))
+    assert np.array_equal(ip, np.concatenate([[0], np.cumsum([len(w) for w in want])]))
+    assert np.array_equal(ix, np.array([c for w in want for c, _ in w], dtype=np.int32))
+    assert np.array_equal(dv, np.array([v for w in want for _, v in w]))
+    x = rng.standard_normal(n)
+    assert np.array_equal(op * x, _reference_coo_matvec(vals, rows, cols, m, x, symmetric))
+    y = rng.standard_normal(m)
+    assert np.array_equal(op.T * y, _reference_coo_matvec(vals, cols, rows, n, y, symmetric))   # linop.py:666-681
+    dense = np.zeros((m, n))
+    for k in range(nnz):
+        dense[rows[k], cols[k]] += vals[k]
+        if symmetric and rows[k] != cols[k]:
+            dense[cols[k], rows[k]] += vals[k]
+    assert np.array_equal(op.to_array(), dense)
+    with pytest.raises(IndexError):
+        CoordLinearOperator(vals, rows + m, cols, nargin=n, nargout=m, symmetric=symmetric, context=ctx)
+    # the reference's own test cases (linop/tests/test_linop.py:374-396)
+    A = rng.random((5, 7))
+    r, c = np.nonzero(A)
+    C1 = CoordLinearOperator(A[r, c], r, c, 7, 5, symmetric=False, context=ctx)
+    xx, yy = rng.random(7), rng.random(5)
+    assert np.allclose(A @ xx, C1 * xx, rtol=1e-14) and np.allclose(A.T @ yy, C1.T * yy, rtol=1e-14)
+
+
+def test_operator_algebra_on_device_operators_stays_in_hbm(ctx):
+    """A + sigma*I, A - D, -A, A/2, 3*A, A + B, I - A, A*B of device operators are device operators
+    (reference linop.py:307-345, 378-410 returns host closures): solvers keep their device-resident
+    loop.  Shifts, diagonal terms and negation reproduce the reference's closure expression bit for
+    bit; general scalings and sums to rounding (documented in csrc/assemble.cu)."""
+    import pykrylov_b200._engine as eng
+    from pykrylov_b200.linop import (CsrLinearOperator, DeviceChainOperator, DiagonalOperator, IdentityOperator,
+                                     LinearOperator, csr_operator)
+    from pykrylov_b200.cg import CG
+    rng = np.random.default_rng(21)
+    M = fixtures()["poisson2d_123"]
+    n = M.shape[0]
+    A = csr_operator(M.shape, M.indptr, M.indices, M.data, symmetric=True, context=ctx)
+    R = sp.random(n, n, density=0.001, random_state=3, format="csr")
+    R.sort_indices()
+    Rm = CsrRef.from_scipy(R)
+    B = csr_operator(R.shape, R.indptr, R.indices, R.data, context=ctx)
+    x = rng.standard_normal(n)
+    d = rng.standard_normal(n)
+    D, I = DiagonalOperator(d), IdentityOperator(n)
+    Ax, Bx = M.matvec(x), Rm.matvec(x)
+
+    def dev(op):
+        assert isinstance(op, CsrLinearOperator) and op.device_csr is not None, type(op)
+        return op
+
+    # exact cases: the reference's closures evaluate A(v) + sign*other(v) and alpha*A(v)
+    assert np.array_equal(dev(A + 0.75 * I) * x, Ax + 0.75 * x)
+    assert np.array_equal(dev(A - 0.75 * I) * x, Ax + (-1) * (0.75 * x))
+    assert np.array_equal(dev(A + I) * x, Ax + x)
+    assert np.array_equal(dev(A - D) * x, Ax + (-1) * (d * x))
+    assert np.array_equal(dev(D + A) * x, d * x + Ax)
+    assert np.array_equal(dev(I - A) * x, x + (-1) * Ax)
+    assert np.array_equal(dev(-A) * x, -1 * Ax)
+    assert np.array_equal(dev(A / 2) * x, 0.5 * Ax) and np.array_equal(dev(4 * A) * x, 4 * Ax)
+    # rounding-level cases
+    tol = 1e-14 * np.max(np.abs(Ax))
+    assert np.max(np.abs(dev(3 * A) * x - 3 * Ax)) <= 3 * tol
+    assert np.max(np.abs(dev(A * 0.3) * x - 0.3 * Ax)) <= tol
+    assert np.max(np.abs(dev(A + B) * x - (Ax + Bx))) <= tol
+    assert np.max(np.abs(dev(A - B) * x - (Ax - Bx))) <= tol
+    S = dev(A + B)
+    assert not S.symmetric and dev(A + A).symmetric
+    assert np.max(np.abs(S.T * x - (M.rmatvec(x) + Rm.rmatvec(x)))) <= tol
+    # products: SpMVs back to back in HBM
+    P = A * B
+    assert isinstance(P, DeviceChainOperator) and P.shape == (n, n)
+    assert np.array_equal(P * x, M.matvec(Bx))
+    assert np.array_equal(P.T * x, Rm.rmatvec(M.rmatvec(x)))
+    assert np.array_equal((P * A) * x, M.matvec(Rm.matvec(Ax)))
+    assert type(A * 0) .__name__ == "ZeroOperator"
+    # anything the device cannot see keeps the reference's closure semantics
+    H = LinearOperator(n, n, lambda v: 2 * v, symmetric=True)
+    mixed = A + H
+    assert not isinstance(mixed, CsrLinearOperator) and np.array_equal(mixed * x, Ax + 2 * x)
+    with pytest.raises(Exception):
+        A + csr_operator((n, n + 1), np.zeros(n + 1, np.int32), np.zeros(0, np.int32), np.zeros(0), context=ctx)
+    # a shifted operator handed to a solver iterates on the device
+    shifted = A + 0.5 * I
+    rhs = shifted * np.ones(n)
+    assert eng.resolve(shifted, None, n) is not None
+    cg = CG(shifted)
+    l0 = ctx.launch_count()
+    cg.solve(rhs)
+    ip, ix, dv = shifted.device_csr.download()
+    ref = kr.cg_solve(CsrRef((n, n), ip, ix, dv), rhs)
+    assert cg.nMatvec == ref.nMatvec and ctx.launch_count() - l0 >= 2 * cg.nMatvec
+    assert rel(np.array(cg.residHistory), np.array(ref.residHistory)) <= 1e-9
+    assert np.max(np.abs(cg.bestSolution - 1.0)) <= 1e-5
+    # to_array on the device
+    small = csr_operator((3, 4), np.array([0, 2, 2, 4]), np.array([0, 3, 1, 1]), np.array([1.0, 2.0, 3.0, 4.0]), context=ctx)
+    assert np.array_equal(small.to_array(), np.array([[1.0, 0, 0, 2.0], [0, 0, 0, 0], [0, 7.0, 0, 0]]))
