@@ -46,6 +46,7 @@ typedef struct kry_ctx    kry_ctx;     /* device + stream + reduction workspace 
 typedef struct kry_csr    kry_csr;     /* device-resident CSR operator               */
 typedef struct kry_vec    kry_vec;     /* device-resident fp64 vector                */
 typedef struct kry_solver kry_solver;  /* device-resident Krylov iteration state     */
+typedef struct kry_lls kry_lls;        /* device-resident scalar plane of the lls solvers / SYMMLQ */
 
 /* ------------------------------------------------------------------ misc */
 int         kry_abi_version(void);
@@ -338,6 +339,41 @@ int kry_comm_allreduce_host(kry_ctx *ctx, double *inout, int count, int op /*0 s
  * exchanges the boundary sets once, remaps columns to [local | halo] and, per
  * SpMV, packs + ncclAllGathers only the boundary entries of x.                     */
 int kry_csr_shard_finalize(kry_csr *A_local, int64_t n_global, int64_t row_begin);
+
+/* ------------------------------------------------- LSQR / LSMR / CRAIG / CRAIG-MR / SYMMLQ
+ * The vector work of these solvers is kry_spmv (A and A^T) + kry_multi_axpy_dot; their scalar
+ * plane -- plane rotations, norm estimates, stopping tests (reference lls/lsqr.py:277-390,
+ * lls/lsmr.py:337-475, lls/craig.py:314-455, lls/craigmr.py:159-215, symmlq/symmlq.py:235-355) --
+ * runs on the device in single-thread step kernels that read the inner products from the
+ * context's scalar slots 0..2 and write the coefficients of the next vector launches into slots
+ * 8.. (kry_axpby::a_slot / b_slot).  The host enqueues whole iterations and reads one status
+ * block per check interval; after the reference's stopping test has fired every later launch,
+ * vector kernels included, is a no-op (kry_lls_setup installs the context's gate).
+ * Coefficient slots: 8 alpha, 9 u-divisor, 10/11 (A^T u, Nv) coefficients, 12 v-divisor,
+ * 13..20 method specific C0..C7 (see csrc/lls.cu).                                            */
+#define KRY_LLS_LSQR    0
+#define KRY_LLS_LSMR    1
+#define KRY_LLS_CRAIG   2
+#define KRY_LLS_CRAIGMR 3
+#define KRY_LLS_SYMMLQ  4
+#define KRY_LLS_HIST_WIDTH 4
+typedef struct kry_lls_params {
+    int32_t window, istop;
+    int64_t itn, nmatvec, itnlim;     /* SYMMLQ: itnlim carries matvec_max */
+    double  damp, atol, btol, ctol, etol, rtol, shift, eps;
+} kry_lls_params;
+typedef struct kry_lls_status_t {
+    int32_t done, istop;
+    int64_t itn, nmatvec, hist_count;
+} kry_lls_status_t;
+int kry_lls_create(kry_ctx *ctx, int method, kry_lls **out);
+int kry_lls_destroy(kry_lls *L);
+const char *kry_lls_scalar_name(int method, int index);   /* NULL past the end */
+int kry_lls_setup(kry_lls *L, const kry_lls_params *params, const double *scalars, int n_scalars);
+int kry_lls_step(kry_lls *L, int phase);                   /* enqueue one scalar step (no sync) */
+int kry_lls_status(kry_lls *L, kry_lls_status_t *out, double *scalars, int n_scalars);
+int kry_lls_history(kry_lls *L, int64_t first, int64_t count, double *host);   /* 4 doubles per entry */
+int kry_lls_release_gate(kry_lls *L);                      /* stand-alone launches run unconditionally again */
 
 #ifdef __cplusplus
 }

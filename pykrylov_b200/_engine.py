@@ -202,6 +202,51 @@ class HostBridge(object):
         return ()
 
 
+# ------------------------------------------------------------------ device-resident scalar planes
+def plane_csr(op):
+    """The unsharded device CSR behind `op` if the lls / SYMMLQ loops can run device-resident."""
+    csr = getattr(op, "device_csr", None)
+    if csr is None or getattr(csr, "sharded", False):
+        return None
+    return csr
+
+
+class PlaneLoop(object):
+    """Drives a solver whose vector work is stand-alone launches (SpMV, fused multi-AXPY + dot)
+    and whose scalar recurrence lives in a device ScalarPlane: `trip()` enqueues one iteration
+    without reading anything back; the status block and the history ring are read once per
+    `check_interval` trips.  The plane's `done` flag gates every launch enqueued after the
+    reference's stopping test fired, so the outcome does not depend on the interval."""
+
+    def __init__(self, ctx, method):
+        from .device import ScalarPlane
+        cache = ctx.__dict__.setdefault("_scalar_planes", {})
+        P = cache.get(method)
+        if P is None or not P._h.value:
+            P = ScalarPlane(ctx, method)
+            cache[method] = P
+        self.ctx, self.P = ctx, P
+
+    def ops(self, ops, dots=()):
+        multi_axpy_dot(self.ctx, ops, dots, slot0=0)
+
+    def run(self, trip, check_interval, on_chunk=None):
+        """Returns (status, scalars) after the device latched `done`.  The gate is released on
+        every exit path: later stand-alone launches of this context run unconditionally again."""
+        P = self.P
+        try:
+            st, sc = P.status()
+            while not st.done:
+                for _ in range(max(1, int(check_interval))):
+                    trip()
+                st, sc = P.status()
+                if on_chunk is not None:
+                    on_chunk(st, sc, P.drain_history(st))
+            return st, sc
+        finally:
+            P.release_gate()
+
+
 def require_plan(method, op, precon, n):
     plan = resolve(op, precon, n)
     if plan is None:

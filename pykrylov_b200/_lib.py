@@ -60,6 +60,22 @@ class SolverStatus(C.Structure):
                 ("resid_norm", C.c_double), ("threshold", C.c_double), ("aux", C.c_double * 16)]
 
 
+class LlsParams(C.Structure):
+    _fields_ = [("window", C.c_int32), ("istop", C.c_int32), ("itn", C.c_int64), ("nmatvec", C.c_int64),
+                ("itnlim", C.c_int64), ("damp", C.c_double), ("atol", C.c_double), ("btol", C.c_double),
+                ("ctol", C.c_double), ("etol", C.c_double), ("rtol", C.c_double), ("shift", C.c_double),
+                ("eps", C.c_double)]
+
+
+class LlsStatus(C.Structure):
+    _fields_ = [("done", C.c_int32), ("istop", C.c_int32), ("itn", C.c_int64), ("nmatvec", C.c_int64),
+                ("hist_count", C.c_int64)]
+
+
+KRY_LLS_LSQR, KRY_LLS_LSMR, KRY_LLS_CRAIG, KRY_LLS_CRAIGMR, KRY_LLS_SYMMLQ = 0, 1, 2, 3, 4
+KRY_LLS_HIST_WIDTH = 4
+
+
 class Axpby(C.Structure):
     _fields_ = [("z", handle), ("u", handle), ("w", handle), ("a", C.c_double), ("b", C.c_double),
                 ("a_slot", C.c_int), ("b_slot", C.c_int), ("a_neg", C.c_int), ("b_neg", C.c_int)]
@@ -123,6 +139,14 @@ PROTOTYPES = {
                                      C.c_int]),
     "kry_scalars_read": (C.c_int, [handle, C.c_int, C.c_int, c_f64p]),
     "kry_scalars_write": (C.c_int, [handle, C.c_int, C.c_int, c_f64p]),
+    "kry_lls_create": (C.c_int, [handle, C.c_int, C.POINTER(handle)]),
+    "kry_lls_destroy": (C.c_int, [handle]),
+    "kry_lls_scalar_name": (C.c_char_p, [C.c_int, C.c_int]),
+    "kry_lls_setup": (C.c_int, [handle, C.POINTER(LlsParams), c_f64p, C.c_int]),
+    "kry_lls_step": (C.c_int, [handle, C.c_int]),
+    "kry_lls_status": (C.c_int, [handle, C.POINTER(LlsStatus), c_f64p, C.c_int]),
+    "kry_lls_history": (C.c_int, [handle, C.c_int64, C.c_int64, C.c_void_p]),
+    "kry_lls_release_gate": (C.c_int, [handle]),
     "kry_solver_create": (C.c_int, [handle, C.c_int, handle, C.POINTER(handle)]),
     "kry_solver_destroy": (C.c_int, [handle]),
     "kry_solver_set_precon_diag": (C.c_int, [handle, C.c_void_p, C.c_int]),

@@ -121,11 +121,14 @@ __global__ void to_dense_kernel(const int *rp, const int *col, const double *val
 }
 
 struct Scratch {                 // frees whatever was allocated, on every exit path
-    void *p[12];
+    static constexpr int kMax = 32;
+    void *p[kMax];
     int   n = 0;
     template <class T>
     int get(T **out, size_t bytes)
     {
+        *out = nullptr;
+        KRY_REQUIRE(n < kMax, KRY_ERR_STATE, "assemble: scratch table full");
         void *q = nullptr;
         int rc = kry_alloc(&q, bytes ? bytes : 8);
         if (rc == KRY_OK) p[n++] = q;

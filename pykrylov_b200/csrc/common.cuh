@@ -82,6 +82,7 @@ struct kry_ctx {
     int          partial_stride;
     int          partials_gen; // bumped whenever `partials` is reallocated (kry_ctx_ensure_partials)
     int         *never_done;   // device int == 0: "done" flag of the stand-alone ops
+    int         *gate;         // optional: `done` flag of a device-resident scalar plane (lls.cu) gating the stand-alone ops
     void        *flush_buf;
     size_t       flush_bytes;
     int64_t      launches;
@@ -193,6 +194,7 @@ void kry_ctx_release(kry_ctx *ctx);     // child destroyed: frees a closed conte
 #define KRY_CTX_LIVE(ctx, who)                                                      \
     KRY_REQUIRE(!(ctx)->closed, KRY_ERR_STATE, "%s: the context of this handle was destroyed", who)
 int  kry_alloc(void **p, size_t bytes);
+static inline const int *kry_gate(const kry_ctx *c) { return c->gate ? c->gate : c->never_done; }
 ReduceWs kry_ws(kry_ctx *ctx);
 
 // ---------------------------------------------------------------- device

@@ -54,7 +54,7 @@ extern "C" int kry_spmv(kry_csr *A, int trans, const kry_vec *x, kry_vec *y)
     EpiStoreDots<0> e;
     e.y = y->d;
     e.w[0] = nullptr;
-    return spmv_launch<0>(A, trans != 0, g, e, NoFin(), A->ctx->never_done, 0);
+    return spmv_launch<0>(A, trans != 0, g, e, NoFin(), kry_gate(A->ctx), 0);
 }
 
 template <int ND>
@@ -70,11 +70,11 @@ static int spmv_dot_nd(kry_csr *A, int trans, const kry_vec *x, kry_vec *y,
     if (c->nranks > 1 && A->halo.active) {
         // sharded: local sums -> all-reduce -> publish
         extern int kry_allreduce_sums(kry_ctx * c, int n);
-        KRY_TRY(spmv_launch<ND>(A, trans != 0, g, e, fin, c->never_done, 1));
+        KRY_TRY(spmv_launch<ND>(A, trans != 0, g, e, fin, kry_gate(c), 1));
         KRY_TRY(kry_allreduce_sums(c, ND));
-        return finalize_launch(c, fin, c->never_done);
+        return finalize_launch(c, fin, kry_gate(c));
     }
-    return spmv_launch<ND>(A, trans != 0, g, e, fin, c->never_done, 0);
+    return spmv_launch<ND>(A, trans != 0, g, e, fin, kry_gate(c), 0);
 }
 
 extern "C" int kry_spmv_dot(kry_csr *A, int trans, const kry_vec *x, kry_vec *y, int n_dots,
@@ -181,7 +181,7 @@ static int multi_axpy_nd(kry_ctx *c, int64_t n, int n_ops, const kry_axpby *ops,
     }
     if constexpr (ND == 0) {
         b.du[0] = b.dw[0] = nullptr;
-        return vec_map_launch(c, n, b, c->never_done);
+        return vec_map_launch(c, n, b, kry_gate(c));
     } else {
         for (int d = 0; d < ND; ++d) {
             b.du[d] = dots[d].u->d;
@@ -190,11 +190,11 @@ static int multi_axpy_nd(kry_ctx *c, int64_t n, int n_ops, const kry_axpby *ops,
         SlotFin fin{c->scalars + slot0, ND};
         if (c->nranks > 1) {
             extern int kry_allreduce_sums(kry_ctx * c, int n);
-            KRY_TRY((vec_pass_launch<ND>(c, n, b, fin, c->never_done, 1)));
+            KRY_TRY((vec_pass_launch<ND>(c, n, b, fin, kry_gate(c), 1)));
             KRY_TRY(kry_allreduce_sums(c, ND));
-            return finalize_launch(c, fin, c->never_done);
+            return finalize_launch(c, fin, kry_gate(c));
         }
-        return vec_pass_launch<ND>(c, n, b, fin, c->never_done, 0);
+        return vec_pass_launch<ND>(c, n, b, fin, kry_gate(c), 0);
     }
 }
 

@@ -141,7 +141,7 @@ class Context(object):
     def close(self):
         """Destroy the context after every object that still lives on it."""
         if getattr(self, "_h", None) is not None and self._h.value:
-            order = {"DeviceSolver": 0, "DeviceCsr": 1, "DeviceVector": 2}
+            order = {"DeviceSolver": 0, "ScalarPlane": 0, "DeviceCsr": 1, "DeviceVector": 2}
             for obj in sorted(list(self._children), key=lambda o: order.get(type(o).__name__, 3)):
                 obj._release()
             L.lib.kry_ctx_destroy(self._h)
@@ -496,6 +496,83 @@ def multi_axpy_dot(ctx, ops, dots=(), slot0=0):
         darr[k].u = u._h
         darr[k].w = w._h
     call("kry_multi_axpy_dot", ctx._h, len(ops), arr, len(dots), darr, int(slot0))
+
+
+class ScalarPlane(object):
+    """Device-resident scalar plane of LSQR / LSMR / CRAIG / CRAIG-MR / SYMMLQ (``kry_lls``):
+    named scalars in, ``step(phase)`` enqueues one single-thread recurrence step, the status block
+    and the per-iteration history ring come back at the caller's check interval."""
+    METHODS = {"lsqr": L.KRY_LLS_LSQR, "lsmr": L.KRY_LLS_LSMR, "craig": L.KRY_LLS_CRAIG,
+               "craigmr": L.KRY_LLS_CRAIGMR, "symmlq": L.KRY_LLS_SYMMLQ}
+    # coefficient slots of the context's scalar block (csrc/lls.cu)
+    D0, D1, D2 = 0, 1, 2
+    ALPHA, U_DIV, NV_A, NV_B, V_DIV = 8, 9, 10, 11, 12
+    C0, C1, C2, C3, C4, C5, C6, C7 = 13, 14, 15, 16, 17, 18, 19, 20
+    _names = {}
+
+    def __init__(self, ctx, method):
+        self.ctx = ctx
+        self.method = method
+        self._h = L.handle()
+        call("kry_lls_create", ctx._h, self.METHODS[method], C.byref(self._h))
+        if method not in self._names:
+            names, i = [], 0
+            while True:
+                nm = L.lib.kry_lls_scalar_name(self.METHODS[method], i)
+                if not nm:
+                    break
+                names.append(nm.decode())
+                i += 1
+            self._names[method] = names
+        self.names = self._names[method]
+        self._hist_read = 0
+        ctx._adopt(self)
+
+    def _release(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            L.lib.kry_lls_destroy(self._h)
+            self._h = L.handle()
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def setup(self, scalars, window=5, istop=0, itn=0, nmatvec=0, itnlim=0, damp=0.0, atol=0.0, btol=0.0,
+              ctol=0.0, etol=0.0, rtol=0.0, shift=0.0, eps=2.220446049250313e-16):
+        unknown = set(scalars) - set(self.names)
+        if unknown:
+            raise KeyError("unknown %s scalars: %s" % (self.method, sorted(unknown)))
+        p = L.LlsParams()
+        p.window, p.istop, p.itn, p.nmatvec, p.itnlim = int(window), int(istop), int(itn), int(nmatvec), int(itnlim)
+        p.damp, p.atol, p.btol, p.ctol = float(damp), float(atol), float(btol), float(ctol)
+        p.etol, p.rtol, p.shift, p.eps = float(etol), float(rtol), float(shift), float(eps)
+        vals = (C.c_double * len(self.names))(*[float(scalars.get(nm, 0.0)) for nm in self.names])
+        call("kry_lls_setup", self._h, C.byref(p), vals, len(self.names))
+        self._hist_read = 0
+
+    def step(self, phase):
+        call("kry_lls_step", self._h, int(phase))
+
+    def status(self):
+        """(status struct, dict of the method's scalars) -- one synchronising D2H."""
+        st = L.LlsStatus()
+        vals = (C.c_double * len(self.names))()
+        call("kry_lls_status", self._h, C.byref(st), vals, len(self.names))
+        return st, dict(zip(self.names, vals[:len(self.names)]))
+
+    def drain_history(self, st):
+        count = st.hist_count - self._hist_read
+        if count <= 0:
+            return np.empty((0, L.KRY_LLS_HIST_WIDTH))
+        buf = np.empty((count, L.KRY_LLS_HIST_WIDTH), dtype=np.float64)
+        call("kry_lls_history", self._h, self._hist_read, count, _ptr(buf))
+        self._hist_read = st.hist_count
+        return buf
+
+    def release_gate(self):
+        call("kry_lls_release_gate", self._h)
 
 
 METHODS = {"cg": L.KRY_CG, "bicgstab": L.KRY_BICGSTAB, "cgs": L.KRY_CGS, "tfqmr": L.KRY_TFQMR,

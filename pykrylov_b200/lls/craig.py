@@ -131,7 +131,52 @@ class CRAIGFramework(KrylovMethod):
             self.norms.append(xNrgNorm2)
             self.resids.append(r2norm)
 
-        while itn < itnlim and not x_is_zero:
+        csr = _engine.plane_csr(A)
+        on_device = (csr is not None and M is None and N is None and not show and not store_iterates
+                     and not x_is_zero and itnlim > 0)
+        if on_device:
+            # device-resident loop (scalar plane in csrc/lls.cu, see lsqr.py)
+            from ..device import ScalarPlane as SL
+            loop = _engine.PlaneLoop(B.ctx, "craig")
+            loop.P.setup(dict(alpha=alpha, beta=beta, c=c, s=s, tau=tau, zeta=zeta, eta=eta, xi=xi, rnorm=rnorm,
+                              xnorm=xnorm, r1norm=r1norm, r2norm=r2norm, Arnorm=Arnorm, rNrgNorm2=rNrgNorm2,
+                              xNrgNorm2=xNrgNorm2, bnorm=bnorm),
+                         window=window, itnlim=itnlim, btol=btol, etol=etol)
+
+            def trip():
+                csr.spmv(v, tm)
+                loop.ops([dict(z=Mu, u=tm, w=Mu, a=1.0, b_slot=SL.ALPHA, b_neg=1)], [(Mu, Mu)])
+                loop.P.step(1)
+                loop.ops([dict(z=u, u=u, a_slot=SL.U_DIV, a_div=True)])
+                csr.spmv(u, tn, trans=True)
+                loop.ops([dict(z=Nv, u=tn, w=Nv, a_slot=SL.NV_A, b_slot=SL.NV_B)], [(Nv, Nv)])
+                loop.P.step(2)                              # alpha, rotations, norms, stopping tests
+                loop.ops([dict(z=v, u=v, a_slot=SL.V_DIV, a_div=True)])
+                loop.ops([dict(z=d, u=u, w=d, a=1.0, b_slot=SL.C0, b_neg=1), dict(z=d, u=d, a_slot=SL.C1, a_div=True),
+                          dict(z=r, u=r, w=d, a=1.0, b_slot=SL.C2)])
+                loop.ops([dict(z=wbar, u=wbar, a_slot=SL.C3), dict(z=w, u=v, w=wbar, a_slot=SL.C4, b_slot=SL.C5),
+                          dict(z=wbar, u=wbar, w=v, a_slot=SL.C4, a_neg=1, b_slot=SL.C5),
+                          dict(z=x, u=x, w=w, a=1.0, b_slot=SL.C6)])
+                loop.P.step(9)                              # latch `done` behind this trip's updates
+
+            def replay(st_, sc_, hist):
+                for r2, arn, nrg, direrr in hist:
+                    if store_resids:
+                        self.norms.append(nrg)
+                        self.resids.append(r2)
+                        self.normal_eqns_resids.append(arn)
+                    if direrr == direrr:
+                        self.dir_errors_d_window.append(direrr)
+
+            if not csr.symmetric:
+                csr.build_transpose()
+            st_, sc = loop.run(trip, self.check_interval, replay)
+            itn, istop = int(st_.itn), int(st_.istop)
+            r1norm, r2norm, Arnorm, xnorm = sc["r1norm"], sc["r2norm"], sc["Arnorm"], sc["xnorm"]
+            xNrgNorm2, trncDirErr = sc["xNrgNorm2"], sc["trncDirErr"]
+            A._nMatvec += 2 * itn
+
+        while itn < itnlim and not x_is_zero and not on_device:
             itn += 1
             B.apply(A, v, tm)
             if M is None:

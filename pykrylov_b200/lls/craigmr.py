@@ -103,7 +103,49 @@ class CRAIGMRFramework(KrylovMethod):
         istop = 0
         if store_resids:
             self.norms.append(xNrgNorm2)
-        while itn < itnlim:
+        csr = _engine.plane_csr(A)
+        on_device = (csr is not None and M is None and N is None and not store_iterates and itnlim > 0)
+        if on_device:
+            # device-resident loop (scalar plane in csrc/lls.cu, see lsqr.py)
+            from ..device import ScalarPlane as SL
+            loop = _engine.PlaneLoop(B.ctx, "craigmr")
+            loop.P.setup(dict(alpha=alpha, beta=beta, c=c, s=s, zeta_hat=zeta_hat, alpha_tilde=alpha_tilde, theta=theta,
+                              xNrgNorm2=xNrgNorm2), window=window, itnlim=itnlim, etol=etol)
+
+            def trip():
+                csr.spmv(v, tm)
+                loop.ops([dict(z=Mu, u=tm, w=Mu, a=1.0, b_slot=SL.ALPHA, b_neg=1)], [(Mu, Mu)])
+                loop.P.step(1)
+                loop.ops([dict(z=u, u=u, a_slot=SL.U_DIV, a_div=True)])
+                csr.spmv(u, tn, trans=True)
+                loop.ops([dict(z=Nv, u=tn, w=Nv, a_slot=SL.NV_A, b_slot=SL.NV_B)], [(Nv, Nv)])
+                loop.P.step(2)                              # alpha, rotations, stopping tests
+                loop.ops([dict(z=v, u=v, a_slot=SL.V_DIV, a_div=True)])
+                loop.ops([dict(z=dbar, u=d, w=dbar, a=1.0, b_slot=SL.C0, b_neg=1), dict(z=dbar, u=dbar, a_slot=SL.C1, a_div=True),
+                          dict(z=d, u=u, w=d, a=1.0, b_slot=SL.C2, b_neg=1), dict(z=d, u=d, a_slot=SL.C3, a_div=True)])
+                loop.ops([dict(z=x, u=x, w=dbar, a=1.0, b_slot=SL.C4)])
+                loop.P.step(9)                              # latch `done` behind this trip's updates
+
+            seen = [0]
+
+            def replay(st_, sc_, hist):
+                for nrg, azeta, direrr, _ in hist:
+                    seen[0] += 1
+                    print(seen[0], nrg)                                     # (sic) craigmr.py:190
+                    if store_resids:
+                        self.norms.append(nrg)
+                        self.normal_eqns_resids.append(azeta)
+                    if direrr == direrr:
+                        self.dir_errors_window.append(direrr)
+
+            if not csr.symmetric:
+                csr.build_transpose()
+            st_, sc = loop.run(trip, self.check_interval, replay)
+            itn, istop = int(st_.itn), int(st_.istop)
+            xNrgNorm2, trncDirErr = sc["xNrgNorm2"], sc["trncDirErr"]
+            A._nMatvec += 2 * itn
+
+        while itn < itnlim and not on_device:
             itn += 1
             B.apply(A, v, tm)
             if M is None:

@@ -158,7 +158,50 @@ class LSMRFramework(KrylovMethod):
             self.resids.append(normr)
             self.normal_eqns_resids.append(normar)
 
-        while itn < itnlim:
+        csr = _engine.plane_csr(A)
+        on_device = (csr is not None and M is None and N is None and not show and not store_iterates and itnlim > 0)
+        if on_device:
+            # device-resident loop (scalar plane in csrc/lls.cu, see lsqr.py)
+            from ..device import ScalarPlane as SL
+            loop = _engine.PlaneLoop(B.ctx, "lsmr")
+            loop.P.setup(dict(alpha=alpha, beta=beta, zetabar=zetabar, alphabar=alphabar, rho=rho, rhobar=rhobar,
+                              cbar=cbar, sbar=sbar, betadd=betadd, betad=betad, rhodold=rhodold,
+                              tautildeold=tautildeold, thetatilde=thetatilde, zeta=zeta, d=d, normA2=normA2,
+                              maxrbar=maxrbar, minrbar=minrbar, normA=normA, condA=condA, normx=normx,
+                              normb=normb, normr=normr, normar=normar),
+                         window=window, itnlim=itnlim, damp=damp, atol=atol, btol=btol, ctol=ctol, etol=etol)
+
+            def trip():
+                csr.spmv(v, tm)
+                loop.ops([dict(z=Mu, u=tm, w=Mu, a=1.0, b_slot=SL.ALPHA, b_neg=1)], [(Mu, Mu)])
+                loop.P.step(1)
+                loop.ops([dict(z=u, u=u, a_slot=SL.U_DIV, a_div=True)])
+                csr.spmv(u, tn, trans=True)
+                loop.ops([dict(z=Nv, u=tn, w=Nv, a_slot=SL.NV_A, b_slot=SL.NV_B)], [(Nv, Nv)])
+                loop.P.step(2)
+                loop.ops([dict(z=v, u=v, a_slot=SL.V_DIV, a_div=True), dict(z=hbar, u=h, w=hbar, a=1.0, b_slot=SL.C0),
+                          dict(z=x, u=x, w=hbar, a=1.0, b_slot=SL.C1), dict(z=h, u=v, w=h, a=1.0, b_slot=SL.C2)],
+                         [(x, x)])
+                loop.P.step(3)
+
+            def replay(st_, sc_, hist):
+                for nr, nar, nrg, direrr in hist:
+                    if store_resids:
+                        self.norms.append(nrg)
+                        self.resids.append(nr)
+                        self.normal_eqns_resids.append(nar)
+                    if direrr == direrr:
+                        self.dir_errors_window.append(direrr)
+
+            if not csr.symmetric:
+                csr.build_transpose()
+            st_, sc = loop.run(trip, self.check_interval, replay)
+            itn, istop = int(st_.itn), int(st_.istop)
+            normr, normar, normA, condA, normx = sc["normr"], sc["normar"], sc["normA"], sc["condA"], sc["normx"]
+            xNrgNorm2 = sc["xNrgNorm2"]
+            A._nMatvec += 2 * itn
+
+        while itn < itnlim and not on_device:
             itn += 1
             B.apply(A, v, tm)
             if M is None:

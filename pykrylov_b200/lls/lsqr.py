@@ -149,7 +149,49 @@ class LSQRFramework(KrylovMethod):
             self.resids.append(r2norm)
             self.normal_eqns_resids.append(Arnorm)
 
-        while itn < itnlim and not x_is_zero:
+        csr = _engine.plane_csr(A)
+        on_device = (csr is not None and M is None and N is None and not show and not store_iterates
+                     and not x_is_zero and itnlim > 0)
+        if on_device:
+            # device-resident loop: the scalar plane (rotations, norms, stopping tests) runs in
+            # csrc/lls.cu, the host enqueues whole trips and reads one status block per check interval
+            from ..device import ScalarPlane as SL
+            loop = _engine.PlaneLoop(B.ctx, "lsqr")
+            loop.P.setup(dict(alpha=alpha, beta=beta, rhobar=rhobar, phibar=phibar, bnorm=bnorm, cs2=cs2, sn2=sn2,
+                              rnorm=rnorm, r1norm=r1norm, r2norm=r2norm, Arnorm=Arnorm),
+                         window=window, itnlim=itnlim, damp=damp, atol=atol, btol=btol, ctol=ctol, etol=etol)
+
+            def trip():
+                csr.spmv(v, tm)                                                          # A v
+                loop.ops([dict(z=Mu, u=tm, w=Mu, a=1.0, b_slot=SL.ALPHA, b_neg=1)], [(Mu, Mu)])
+                loop.P.step(1)                                                           # beta, |A|
+                loop.ops([dict(z=u, u=u, a_slot=SL.U_DIV, a_div=True)])
+                csr.spmv(u, tn, trans=True)                                              # A' u
+                loop.ops([dict(z=Nv, u=tn, w=Nv, a_slot=SL.NV_A, b_slot=SL.NV_B)], [(Nv, Nv)])
+                loop.P.step(2)                                                           # alpha, rotations
+                loop.ops([dict(z=v, u=v, a_slot=SL.V_DIV, a_div=True), dict(z=dk, u=w, a_slot=SL.C0),
+                          dict(z=x, u=x, w=w, a=1.0, b_slot=SL.C1), dict(z=w, u=w, w=v, a_slot=SL.C2, b=1.0)],
+                         [(dk, dk)])
+                loop.P.step(3)                                                           # norms, stopping tests
+
+            def replay(st_, sc_, hist):
+                for r2, arn, direrr, _ in hist:
+                    if store_resids:
+                        self.resids.append(r2)
+                        self.normal_eqns_resids.append(arn)
+                    if direrr == direrr:
+                        self.dir_errors_window.append(direrr)
+
+            if not csr.symmetric:
+                csr.build_transpose()
+            st_, sc = loop.run(trip, self.check_interval, replay)
+            itn, istop = int(st_.itn), int(st_.istop)
+            Anorm, Acond, Arnorm, xnorm = sc["Anorm"], sc["Acond"], sc["Arnorm"], sc["xnorm"]
+            r1norm, r2norm = sc["r1norm"], sc["r2norm"]
+            xNrgNorm2, trncDirErr = sc["xNrgNorm2"], sc["trncDirErr"]
+            A._nMatvec += 2 * itn
+
+        while itn < itnlim and not x_is_zero and not on_device:
             itn += 1
             # beta M u = A v - alpha M u
             B.apply(A, v, tm)

@@ -123,7 +123,41 @@ class Symmlq(KrylovMethod):
         log("   Itn     x(1)(cg)  normr(cg)  r(minres)    bstep    anorm    acond")
         log("%6g %12.5e %10.3e %10.3e  %8.1e" % (itn, x1cg, cgnorm, qrnorm, (bstep / beta1) if beta1 else 0.0))
 
-        if not done:
+        csr = _engine.plane_csr(op)
+        on_device = (csr is not None and precon is None and not verbose and not store_iterates and not done)
+        if on_device:
+            # device-resident loop: the scalar plane of symmlq.py:235-355 runs in csrc/lls.cu; the host
+            # enqueues whole Lanczos trips and reads one status block per check interval
+            from ..device import ScalarPlane as SL
+            loop = _engine.PlaneLoop(B.ctx, "symmlq")
+            loop.P.setup(dict(beta1=beta1, beta=beta, oldb=oldb, alfa=alfa, tnorm=tnorm, ynorm2=ynorm2, gbar=gbar,
+                              dbar=dbar, rhs1=rhs1, rhs2=rhs2, snprod=snprod, bstep=bstep, gmax=gmax, gmin=gmin,
+                              cgnorm=cgnorm, qrnorm=qrnorm),
+                         istop=istop, itn=itn, nmatvec=nMatvec, itnlim=matvec_max, rtol=rtol, eps=eps)
+
+            def trip():
+                loop.P.step(1)                                       # norms, stopping tests; s = 1/beta
+                loop.ops([dict(z=v, u=y, a_slot=SL.C0)])             # v = s*y
+                csr.spmv(v, y)
+                ops = [dict(z=y, u=y, w=v, a=1.0, b=-shift)] if shift is not None else []
+                ops.append(dict(z=y, u=y, w=r1, a=1.0, b_slot=SL.C1))
+                loop.ops(ops, [(v, y)])
+                loop.P.step(2)                                       # alfa
+                loop.ops([dict(z=y, u=y, w=r2, a=1.0, b_slot=SL.C2), dict(z=r1, u=r2, a=1.0), dict(z=r2, u=y, a=1.0)],
+                         [(r2, y)])
+                loop.P.step(3)                                       # beta, rotation, step lengths
+                loop.ops([dict(z=tmp, u=w, w=v, a_slot=SL.C3, b_slot=SL.C4), dict(z=x, u=x, w=tmp, a=1.0, b=1.0),
+                          dict(z=w, u=w, w=v, a_slot=SL.C5, b_slot=SL.C6, b_neg=1)])
+
+            st_, sc = loop.run(trip, self.check_interval)
+            istop, itn = int(st_.istop), int(st_.itn)
+            op._nMatvec += int(st_.nmatvec) - nMatvec
+            nMatvec = int(st_.nmatvec)
+            anorm, ynorm, acond = sc["anorm"], sc["ynorm"], sc["acond"]
+            cgnorm, lqnorm, qrnorm, diag = sc["cgnorm"], sc["lqnorm"], sc["qrnorm"], sc["diag"]
+            rhs1, snprod, bstep, ynorm2 = sc["rhs1"], sc["snprod"], sc["bstep"], sc["ynorm2"]
+
+        if not done and not on_device:
             while nMatvec < matvec_max:
                 itn += 1
                 anorm = np.sqrt(tnorm)

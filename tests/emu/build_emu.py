@@ -13,7 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "pykrylov_b200", "csrc")
 OUT = os.path.join(HERE, "_build", "libkrylov_emu.so")
-SOURCES = [os.path.join(CSRC, "solvers.cu"), os.path.join(CSRC, "ops.cu"), os.path.join(CSRC, "comm.cu"),
+SOURCES = [os.path.join(CSRC, "solvers.cu"), os.path.join(CSRC, "ops.cu"), os.path.join(CSRC, "lls.cu"),
+           os.path.join(CSRC, "comm.cu"),
            os.path.join(HERE, "emu_context.cpp")]
 DEPS = SOURCES + [os.path.join(CSRC, h) for h in ("common.cuh", "spmv.cuh", "launch.cuh", "solver.cuh")] + \
     [os.path.join(HERE, "emu_device.h"), os.path.join(ROOT, "include", "krylov_b200.h")]

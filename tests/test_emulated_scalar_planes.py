@@ -1,0 +1,112 @@
+"""Device-resident scalar planes of LSQR / LSMR / CRAIG / CRAIG-MR / SYMMLQ (csrc/lls.cu) on the
+host emulation of the device logic: the step kernels -- the library's own lls.cu built for the
+host -- must reproduce the host-driven scalar path of the same solver BIT FOR BIT (that path is
+pinned bit-for-bit to the live reference in tests/test_host_solvers.py), for any check interval,
+while the host synchronises only once per check interval instead of three times per trip."""
+import io
+from contextlib import redirect_stdout
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import mtx
+from oracle.csr_ref import CsrRef, load_mtx
+
+
+def _solve(K, op, b, ctx, eng, device_plane, interval, **kw):
+    saved = eng.plane_csr
+    if not device_plane:
+        eng.plane_csr = lambda op_: None
+    try:
+        k = K(op, context=ctx, check_interval=interval)
+        with redirect_stdout(io.StringIO()):
+            ret = k.solve(b, **kw)
+    finally:
+        eng.plane_csr = saved
+    return k, ret
+
+
+CASES = [("lsqr", dict()), ("lsqr", dict(damp=0.3)), ("lsqr", dict(atol=0.0, btol=0.0, etol=0.0, itnlim=23)),
+         ("lsmr", dict()), ("lsmr", dict(damp=0.2)), ("craig", dict()), ("craigmr", dict())]
+
+
+@pytest.mark.parametrize("name,kw", CASES)
+def test_scalar_plane_on_device_equals_host_path(emu_ctx, name, kw):
+    import pykrylov_b200._engine as eng
+    from pykrylov_b200 import _lib as L
+    from pykrylov_b200.linop import linop_from_scipy
+    from pykrylov_b200.lls import LSQRFramework, LSMRFramework, CRAIGFramework, CRAIGMRFramework
+    K = dict(lsqr=LSQRFramework, lsmr=LSMRFramework, craig=CRAIGFramework, craigmr=CRAIGMRFramework)[name]
+    rng = np.random.default_rng(14)
+    if name in ("craig", "craigmr"):
+        R = sp.random(90, 150, density=0.1, random_state=5, format="csr")
+        b = R @ rng.standard_normal(150)
+    else:
+        R = sp.random(600, 200, density=0.03, random_state=7, format="csr")
+        b = np.random.default_rng(7).standard_normal(600)
+    R.sort_indices()
+    op = linop_from_scipy(R, context=emu_ctx)
+    host, rh = _solve(K, op, b, emu_ctx, eng, False, 32, store_resids=True, **kw)
+    syncs = []
+    real = L.lib.kry_lls_status
+
+    def counting(*a):
+        syncs.append(1)
+        return real(*a)
+    for interval in (1, 7, 32):
+        del syncs[:]
+        L.lib.kry_lls_status = counting
+        try:
+            devp, rd = _solve(K, op, b, emu_ctx, eng, True, interval, store_resids=True, **kw)
+        finally:
+            L.lib.kry_lls_status = real
+        assert np.array_equal(devp.x, host.x), interval
+        for attr in ("resids", "normal_eqns_resids", "norms"):
+            if hasattr(host, attr):
+                assert getattr(devp, attr) == getattr(host, attr), (attr, interval)
+        for attr in ("istop", "itn", "nMatvec", "r1norm", "r2norm", "Anorm", "Acond", "Arnorm", "xnorm"):
+            if hasattr(host, attr) and name != "lsmr":
+                assert getattr(devp, attr) == getattr(host, attr), (attr, interval)
+        if rh is not None:                                    # LSMR returns its results as a tuple
+            assert all(np.array_equal(a, c) for a, c in zip(rd, rh))
+        itn = devp.itn if name != "lsmr" else rd[2]
+        assert 1 <= len(syncs) <= itn // interval + 3, (len(syncs), itn, interval)
+    # truncated direct-error estimates: np.linalg.norm of the window on the host, an ordered sum of
+    # squares on the device -- equal to rounding
+    for attr in ("dir_errors_window", "dir_errors_d_window"):
+        a, h = np.array(getattr(devp, attr, [])), np.array(getattr(host, attr, []))
+        assert len(a) == len(h) and (len(a) == 0 or np.max(np.abs(a - h) / np.abs(h)) <= 1e-15)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(shift=0.5), dict(matvec_max=40), dict(rtol=1e-14)])
+def test_symmlq_scalar_plane_on_device_equals_host_path(emu_ctx, kw):
+    import pykrylov_b200._engine as eng
+    from pykrylov_b200.linop import csr_operator
+    from pykrylov_b200.symmlq import Symmlq
+    M = load_mtx(mtx("jpwh_991"))
+    S0 = M.to_scipy()
+    S = CsrRef.from_scipy((S0 + S0.T) * 0.5)
+    n = S.shape[0]
+    op = csr_operator(S.shape, S.indptr, S.indices, S.data, symmetric=True, context=emu_ctx)
+    rhs = S.matvec(np.ones(n))
+    host, _ = _solve(Symmlq, op, rhs, emu_ctx, eng, False, 32, **kw)
+    for interval in (1, 5, 64):
+        devp, _ = _solve(Symmlq, op, rhs, emu_ctx, eng, True, interval, **kw)
+        assert np.array_equal(devp.x, host.x)
+        for attr in ("nMatvec", "istop", "itn", "anorm", "acond", "xNorm", "residNorm", "converged"):
+            assert getattr(devp, attr) == getattr(host, attr), (attr, interval)
+
+
+def test_stand_alone_launches_run_again_after_a_plane_solve(emu_ctx):
+    """The plane's `done` flag gates the context's stand-alone launches only while a plane loop is
+    running: afterwards SpMV and fused vector ops execute unconditionally again."""
+    from pykrylov_b200.linop import linop_from_scipy
+    from pykrylov_b200.lls import LSQRFramework
+    R = sp.random(60, 20, density=0.2, random_state=1, format="csr")
+    R.sort_indices()
+    op = linop_from_scipy(R, context=emu_ctx)
+    b = np.random.default_rng(2).standard_normal(60)
+    LSQRFramework(op, context=emu_ctx).solve(b)
+    x = np.random.default_rng(3).standard_normal(20)
+    assert np.array_equal(op * x, CsrRef.from_scipy(R).matvec(x))
