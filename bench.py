@@ -296,6 +296,92 @@ def run_reference_cg(g, max_steps, warmup, budget_s):
                       "host has %d logical cores" % (done, warmup, kind, g, g, n, blas_threads, os.cpu_count() or 0)}
 
 
+def _time_iterations(ctx, S, setup, steps, warmup, reps=3):
+    """Best of `reps`: `steps` device-resident iterations after `warmup`, CUDA events."""
+    best = float("inf")
+    for _ in range(reps):
+        setup()
+        S.iterate(warmup)
+        ctx.sync()
+        ctx.timer_start()
+        S.iterate(steps)
+        best = min(best, ctx.timer_stop() / steps)
+        assert not S.status().done, "the timed iterations were not all live"
+    return best
+
+
+def other_config_minres(ctx, peak, peak_src):
+    """BASELINE.json configs[2]: MINRES on kron(I_1009, sym(jpwh_991)), N = 999 919."""
+    from pykrylov_b200.device import DeviceCsr, DeviceSolver
+    from pykrylov_b200.gallery import kron_sym_jpwh
+    shape, ip, ix, dv = kron_sym_jpwh(os.path.join(ROOT, "tests", "golden", "jpwh_991.mtx"), 1009)
+    n, nnz = shape[0], len(dv)
+    A = DeviceCsr.from_arrays(ctx, shape, ip, ix, dv, symmetric=True)
+    ones = A.input_vector()
+    ones.fill(1.0)
+    from pykrylov_b200.device import DeviceVector
+    rhs = DeviceVector(ctx, n)
+    A.spmv(ones, rhs)
+    S = DeviceSolver(ctx, "minres", A)
+    # (t1 <= 1 fires after ~90 trips on this system: time inside the live range)
+    ms = _time_iterations(ctx, S, lambda: S.setup_dev(rhs, abstol=0.0, reltol=0.0, matvec_max=10 ** 9, rtol=0.0,
+                                                      etol=0.0, window=5), steps=48, warmup=16)
+    it_bytes = spmv_bytes(n, nnz) + 96 * n
+    S.setup_dev(rhs, abstol=0.0, reltol=0.0, matvec_max=5 * n, rtol=1e-12, etol=1e-6, window=5)
+    st = S.run(16)
+    out = {"workload": "BASELINE.json configs[2]: MINRES fp64 on kron(I_1009, sym(jpwh_991))", "rows": n, "nnz": nnz,
+           "metric": "minres_iters_per_s", "value": 1e3 / ms, "unit": UNIT, "ms_per_step": ms,
+           "to_convergence": {"istop": int(st.istop), "itn": int(st.n_iter), "rnorm": st.resid_norm},
+           "roofline": {"bound": "hbm", "kernel": "whole MINRES iteration (SpMV + 96 N bytes, SURVEY.md 8d)",
+                        "achieved": it_bytes / ms / 1e6, "peak": peak, "unit": "GB/s",
+                        "frac": it_bytes / ms / 1e6 / peak, "traffic": None, "peak_source": peak_src,
+                        "algorithmic_bytes_per_step": it_bytes,
+                        "note": "working set 153 MB ~ L2: two dependent launches of ~25 us, latency-bound"}}
+    S._release()
+    A._release()
+    return out
+
+
+def other_config_bicgstab(ctx, peak, peak_src):
+    """BASELINE.json configs[3]: Bi-CGSTAB on the 7-pt convection-diffusion operator, grid 215^3."""
+    from pykrylov_b200.device import DeviceCsr, DeviceSolver, DeviceVector
+    m = 215
+    n = m ** 3
+    A = DeviceCsr.convdiff3d(ctx, m, 0.5, build_transpose=True)
+    ones = DeviceVector(ctx, n).fill(1.0)
+    rhs = DeviceVector(ctx, n)
+    A.spmv(ones, rhs)
+    S = DeviceSolver(ctx, "bicgstab", A)
+    ms = _time_iterations(ctx, S, lambda: S.setup_dev(rhs, abstol=0.0, reltol=0.0, matvec_max=10 ** 12),
+                          steps=60, warmup=6, reps=2)
+    sp_b = spmv_bytes(n, A.nnz)
+    it_bytes = 2 * sp_b + 120 * n
+    y = DeviceVector(ctx, n)
+    spmv = {}
+    for trans, key in ((False, "A_x"), (True, "AT_x")):
+        for _ in range(3):
+            A.spmv(ones, y, trans=trans)
+        ctx.sync()
+        ctx.timer_start()
+        for _ in range(20):
+            A.spmv(ones, y, trans=trans)
+        t = ctx.timer_stop() / 20
+        spmv[key] = {"ms": t, "GBs": sp_b / t / 1e6, "frac": sp_b / t / 1e6 / peak}
+    out = {"workload": "BASELINE.json configs[3]: Bi-CGSTAB fp64, 7-pt convection-diffusion grid 215^3", "rows": n,
+           "nnz": int(A.nnz), "metric": "bicgstab_iters_per_s", "value": 1e3 / ms, "unit": UNIT, "ms_per_step": ms,
+           "spmv": spmv,
+           "roofline": {"bound": "hbm", "kernel": "whole Bi-CGSTAB iteration (2 SpMV + 120 N bytes, SURVEY.md 8d; the "
+                                                  "launch plan moves 2 SpMV + 104 N)",
+                        "achieved": it_bytes / ms / 1e6, "peak": peak, "unit": "GB/s",
+                        "frac": it_bytes / ms / 1e6 / peak, "traffic": None, "peak_source": peak_src,
+                        "algorithmic_bytes_per_step": it_bytes,
+                        "moved_bytes_per_step": 2 * sp_b + 104 * n,
+                        "frac_of_moved_bytes": (2 * sp_b + 104 * n) / ms / 1e6 / peak}}
+    S._release()
+    A._release()
+    return out
+
+
 def load_traffic():
     """ncu-measured DRAM bytes per launch of the dominant kernel (profiles/), or None."""
     try:
@@ -429,6 +515,16 @@ def main_ours(args):
         except Exception as exc:                      # never lose the headline line over the side leg
             extra["config5_one_gpu"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
 
+    if world == 1 and g == G_CONFIG2 and not args.no_other_configs:
+        # BASELINE.json configs[2] and configs[3] on this GPU, each with its own roofline object
+        # (whole-iteration bytes of SURVEY.md 8d over the device-timed iteration), so that these
+        # numbers are driver-visible too.  Never lose the headline line over a side leg.
+        for name, leg in (("config3_minres", other_config_minres), ("config4_bicgstab", other_config_bicgstab)):
+            try:
+                extra[name] = leg(ctx, peak, peak_src)
+            except Exception as exc:
+                extra[name] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline(g)
@@ -499,6 +595,8 @@ def main():
     ap.add_argument("--no-single", action="store_true", help="skip the 1-GPU same-workload leg (N>1)")
     ap.add_argument("--no-config5", action="store_true",
                     help="N=1: skip the side leg that times the 10^8-row operator of configs[4] on this GPU")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="N=1: skip the side legs for BASELINE configs[2] (MINRES) and configs[3] (Bi-CGSTAB)")
     ap.add_argument("--cg-fuse", type=int, default=None, choices=[0, 1, 2],
                     help="CG launch plan (KRY_OPT_CG_FUSE); default: the library's default")
     ap.add_argument("--cg-fuse-shards", type=int, default=None, choices=[0, 1],

@@ -79,7 +79,7 @@ def test_our_arm_code_path_under_emulation(emu_ctx, capsys, monkeypatch):
     monkeypatch.setattr(bench, "G_CONFIG5", 40)
     monkeypatch.setattr(comm, "init_from_env", lambda *a, **k: (emu_ctx, 0, 1))
     args = argparse.Namespace(gpus=1, steps=30, warmup=3, impl="ours", grid=0, no_cpu=True, no_single=False,
-                              no_config5=False, cg_fuse=None, cg_fuse_shards=None, nccl_allreduce=False, halo_p2p=None)
+                              no_config5=False, no_other_configs=True, cg_fuse=None, cg_fuse_shards=None, nccl_allreduce=False, halo_p2p=None)
     bench.main_ours(args)
     lines = [ln for ln in capsys.readouterr().out.splitlines() if ln.strip()]
     assert len(lines) == 1
@@ -138,7 +138,7 @@ def test_our_arm_multi_rank_code_path_under_emulation(emu_ctx, capsys, monkeypat
     def body(rank):
         local.rank = rank
         args = argparse.Namespace(gpus=world, steps=24, warmup=3, impl="ours", grid=0, no_cpu=True, no_single=False,
-                                  no_config5=False, cg_fuse=None, cg_fuse_shards=None, nccl_allreduce=False, halo_p2p=None)
+                                  no_config5=False, no_other_configs=True, cg_fuse=None, cg_fuse_shards=None, nccl_allreduce=False, halo_p2p=None)
         try:
             bench.main_ours(args)
         except BaseException as exc:                    # noqa: BLE001
