@@ -100,7 +100,7 @@ int kry_prof_read(kry_ctx *ctx, int64_t *samples, double *total_ms);
 #define KRY_OPT_MINRES_FUSE 7 /* 1 (default): MINRES runs 2 launches per iteration -- the w / x update of a trip
                                 (minres.py:294-297, no reduction in it) rides in the second launch of the next
                                 trip; 0: 3 launches.  Candidate; latched at kry_solver_setup.               */
-#define KRY_OPT_MINRES_PERSISTENT 8 /* 1 (default): unsharded, unpreconditioned MINRES runs as ONE cooperative
+#define KRY_OPT_MINRES_PERSISTENT 8 /* 1 (default 0: measured no faster than the 2-launch plan): unsharded, unpreconditioned MINRES runs as ONE cooperative
                                 persistent kernel per kry_solver_iterate call: one CTA wave, the three phases of
                                 a trip separated by two grid-wide barriers that carry the reductions -- no launch
                                 between trips.  Candidate; latched at kry_solver_setup.                        */

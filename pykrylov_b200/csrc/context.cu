@@ -70,7 +70,8 @@ extern "C" int kry_ctx_create(int device, kry_ctx **out)
     c->use_graphs = 1;
     c->cg_one_cta = 1;
     c->minres_fuse = 1;
-    c->minres_persistent = 1;
+    c->minres_persistent = 0;  // measured on B200, config 3: 51.5 us/iteration against 50.9 for the 2-launch plan and 54.4
+                               // for 3 launches (profiles/r2f_minres_ab.json): kept as an option, not the default
     c->cg_fuse = 2;        // measured on B200, 10^7-row 5-pt Laplacian: 0.222 ms/iteration against 0.233
                            // (form 1) and 0.249 (form 0) -- profiles/r1b_ab_cgfuse*.json, r1_final_bench_n1.json
     c->cg_fuse_shards = 1; // row shards use the same plan: 2 x B200, 10^8 rows: 825.7 vs 803.8 it/s with the same

@@ -8,7 +8,7 @@ for f in gpurun_out/multi_gpu_worker_n*.log; do echo "== $f"; grep -v "^$" $f | 
 run_bench () {
   tag=$1; shift
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 500)) \
-      bench.py --gpus $N --steps 100 --warmup 10 "$@" > gpurun_out/r2h_bench_n${N}_$tag.json 2> gpurun_out/r2h_bench_n${N}_$tag.err
+      bench.py --gpus $N --steps ${STEPS:-100} --warmup 10 "$@" > gpurun_out/r2h_bench_n${N}_$tag.json 2> gpurun_out/r2h_bench_n${N}_$tag.err
   python - <<PY
 import json
 try:

@@ -70,3 +70,24 @@ def emu_ctx():
         gc.collect()
         device.result_pool.trim()
         L.lib, device._default = real_lib, real_default
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Largest per-step errors the GPU parity tests saw (tests/test_gpu_parity.py::within), kept next
+    to the other run artefacts: the per-solver bars of DESIGN.md section 3 are read off this file."""
+    try:
+        import test_gpu_parity as GP
+    except Exception:
+        return
+    if not GP.MARGINS:
+        return
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if not os.path.isdir(out_dir):
+        return
+    try:
+        from pykrylov_b200.device import device_count
+        tag = "gpu" if device_count() > 0 else "emulated"
+    except Exception:
+        tag = "emulated"
+    with open(os.path.join(out_dir, "parity_margins_%s.json" % tag), "w") as fh:
+        json.dump(GP.MARGINS, fh, indent=1, sort_keys=True)

@@ -307,7 +307,7 @@ extern "C" int kry_ctx_create(int device, kry_ctx **out)
     c->minres_fuse = 1;
 #endif
 #ifdef KRY_OPT_MINRES_PERSISTENT
-    c->minres_persistent = 1;
+    c->minres_persistent = 0;
 #endif
     KRY_TRY(kry_alloc((void **)&c->scalars, KRY_NUM_SLOTS * sizeof(double)));
     KRY_TRY(kry_alloc((void **)&c->sums, 2 * KRY_MAX_DOTS * sizeof(double)));
@@ -377,7 +377,7 @@ extern "C" int kry_ctx_set_option(kry_ctx *c, int option, int value)
         case KRY_OPT_MINRES_FUSE: c->minres_fuse = value ? 1 : 0; return KRY_OK;
 #endif
 #ifdef KRY_OPT_MINRES_PERSISTENT
-        case KRY_OPT_MINRES_PERSISTENT: c->minres_persistent = value ? 1 : 0; return KRY_OK;
+        case KRY_OPT_MINRES_PERSISTENT: c->minres_persistent = (value && emu_fibers_on) ? 1 : 0; return KRY_OK;   // SIMT mode only
 #endif
 #ifdef KRY_OPT_CG_ONE_CTA
         case KRY_OPT_CG_ONE_CTA: c->cg_one_cta = (value && emu_fibers_on) ? 1 : 0; return KRY_OK;   // SIMT mode only

@@ -20,6 +20,17 @@ from oracle.csr_ref import CsrRef, load_mtx
 pytestmark = pytest.mark.gpu
 
 RTOL_STEP = 1.0e-12      # per-iteration floating point bar
+MARGINS = {}             # label -> largest per-step relative error seen in this session (conftest dumps it)
+
+
+def within(err, tol, label):
+    """Assert err <= tol and remember the largest error seen per label: the session writes them to
+    gpurun_out/parity_margins.json, which is where the bars quoted in DESIGN.md section 3 come from."""
+    err = float(err)
+    cur = MARGINS.get(label)
+    if cur is None or err > cur["max_err"]:
+        MARGINS[label] = {"max_err": err, "bar": float(tol)}
+    assert err <= tol, (label, err, tol)
 RTOL_FINAL = 1.0e-8      # final residual bar
 
 
@@ -254,13 +265,13 @@ def test_cg_single_step_from_identical_state(ctx, name, precon, cg_form):
         kr.cg_step(M, st)
         S.iterate(1)
         assert np.array_equal(S.get_vector("Ap"), st.Ap)           # SpMV: bit-exact
-        assert srel(S.get_scalar("pAp"), st.pAp) <= RTOL_STEP
-        assert srel(S.get_scalar("alpha"), st.alpha) <= RTOL_STEP
-        assert srel(S.get_scalar("beta"), st.beta) <= RTOL_STEP
-        assert srel(S.get_scalar("ry"), st.ry) <= RTOL_STEP
-        assert srel(S.status().resid_norm, st.residNorm) <= RTOL_STEP
+        within(srel(S.get_scalar("pAp"), st.pAp), RTOL_STEP, "cg:scalar pAp")
+        within(srel(S.get_scalar("alpha"), st.alpha), RTOL_STEP, "cg:scalar alpha")
+        within(srel(S.get_scalar("beta"), st.beta), RTOL_STEP, "cg:scalar beta")
+        within(srel(S.get_scalar("ry"), st.ry), RTOL_STEP, "cg:scalar ry")
+        within(srel(S.status().resid_norm, st.residNorm), RTOL_STEP, "cg:scalar residNorm")
         for v in ("x", "r", "p"):
-            assert rel(S.get_vector(v), st[v]) <= RTOL_STEP, (k, v)
+            within(rel(S.get_vector(v), st[v]), RTOL_STEP, "cg:vector " + v)
 
 
 def nonsym_case():
@@ -280,8 +291,8 @@ def test_bicgstab_single_step_from_identical_state(ctx, precon):
     S = dev().DeviceSolver(ctx, "bicgstab", A)
     S.set_precon_diag(None if precon == 0 else d, precon)
     S.setup(rhs, guess=guess, matvec_max=10 ** 6)
-    assert srel(S.status().resid_norm0, st.residNorm0) <= RTOL_STEP
-    assert rel(S.get_vector("r0"), st.r0) <= RTOL_STEP
+    within(srel(S.status().resid_norm0, st.residNorm0), RTOL_STEP, "bicgstab:scalar residNorm")
+    within(rel(S.get_vector("r0"), st.r0), RTOL_STEP, "bicgstab:vector r0")
     for k in range(10):
         for _ in range(2 if k else 0):
             kr.bicgstab_step(M, st)
@@ -307,12 +318,14 @@ def test_bicgstab_single_step_from_identical_state(ctx, precon):
         s_vec = st.s if precon else st.s / st.omega                # (z *= omega aliases s, :135)
         amp = max(1.0, r_scale / np.max(np.abs(s_vec)))
         tol = (RTOL_STEP + 4 * alpha_err) * amp
-        assert alpha_err <= RTOL_STEP
-        assert rel(S.get_vector("t"), st.t) <= tol
-        assert srel(S.get_scalar("omega"), st.omega) <= tol
-        assert srel(S.get_scalar("rho"), st.rho_next) <= 10 * tol  # -omega*(r0.t): one more cancellation
-        assert srel(S.status().resid_norm, st.residNorm) <= tol
-        assert rel(S.get_vector("x"), st.x) <= RTOL_STEP           # x is not formed by cancellation
+        within(alpha_err, RTOL_STEP, "bicgstab:scalar alpha")
+        MARGINS["bicgstab:cancellation factor |r|/|s|"] = {"max_err": max(amp, MARGINS.get(
+            "bicgstab:cancellation factor |r|/|s|", {"max_err": 0.0})["max_err"]), "bar": float("inf")}
+        within(rel(S.get_vector("t"), st.t), tol, "bicgstab:vector t (bar scaled by |r|/|s|)")
+        within(srel(S.get_scalar("omega"), st.omega), tol, "bicgstab:scalar omega (bar scaled by |r|/|s|)")
+        within(srel(S.get_scalar("rho"), st.rho_next), 10 * tol, "bicgstab:scalar rho (-omega r0.t: one more cancellation)")
+        within(srel(S.status().resid_norm, st.residNorm), tol, "bicgstab:scalar residNorm (bar scaled by |r|/|s|)")
+        within(rel(S.get_vector("x"), st.x), RTOL_STEP, "bicgstab:vector x")  # x is not formed by cancellation
         assert rel(S.get_vector("r"), st.r) / max(1.0, np.max(np.abs(s_vec)) / np.max(np.abs(st.r))) <= tol, k
 
 
@@ -337,15 +350,16 @@ def test_cgs_single_step_from_identical_state(ctx, precon):
         S.set_scalar("rho", float(st.rho))
         kr.cgs_step(M, st)
         S.iterate(1)
-        assert srel(S.get_scalar("alpha"), st.alpha) <= RTOL_STEP
+        within(srel(S.get_scalar("alpha"), st.alpha), RTOL_STEP, "cgs:scalar alpha")
         if st.finished:                      # beta / u / p are not formed on the last trip
-            assert rel(S.get_vector("x"), st.x) <= 1e-11 and S.status().done
+            within(rel(S.get_vector("x"), st.x), RTOL_STEP, "early exit:vector x")
+            assert S.status().done
             break
-        assert srel(S.get_scalar("beta"), st.beta) <= 1e-11
-        assert srel(S.get_scalar("rho"), st.rho) <= 1e-11
-        assert srel(S.status().resid_norm, st.residNorm) <= RTOL_STEP
+        within(srel(S.get_scalar("beta"), st.beta), RTOL_STEP, "cgs:scalar beta")
+        within(srel(S.get_scalar("rho"), st.rho), RTOL_STEP, "cgs:scalar rho")
+        within(srel(S.status().resid_norm, st.residNorm), RTOL_STEP, "cgs:scalar residNorm")
         for v in ("x", "r", "u", "p"):
-            assert rel(S.get_vector(v), st[v]) <= 1e-11, (k, v)
+            within(rel(S.get_vector(v), st[v]), RTOL_STEP, "cgs:vector " + v)
 
 
 @pytest.mark.parametrize("precon", [0, 2])
@@ -373,14 +387,15 @@ def test_tfqmr_single_step_from_identical_state(ctx, precon):
         kr.tfqmr_step(M, st)
         S.iterate(1)
         if st.finished:
-            assert rel(S.get_vector("x"), st.x) <= 1e-11 and S.status().done
+            within(rel(S.get_vector("x"), st.x), RTOL_STEP, "early exit:vector x")
+            assert S.status().done
             break
-        assert srel(S.get_scalar("theta"), st.theta) <= RTOL_STEP
-        assert srel(S.get_scalar("eta"), st.eta) <= RTOL_STEP
-        assert srel(S.get_scalar("rho"), st.rho) <= 1e-11
-        assert srel(S.status().resid_norm, st.residNorm) <= RTOL_STEP
+        within(srel(S.get_scalar("theta"), st.theta), RTOL_STEP, "tfqmr:scalar theta")
+        within(srel(S.get_scalar("eta"), st.eta), RTOL_STEP, "tfqmr:scalar eta")
+        within(srel(S.get_scalar("rho"), st.rho), RTOL_STEP, "tfqmr:scalar rho")
+        within(srel(S.status().resid_norm, st.residNorm), RTOL_STEP, "tfqmr:scalar residNorm")
         for v in ("x", "y", "w", "d", "u", "v"):
-            assert rel(S.get_vector(v), st[v]) <= 1e-11, (k, v)
+            within(rel(S.get_vector(v), st[v]), RTOL_STEP, "tfqmr:vector " + v)
 
 
 def minres_case():
@@ -390,13 +405,19 @@ def minres_case():
     return Sm, Sm.matvec(np.ones(Sm.shape[0]))
 
 
-@pytest.fixture(params=[0, 1], ids=["minres3launch", "minres2launch"])
+@pytest.fixture(params=[0, 1, 2], ids=["minres3launch", "minres2launch", "minrespersistent"])
 def minres_plan(ctx, request):
-    """MINRES tests run under both launch plans (KRY_OPT_MINRES_FUSE)."""
-    default = ctx.get_option(L().KRY_OPT_MINRES_FUSE)
-    ctx.set_option(L().KRY_OPT_MINRES_FUSE, request.param)
+    """MINRES tests run under every launch plan: 3 launches, 2 launches (KRY_OPT_MINRES_FUSE) and the
+    cooperative persistent kernel (KRY_OPT_MINRES_PERSISTENT; CUDA or the emulation's SIMT mode only)."""
+    saved = (ctx.get_option(L().KRY_OPT_MINRES_FUSE), ctx.get_option(L().KRY_OPT_MINRES_PERSISTENT))
+    ctx.set_option(L().KRY_OPT_MINRES_FUSE, 1 if request.param == 1 else 0)
+    ctx.set_option(L().KRY_OPT_MINRES_PERSISTENT, 1 if request.param == 2 else 0)
+    if request.param == 2 and not ctx.get_option(L().KRY_OPT_MINRES_PERSISTENT):
+        ctx.set_option(L().KRY_OPT_MINRES_FUSE, saved[0])
+        pytest.skip("the persistent kernel needs CUDA (or the SIMT mode of the emulation)")
     yield request.param
-    ctx.set_option(L().KRY_OPT_MINRES_FUSE, default)
+    ctx.set_option(L().KRY_OPT_MINRES_FUSE, saved[0])
+    ctx.set_option(L().KRY_OPT_MINRES_PERSISTENT, saved[1])
 
 
 @pytest.mark.parametrize("shift", [0.0, 0.5])
@@ -406,7 +427,7 @@ def test_minres_single_step_from_identical_state(ctx, shift, minres_plan):
     st = kr.minres_start(M, rhs, shift=shift)
     S = dev().DeviceSolver(ctx, "minres", A)
     S.setup(rhs, matvec_max=10 ** 6, shift=shift, rtol=1e-12, etol=1e-6, window=5)
-    assert srel(S.status().resid_norm0, st.beta1) <= RTOL_STEP
+    within(srel(S.status().resid_norm0, st.beta1), RTOL_STEP, "minres:scalar residNorm")
     names = dict(mbeta="beta", oldb="oldb", dbar="dbar", epsln="epsln", phibar="phibar", cs="cs", sn="sn",
                  tnorm2="tnorm2", ynorm2="ynorm2", rhs1="rhs1", rhs2="rhs2", gmax="gmax", gmin="gmin",
                  beta1="beta1", xnrg2="xNrgNorm2")
@@ -425,14 +446,15 @@ def test_minres_single_step_from_identical_state(ctx, shift, minres_plan):
         S.iterate(1)
         ds = S.status()
         assert ds.n_iter == st.itn and ds.istop == st.istop
-        assert srel(S.get_scalar("alfa"), st.alfa) <= RTOL_STEP
-        assert srel(S.get_scalar("mbeta"), st.beta) <= RTOL_STEP
+        within(srel(S.get_scalar("alfa"), st.alfa), RTOL_STEP, "minres:scalar alfa")
+        within(srel(S.get_scalar("mbeta"), st.beta), RTOL_STEP, "minres:scalar mbeta")
         for dname in ("phibar", "cs", "sn", "tnorm2", "ynorm2", "rhs1", "gmax", "gmin", "dbar", "epsln"):
-            assert srel(S.get_scalar(dname), float(st[names.get(dname, dname)])) <= 1e-11, dname
-        assert srel(ds.resid_norm, st.rnorm) <= RTOL_STEP
-        assert srel(ds.aux[0], st.Anorm) <= RTOL_STEP and srel(ds.aux[3], st.Arnorm) <= 1e-11
+            within(srel(S.get_scalar(dname), float(st[names.get(dname, dname)])), RTOL_STEP, "minres:scalar " + dname)
+        within(srel(ds.resid_norm, st.rnorm), RTOL_STEP, "minres:scalar rnorm")
+        within(srel(ds.aux[0], st.Anorm), RTOL_STEP, "minres:scalar Anorm")
+        within(srel(ds.aux[3], st.Arnorm), RTOL_STEP, "minres:scalar Arnorm")
         for v in ("x", "r2", "r1", "w"):
-            assert rel(S.get_vector(v), st[v]) <= 1e-11, (k, v)
+            within(rel(S.get_vector(v), st[v]), RTOL_STEP, "minres:vector " + v)
 
 
 # ================================================= trajectories and known answers
@@ -449,7 +471,7 @@ def test_cg_trajectory_poisson2d(ctx, golden, cg_form):
     hist = S.drain_history(st)[:, 0]
     rec = golden["cg/poisson2d_csr/100"]
     assert st.n_matvec == ref.nMatvec == rec["nMatvec"] == 160
-    assert rel(hist[:20], ref.residHistory[:20]) <= RTOL_STEP
+    within(rel(hist[:20], ref.residHistory[:20]), RTOL_STEP, "cg_trajectory_poisson2d:hist_20_ref_residHistory_20_")
     assert np.max(np.abs(hist - np.array(ref.residHistory)) / np.array(ref.residHistory)) <= 1e-10
     assert srel(st.resid_norm0, rec["residNorm0"]) <= 1e-14
     # final residual: true residuals of both solutions agree to 1e-8 (relative to |b|)
@@ -486,7 +508,7 @@ def test_public_api_known_answers(ctx, golden):
             rec = golden["cg/poisson2d_csr/%d" % g]
             assert srel(cg.residNorm0, rec["residNorm0"]) <= 1e-14
             assert len(cg.residHistory) == nmv + 1
-            assert rel(cg.residHistory[:25], rec["residHistory"]) <= 1e-11
+            within(rel(cg.residHistory[:25], rec["residHistory"]), RTOL_STEP, "public_api_known_answers:cg_residHistory_25_rec_residHistory_")
         assert np.linalg.norm(e - cg.bestSolution) / g <= 1e-5
 
 
@@ -738,7 +760,7 @@ def test_fullsize_kernels_agree_bitwise_and_operator_is_symmetric(ctx, big):
     A.set_kernel(0, 0, 0)
     A.spmv_dot(w, y2, [x], slot0=2)
     x_Aw = ctx.scalars(2, 1)[0]
-    assert srel(w_Ax, x_Aw) <= 1e-11                               # symmetry, reduction-order noise only
+    within(srel(w_Ax, x_Aw), RTOL_STEP, "fullsize_kernels_agree_bitwise_and_operator_is_symmetric:w_Ax_x_Aw")  # symmetry, reduction-order noise only
     # linearity: A(2x - 3w) == 2Ax - 3Aw up to rounding of the combination
     dev().multi_axpy_dot(ctx, [dict(z=z, u=x, w=w, a=2.0, b=-3.0)])
     y3 = dev().DeviceVector(ctx, n)
