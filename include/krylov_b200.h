@@ -195,8 +195,10 @@ int kry_csr_create_convdiff3d(kry_ctx *ctx, int64_t m, double gamma,
 #define KRY_SPMV_ROWB8   4   /* one thread per row, loads batched 8 entries at a time */
 #define KRY_SPMV_ROWB4   5   /* one thread per row, loads batched 4 entries at a time */
 #define KRY_SPMV_ROWPF   6   /* one thread per row, row pointers loaded one trip ahead (candidate)  */
-#define KRY_SPMV_ROWPF2  7   /* ... two trips ahead, and the next trip's col/val window prefetched
-                                into L2 (candidate)                                                */
+#define KRY_SPMV_ROWPF2  7   /* one thread per row; the TMA unit stages the row pointers of the next tiles in
+                                shared memory (cp.async.bulk + mbarrier, two trips ahead) and bulk-prefetches
+                                the next tile's col/val windows into L2 -- no register cost (spmv_rowtma_kernel) */
+#define KRY_SPMV_ROWTMA  KRY_SPMV_ROWPF2
 int kry_csr_set_kernel(kry_csr *A, int kind, int tile_nnz, int threads);
 
 /* ------------------------------------------------------- hot-path kernels */

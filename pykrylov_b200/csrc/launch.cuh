@@ -58,8 +58,13 @@ int spmv_launch(kry_csr *M, bool trans, Gather g, Epi epi, Fin fin, const int *d
     int kind = M->kind;
     if (kind == KRY_SPMV_AUTO) kind = (m->max_row <= 64) ? KRY_SPMV_ROW : KRY_SPMV_STREAM;
 #ifdef KRY_EMULATE
-    if (kind == KRY_SPMV_STREAM || kind == KRY_SPMV_TMA) kind = KRY_SPMV_ROW;   // host emulation: row loops only
+    if (kind == KRY_SPMV_STREAM || kind == KRY_SPMV_TMA || kind == KRY_SPMV_ROWPF2) kind = KRY_SPMV_ROW;   // host emulation: row loops only
 #endif
+    // The TMA-staged row kernel is an experiment for the stand-alone products (kry_spmv / kry_spmv_dot):
+    // bit-exact there, but no faster than the plain row kernel (0.1317 vs 0.1292 ms on config 2) and, inside
+    // the graph-replayed CG loop with exactly one resident wave, it showed multi-millisecond stalls that are
+    // not understood (profiles/r2k_tune.log).  The solver loops therefore never use it.
+    if (kind == KRY_SPMV_ROWPF2 && done != c->never_done && done != c->gate) kind = KRY_SPMV_ROW;
     const int tile = M->tile_nnz ? M->tile_nnz : KRY_DEFAULT_TILE;
     const int threads = M->threads ? M->threads : KRY_DEFAULT_THREADS;
     const size_t budget = (size_t)c->smem_optin - 2048;   // static smem of the reduction + barriers
@@ -94,7 +99,11 @@ int spmv_launch(kry_csr *M, bool trans, Gather g, Epi epi, Fin fin, const int *d
                 else if (kind == KRY_SPMV_ROWPF)
                     qe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, spmv_rowpf_kernel<ND, 1, Gather, Epi, Fin>, 256, 0);
                 else
-                    qe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, spmv_rowpf_kernel<ND, 2, Gather, Epi, Fin>, 256, 0);
+#ifdef KRY_EMULATE
+                    qe = cudaErrorUnknown;
+#else
+                    qe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, spmv_rowtma_kernel<ND, Gather, Epi, Fin>, 256, 0);
+#endif
                 if (qe != cudaSuccess || b < 1) b = 8;
                 occ = b;
             }
@@ -130,8 +139,6 @@ int spmv_launch(kry_csr *M, bool trans, Gather g, Epi epi, Fin fin, const int *d
         emu_launch<ND>(grid, 256, ws, fin, [&] { spmv_row_kernel<ND, Gather, Epi, Fin>(A, g, epi, ws, fin, done); });
     else if (kind == KRY_SPMV_ROWPF)
         emu_launch<ND>(grid, 256, ws, fin, [&] { spmv_rowpf_kernel<ND, 1, Gather, Epi, Fin>(A, g, epi, ws, fin, done); });
-    else if (kind == KRY_SPMV_ROWPF2)
-        emu_launch<ND>(grid, 256, ws, fin, [&] { spmv_rowpf_kernel<ND, 2, Gather, Epi, Fin>(A, g, epi, ws, fin, done); });
     else if (kind == KRY_SPMV_ROWB8)
         emu_launch<ND>(grid, 256, ws, fin, [&] { spmv_rowb_kernel<ND, 8, Gather, Epi, Fin>(A, g, epi, ws, fin, done); });
     else
@@ -141,8 +148,8 @@ int spmv_launch(kry_csr *M, bool trans, Gather g, Epi epi, Fin fin, const int *d
         spmv_row_kernel<ND, Gather, Epi, Fin><<<grid, 256, 0, c->stream>>>(A, g, epi, ws, fin, done);
     } else if (kind == KRY_SPMV_ROWPF) {
         spmv_rowpf_kernel<ND, 1, Gather, Epi, Fin><<<grid, 256, 0, c->stream>>>(A, g, epi, ws, fin, done);
-    } else if (kind == KRY_SPMV_ROWPF2) {
-        spmv_rowpf_kernel<ND, 2, Gather, Epi, Fin><<<grid, 256, 0, c->stream>>>(A, g, epi, ws, fin, done);
+    } else if (kind == KRY_SPMV_ROWPF2) {        // TMA-staged row pointers + bulk L2 prefetch of the next tile's CSR window
+        spmv_rowtma_kernel<ND, Gather, Epi, Fin><<<grid, 256, 0, c->stream>>>(A, g, epi, ws, fin, done);
     } else if (kind == KRY_SPMV_ROWB8) {
         spmv_rowb_kernel<ND, 8, Gather, Epi, Fin><<<grid, 256, 0, c->stream>>>(A, g, epi, ws, fin, done);
     } else if (kind == KRY_SPMV_ROWB4) {

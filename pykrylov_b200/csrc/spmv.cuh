@@ -497,6 +497,31 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
         : "memory");
 }
 
+// non-blocking probe (mbarrier.try_wait may suspend the thread up to a system time limit)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t *bar, unsigned phase)
+{
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// bulk prefetch of a global window into L2 by the TMA unit (no destination, no register cost)
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src_gmem, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
+
 }  // namespace tma
 
 // smem per stage: cap doubles (val, overwritten by products) + cap ints (col),
@@ -577,6 +602,96 @@ spmv_tma_kernel(CsrView A, int cap, Gather g, Epi epi, ReduceWs ws, Fin fin, con
         if (tid == 0) {
             const int nxt = tile + kStages * step;
             if (nxt < A.nblocks) issue(nxt, s);
+        }
+    }
+    if constexpr (ND > 0) block_reduce_finalize<ND>(acc, ws, fin);
+}
+// ------------------------------------------- thread per row, TMA-staged row pointers
+// The row kernel's per-row chain is rowptr -> (col, val) -> gathers, three dependent memory
+// latencies (ncu: 0.26 eligible warps per scheduler, long-scoreboard stalls on exactly these
+// instructions).  Here the TMA unit runs ahead of the threads, at no register cost:
+//   * the row pointers of a CTA's next tiles (256 rows + 1) arrive in shared memory through
+//     cp.async.bulk + mbarrier, two trips ahead (ring of kStages tiles): a thread reads its
+//     [s, e) from shared memory and its col/val loads start at once;
+//   * as soon as the row pointers of the next tile have landed, one thread asks the TMA unit to
+//     pull that tile's col / val windows (contiguous: the rows of a tile are consecutive) into
+//     L2 (cp.async.bulk.prefetch.L2), so the second link of the chain is an L2 hit.
+// Row -> thread mapping and order inside a row are those of spmv_row_kernel: same bits.
+template <int ND, class Gather, class Epi, class Fin>
+__global__ void __launch_bounds__(256, epi_min_blocks<Epi>::value)
+spmv_rowtma_kernel(CsrView A, Gather g, Epi epi, ReduceWs ws, Fin fin, const int *done)
+{
+    constexpr int kStages = 4, kLag = 2, kTile = 256, kCap = 264;
+    if (*done) return;
+    __shared__ __align__(16) int s_rp[kStages][kCap];
+    __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages];
+    g.init();
+    epi.init();
+    const int tid = threadIdx.x;
+    const int ntiles = (A.nrows + kTile - 1) / kTile;
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            tma::mbar_init(&s_full[s], 1);
+            tma::mbar_init(&s_empty[s], 8);              // one arrival per warp
+        }
+        tma::fence_barrier_init();
+    }
+    __syncthreads();
+    auto rows_of = [&](int tile) {
+        const int left = A.nrows - tile * kTile;
+        return left < kTile ? left : kTile;
+    };
+    auto issue = [&](int tile, int s) {                  // thread 0 only
+        const unsigned bytes = (unsigned)(((rows_of(tile) + 1 + 3) & ~3) * 4);    // rowptr is padded by 8 entries
+        tma::mbar_expect_tx(&s_full[s], bytes);
+        tma::bulk_g2s(s_rp[s], A.rowptr + (size_t)tile * kTile, bytes, &s_full[s]);
+    };
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            const int t = blockIdx.x + s * gridDim.x;
+            if (t < ntiles) issue(t, s);
+        }
+    }
+    double acc[ND > 0 ? ND : 1];
+#pragma unroll
+    for (int d = 0; d < (ND > 0 ? ND : 1); ++d) acc[d] = 0.0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int s = it % kStages;
+        tma::mbar_wait(&s_full[s], (unsigned)(it / kStages) & 1u);
+        const int row = tile * kTile + tid;
+        int rs = 0, re = 0;
+        if (row < A.nrows) {
+            rs = s_rp[s][tid];
+            re = s_rp[s][tid + 1];
+        }
+        __syncwarp();
+        if ((tid & 31) == 0) tma::mbar_arrive(&s_empty[s]);          // this warp has read its row pointers
+        if (tid == 0 && it >= kLag) {
+            // refill the stage every warp left kLag trips ago with the tile kStages - kLag trips ahead
+            const int ip = it - kLag, nxt = tile + (kStages - kLag) * gridDim.x;
+            if (nxt < ntiles) {
+                tma::mbar_wait(&s_empty[ip % kStages], (unsigned)(ip / kStages) & 1u);
+                issue(nxt, ip % kStages);
+            }
+        }
+        if (tid == 32) {
+            // next tile: once its row pointers are in shared memory, pull its col / val windows into L2
+            const int nt = tile + gridDim.x;
+            if (nt < ntiles && tma::mbar_test_wait(&s_full[(it + 1) % kStages], (unsigned)((it + 1) / kStages) & 1u)) {
+                const int *rp = s_rp[(it + 1) % kStages];
+                const int k0 = rp[0] & ~3, k1 = (rp[rows_of(nt)] + 3) & ~3;          // 16-byte aligned for both arrays
+                if (k1 > k0) {
+                    tma::bulk_prefetch_l2(A.val + k0, (unsigned)(k1 - k0) * 8u);
+                    tma::bulk_prefetch_l2(A.col + k0, (unsigned)(k1 - k0) * 4u);
+                }
+            }
+        }
+        if (row < A.nrows) {
+            double sum = 0.0;
+            for (int k = rs; k < re; ++k)
+                sum = __dadd_rn(sum, __dmul_rn(__ldg(A.val + k), g(__ldg(A.col + k))));
+            epi(row, sum, acc);
         }
     }
     if constexpr (ND > 0) block_reduce_finalize<ND>(acc, ws, fin);
