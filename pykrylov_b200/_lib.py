@@ -10,6 +10,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libkrylov_b200.so")
+if os.environ.get("KRY_B200_LIB"):        # A/B measurement builds of the same library (scripts/gpu_*.sh)
+    LIB_PATH = os.path.join(_HERE, os.path.basename(os.environ["KRY_B200_LIB"]))
 
 
 class KrylovDeviceError(RuntimeError):

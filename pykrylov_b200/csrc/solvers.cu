@@ -202,13 +202,22 @@ struct CgGatherDir {
     __device__ double operator()(int c) const
     {
         if constexpr (SHARD) {
-            if (c >= n_local) return __ldcg(p_old + c);     // halo entry: may have been written by a peer
-        }                                                   // GPU during this launch -- read at the L2
-        const double po = __ldg(p_old + c);
-        if constexpr (PEND) {
-            return __dsub_rn(__dmul_rn(beta, po), __ldg(r + c));                   // cg.py:150-151
+            // one weak load for local and halo columns alike: halo entries are written by peer GPUs
+            // during the launch and read after the flag wait + fence (spmv.cuh, Gather::coherent)
+            const double pq = p_old[c];
+            if constexpr (PEND) {
+                if (c >= n_local) return pq;            // arrives already updated
+                return __dsub_rn(__dmul_rn(beta, pq), __ldg(r + c));               // cg.py:150-151
+            } else {
+                return pq;
+            }
         } else {
-            return po;
+            const double po = __ldg(p_old + c);
+            if constexpr (PEND) {
+                return __dsub_rn(__dmul_rn(beta, po), __ldg(r + c));               // cg.py:150-151
+            } else {
+                return po;
+            }
         }
     }
     // what this rank publishes for its boundary entry j (spmv_row_shard_kernel): the updated
@@ -218,7 +227,7 @@ struct CgGatherDir {
         if constexpr (PEND) return __dsub_rn(__dmul_rn(beta, p_old[j]), r[j]);
         else return p_old[j];
     }
-    __device__ double halo(int c) const { return __ldcg(p_old + c); }
+    __device__ double coherent(int c) const { return (*this)(c); }
 };
 
 template <bool PEND, bool XLAG>
@@ -1347,7 +1356,7 @@ struct MinGather {            // x[c] * (1/beta): v = s*y with s = 1.0/beta, min
     __device__ void   init() { inv = 1.0 / s->s[M_BETA]; }
     __device__ double operator()(int c) const { return __dmul_rn(inv, __ldg(y + c)); }
     __device__ double boundary(int j) const { return y[j]; }
-    __device__ double halo(int c) const { return __dmul_rn(inv, __ldcg(y + c)); }
+    __device__ double coherent(int c) const { return __dmul_rn(inv, y[c]); }
 };
 
 struct MinEpiY {

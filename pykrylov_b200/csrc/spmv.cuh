@@ -50,16 +50,21 @@ static inline CsrView csr_view(const CsrDev &m)
 // Besides operator()(col) every gather functor states, for the sharded launch with the halo
 // exchange fused in (spmv_row_shard_kernel):
 //   boundary(j)  what this rank publishes for its local entry j -- the raw vector entry, such
-//                that the reader's halo(c) of the column it lands in gives operator()'s value;
-//   halo(c)      operator() for a halo column (c >= n_local): the entry was written by a peer
-//                GPU while this kernel may already be running, so it is read at the L2
-//                (ld.global.cg), never through the non-coherent L1 path of __ldg.
+//                that the reader's gather of the column it lands in gives operator()'s value;
+//   coherent(c)  operator() with the gathered vector read by ordinary (weak) loads instead of the
+//                read-only path of __ldg.  Halo entries are written by peer GPUs while the kernel
+//                runs; a thread reads them only after it has seen the peers' flags and executed a
+//                system-scope fence (halo_wait), which is the acquire pattern of the PTX memory
+//                model for weak loads -- ld.global.nc gives no such guarantee.  One unconditional
+//                load for local and halo columns alike: a predicated pair of loads (read-only path
+//                for local, ld.cg for halo columns) measured 2.6 % slower on the fused CG launch
+//                (profiles/r2m_*).
 struct GatherPlain {
     const double *x;
     __device__ void   init() {}
     __device__ double operator()(int c) const { return __ldg(x + c); }
     __device__ double boundary(int j) const { return x[j]; }
-    __device__ double halo(int c) const { return __ldcg(x + c); }
+    __device__ double coherent(int c) const { return x[c]; }
 };
 
 // x[c] * s with s read from device memory (MINRES: v = (1/beta) * y on the fly)
@@ -70,16 +75,16 @@ struct GatherScaled {
     __device__ void   init() { s = *s_ptr; }
     __device__ double operator()(int c) const { return __dmul_rn(s, __ldg(x + c)); }
     __device__ double boundary(int j) const { return x[j]; }
-    __device__ double halo(int c) const { return __dmul_rn(s, __ldcg(x + c)); }
+    __device__ double coherent(int c) const { return __dmul_rn(s, x[c]); }
 };
 
-// Halo-aware view of a gather for row shards: columns below n_local are this rank's own entries.
+// Halo-aware view of a gather for row shards (columns >= n_local address the halo tail).
 template <class G>
 struct HaloGather {
     G   g;
     int n_local;
     __device__ void   init() { g.init(); }
-    __device__ double operator()(int c) const { return c < n_local ? g(c) : g.halo(c); }
+    __device__ double operator()(int c) const { return g.coherent(c); }
     __device__ double boundary(int j) const { return g.boundary(j); }
 };
 
@@ -212,7 +217,7 @@ spmv_rowpf_kernel(CsrView A, Gather g, Epi epi, ReduceWs ws, Fin fin, const int 
 //      behind the wave, out of the L2 window the others share, and never catches up -- the launch
 //      then takes 12 % longer; profiles/r2e_*).
 //   3. A thread that reaches v >= v_wait first waits until every rank it reads from has
-//      published this tag; halo columns are then read at the L2 (Gather::halo).
+//      published this tag and fences; the gather reads with weak loads (Gather::coherent).
 // Every sharded row launch uses this kernel and this row order -- also when the entries travelled
 // by pack kernel + ncclAllGather (skip bits set) -- so the fused inner products are the same
 // bits whichever way the halo travelled.
