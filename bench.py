@@ -481,6 +481,13 @@ def main_ours(args):
            "api": "pykrylov_b200.cg.CG(op, abstol=0, reltol=0).solve(rhs_host_pinned, matvec_max=K)",
            "wall_ms": 1e3 * e2e_dt}
 
+    if world > 1:
+        # the same launch on every rank (with the in-kernel all-reduce they wait for each other inside it;
+        # with --nccl-allreduce these are the ranks' own kernel times: the skew the all-reduce absorbs)
+        per_rank = [float(np.frombuffer(b, dtype=np.float64)[0])
+                    for b in ctx.allgather_bytes(np.array([k1_ms], dtype=np.float64).tobytes())]
+        roofline["avg_launch_ms_per_rank"] = per_rank
+
     extra = {}
     if world > 1 and not args.no_single:
         # same 10^8-row operator on ONE GPU (rank 0), for the speed-up claim
