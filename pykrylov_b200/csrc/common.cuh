@@ -154,12 +154,14 @@ struct HaloTable {
 struct HaloArgs {                // by value into the sharded SpMV launch
     const HaloTable   *tbl;
     const int         *send_idx;
-    int                n_send, push_ctas;
+    int                n_send, push_ctas;   // the LAST push_ctas CTAs of the grid only publish, they own no rows
+    int                row_ctas;            // CTAs that walk rows: gridDim.x - push_ctas
     unsigned          *ticket;   // self-resetting retirement ticket of the push CTAs
     unsigned long long tag;      // monotonic per context, identical on every rank
     int                rot, v_wait;
     int                skip_push;   // bit 0: no push (the entries travelled by ncclAllGather, or tests/emu played
                                     // the push in the launcher); bit 1: no wait
+    int                emu_phase;   // tests/emu SIMT mode only: 1 = publishing CTAs act, 2 = row CTAs act (0: all)
     unsigned long long *trace;      // optional (KRY_HALO_TRACE): in-kernel %globaltimer statistics, see kry_halo_trace_read
 };
 

@@ -8,6 +8,7 @@
 constexpr int KRY_DEFAULT_TILE    = 4096;
 constexpr int KRY_DEFAULT_THREADS = 256;
 constexpr int KRY_TMA_STAGES      = 3;
+constexpr int KRY_HALO_DEDICATED_CTAS = 0;   // default of KRY_HALO_PUSH_CTAS (measured, profiles/r2p_*)
 
 int csr_build_partition(kry_ctx *c, CsrDev &m, int tile_nnz);
 int kry_halo_exchange(kry_csr *M, double *x_dev);    // comm.cu; no-op unless sharded
@@ -208,8 +209,26 @@ int spmv_shard_launch(kry_csr *M, Gather g, Epi epi, Fin fin, const int *done, c
             b = 8;
         occ = b < 8 ? b : 8;
     }
-    const int64_t capg = (int64_t)c->sm_count * occ;       // one resident wave: the push CTAs and the
-    const int grid = (int)(need < capg ? need : capg);     // waiting CTAs must be co-resident
+    // a few CTAs of the wave only publish the boundary entries (same grid whichever way the halo travels,
+    // so the fused inner products are the same bits); one resident wave: publishing and waiting CTAs
+    // must be co-resident
+    // KRY_HALO_PUSH_CTAS (A/B switch, read once): N > 0 = N dedicated publishing CTAs that own no rows;
+    // 0 = the last ceil(n_send/256) row CTAs publish before they walk their rows
+    static int dedicated = -1;
+    if (dedicated < 0) {
+        const char *e = getenv("KRY_HALO_PUSH_CTAS");
+        dedicated = e ? atoi(e) : KRY_HALO_DEDICATED_CTAS;
+    }
+    int push = (hp.n_send + 255) / 256;
+    int64_t capg = (int64_t)c->sm_count * occ;
+    if (dedicated > 0) {
+        if (push > dedicated) push = dedicated;
+        capg -= push;
+    }
+    if (capg < 1) capg = 1;
+    const int row_ctas = (int)(need < capg ? need : capg);
+    const int grid = dedicated > 0 ? row_ctas + push : row_ctas;
+    if (push > grid) push = grid;
     KRY_TRY(kry_ctx_ensure_partials(c, grid));
     ReduceWs ws = kry_ws(c);
     ws.defer = (defer == 1);
@@ -219,13 +238,14 @@ int spmv_shard_launch(kry_csr *M, Gather g, Epi epi, Fin fin, const int *done, c
     h.tbl = tbl;
     h.send_idx = hp.send_idx;
     h.n_send = hp.n_send;
-    h.push_ctas = (hp.n_send + 255) / 256;
-    if (h.push_ctas > grid) h.push_ctas = grid;
+    h.push_ctas = push;
+    h.row_ctas = row_ctas;
     h.ticket = c->counter + 24;                             // inside the zeroed 256-byte counter block
     h.tag = tbl ? ++c->halo_seq : 0ull;
     h.rot = hp.rot;
     h.v_wait = hp.v_wait;
     h.skip_push = tbl ? 0 : 3;
+    h.emu_phase = 0;
     h.trace = tbl ? c->halo_trace : nullptr;
     KRY_REQUIRE(!tbl || defer == 2, KRY_ERR_STATE, "fused halo exchange without the in-kernel all-reduce");
     const bool prof = c->prof_ev && c->prof_n < c->prof_cap;
@@ -235,7 +255,11 @@ int spmv_shard_launch(kry_csr *M, Gather g, Epi epi, Fin fin, const int *done, c
         // SIMT mode: all blocks alive at once (a block that waits for a peer's flag must not keep
         // this rank's later push blocks from running)
         auto body = [&] { spmv_row_shard_kernel<ND, Gather, Epi, Fin>(A, g, epi, ws, fin, done, h); };
-        emu_launch_fibers_mode(grid, 256, &body, [](const void *k) { (*static_cast<const decltype(body) *>(k))(); }, 1);
+        auto call = [](const void *k) { (*static_cast<const decltype(body) *>(k))(); };
+        h.emu_phase = 1;                                   // the publishing blocks first (they wait for nobody) ...
+        emu_launch_fibers_mode(grid, 256, &body, call, 0);
+        h.emu_phase = 2;                                   // ... then the row blocks
+        emu_launch_fibers_mode(grid, 256, &body, call, 1);
     } else {
         // fast mode plays the threads one after the other: the push (all of it, then the flags) is
         // played first by the launcher with the kernel's own device function

@@ -205,10 +205,12 @@ spmv_rowpf_kernel(CsrView A, Gather g, Epi epi, ReduceWs ws, Fin fin, const int 
 // ------------------------------------- thread per row, halo exchange fused in
 // Row shards with KRY_OPT_HALO_P2P: ONE launch does the exchange of the boundary entries and
 // the SpMV (+ epilogue + fused inner products + in-kernel all-reduce).
-//   1. The first `push_ctas` CTAs store this rank's boundary entries g.boundary(send_idx[i])
-//      straight into the halo tails of the ranks that read them, over NVLink peer memory
-//      (CUDA IPC mapping of the readers' solver slabs); the CTA that finishes the push last
-//      publishes the launch's tag in every reader's flag word (system-scope fence in between).
+//   1. A few dedicated CTAs at the end of the grid (they own no rows: a CTA that pushed first and
+//      walked rows afterwards started ~10 us late and ended the launch ~10 us late, measured)
+//      store this rank's boundary entries g.boundary(send_idx[i]) straight into the halo tails of
+//      the ranks that read them, over NVLink peer memory (CUDA IPC mapping of the readers' solver
+//      slabs); the one that finishes last publishes the launch's tag in every reader's flag word
+//      (release fence in between).  They take part in the reduction with zero partial sums.
 //   2. All CTAs walk the rows in the rotated order v -> (v + rot) mod nrows, which puts the rows
 //      that may touch halo columns last (HaloPlan::rot / v_wait, found at kry_csr_shard_finalize;
 //      for a banded operator they are two thin slabs at the ends of the shard): the interior is
@@ -246,8 +248,8 @@ __device__ __forceinline__ void halo_push_entries(const HaloArgs &h, const Gathe
 {
     const HaloTable *T = h.tbl;
     const int n_to = T->n_to;
-    // the LAST push_ctas CTAs publish (the first ones own the leading boundary rows and wait first)
-    for (int i = (gridDim.x - 1 - blockIdx.x) * blockDim.x + threadIdx.x; i < h.n_send; i += h.push_ctas * blockDim.x) {
+    const int first = (int)gridDim.x - h.push_ctas;       // the last push_ctas CTAs of the grid publish
+    for (int i = ((int)blockIdx.x - first) * blockDim.x + threadIdx.x; i < h.n_send; i += h.push_ctas * blockDim.x) {
         const double v = g.boundary(__ldg(h.send_idx + i));
         for (int q = 0; q < n_to; ++q) T->to_tail[q][i] = v;
     }
@@ -290,7 +292,6 @@ __device__ __forceinline__ void halo_publish(const HaloArgs &h)
 template <class Gather>
 __device__ __forceinline__ void halo_push(const HaloArgs &h, const Gather &g, const unsigned long long &t_entry)
 {
-    if ((int)(gridDim.x - 1 - blockIdx.x) >= h.push_ctas) return;
     halo_push_entries(h, g);
     __syncthreads();                  // the CTA's stores happen-before thread 0's fence (cumulative)
     if (threadIdx.x == 0) {
@@ -315,7 +316,7 @@ static inline void emu_halo_push_all(const HaloArgs &h, const Gather &g)
 {
     for (int b = 0; b < h.push_ctas; ++b)
         for (int t = 0; t < 256; ++t) {
-            blockIdx = EmuDim{gridDim.x - 1 - (unsigned)b, 0, 0};
+            blockIdx = EmuDim{(unsigned)((int)gridDim.x - h.push_ctas + b), 0, 0};
             threadIdx = EmuDim{(unsigned)t, 0, 0};
             halo_push_entries(h, g);
         }
@@ -354,11 +355,24 @@ spmv_row_shard_kernel(CsrView A, Gather g, Epi epi, ReduceWs ws, Fin fin, const 
         if (threadIdx.x == 0) t_entry = global_ns();
         __syncthreads();
     }
-    if (!(h.skip_push & 1)) halo_push(h, g, t_entry);
     double acc[ND > 0 ? ND : 1];
 #pragma unroll
     for (int d = 0; d < (ND > 0 ? ND : 1); ++d) acc[d] = 0.0;
-    const int stride = gridDim.x * blockDim.x;
+#ifdef KRY_EMULATE
+    // tests/emu, SIMT mode: __shared__ is one copy per host thread there, so a publishing block must not
+    // run its reduction while warps of a row block sit in theirs; the launcher plays the two kinds of
+    // blocks one after the other (launch.cuh)
+    if (h.emu_phase == 1 && (int)blockIdx.x < h.row_ctas) return;
+    if (h.emu_phase == 2 && (int)blockIdx.x >= h.row_ctas) return;
+#endif
+    if ((int)blockIdx.x >= (int)gridDim.x - h.push_ctas) {
+        if (!(h.skip_push & 1)) halo_push(h, g, t_entry);
+        if ((int)blockIdx.x >= h.row_ctas) {              // dedicated publishing CTA: no rows
+            if constexpr (ND > 0) block_reduce_finalize<ND>(acc, ws, fin);
+            return;
+        }
+    }
+    const int stride = h.row_ctas * blockDim.x;
     auto one_row = [&](int v) {
         int row = v + h.rot;
         if (row >= A.nrows) row -= A.nrows;

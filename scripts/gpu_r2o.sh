@@ -24,5 +24,4 @@ except Exception as e:
 PY
 }
 run_bench halo1
-run_bench all_nccl --halo-p2p 0 --nccl-allreduce --no-single
-python bench.py --impl reference --gpus $N --steps 5 --warmup 1 > gpurun_out/r2o_reference_arm_n$N.json 2> gpurun_out/r2o_reference_arm_n$N.err; cut -c1-400 gpurun_out/r2o_reference_arm_n$N.json
+run_bench halo0 --halo-p2p 0 --no-single
