@@ -559,7 +559,9 @@ def main_ours(args):
 # ---------------------------------------------------------- reference arm
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+    # the workload is the one our arm runs at this N: under torchrun WORLD_SIZE says so, launched as a
+    # plain process --gpus does
+    world = int(os.environ.get("WORLD_SIZE", str(max(1, args.gpus))))
     if rank != 0:
         return
     g = args.grid or (G_CONFIG2 if world == 1 else G_CONFIG5)

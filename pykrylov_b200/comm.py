@@ -38,6 +38,8 @@ def row_partition(n, nranks):
 
 def _rendezvous_path(tag=None):
     if tag is None:
+        tag = os.environ.get("KRY_RENDEZVOUS_TAG")     # explicit (e.g. ranks started under different parents)
+    if tag is None:
         # all workers of one torchrun share the agent as parent and the master port
         tag = "%s_%s_%d" % (os.environ.get("MASTER_PORT", "0"),
                             os.environ.get("TORCHELASTIC_RUN_ID", "none"), os.getppid())
