@@ -47,6 +47,7 @@ typedef struct kry_csr    kry_csr;     /* device-resident CSR operator          
 typedef struct kry_vec    kry_vec;     /* device-resident fp64 vector                */
 typedef struct kry_solver kry_solver;  /* device-resident Krylov iteration state     */
 typedef struct kry_lls kry_lls;        /* device-resident scalar plane of the lls solvers / SYMMLQ */
+typedef struct kry_graph kry_graph;    /* a captured sequence of stand-alone launches             */
 
 /* ------------------------------------------------------------------ misc */
 int         kry_abi_version(void);
@@ -376,6 +377,15 @@ int kry_lls_step(kry_lls *L, int phase);                   /* enqueue one scalar
 int kry_lls_status(kry_lls *L, kry_lls_status_t *out, double *scalars, int n_scalars);
 int kry_lls_history(kry_lls *L, int64_t first, int64_t count, double *host);   /* 4 doubles per entry */
 int kry_lls_release_gate(kry_lls *L);                      /* stand-alone launches run unconditionally again */
+
+/* A static sequence of stand-alone launches on the context's stream (one trip of an lls / SYMMLQ loop:
+ * kry_spmv, kry_multi_axpy_dot, kry_lls_step ...) captured as a CUDA graph and replayed with one call
+ * per trip.  Everything issued between kry_graph_begin and kry_graph_end is recorded, not executed;
+ * the sequence must have run un-captured once before.                                              */
+int kry_graph_begin(kry_ctx *ctx, kry_graph **out);
+int kry_graph_end(kry_graph *g);
+int kry_graph_launch(kry_graph *g, int times);
+int kry_graph_destroy(kry_graph *g);
 
 #ifdef __cplusplus
 }

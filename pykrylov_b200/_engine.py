@@ -226,6 +226,7 @@ class PlaneLoop(object):
             P = ScalarPlane(ctx, method)
             cache[method] = P
         self.ctx, self.P = ctx, P
+        self.use_graphs = True
 
     def ops(self, ops, dots=()):
         multi_axpy_dot(self.ctx, ops, dots, slot0=0)
@@ -233,18 +234,34 @@ class PlaneLoop(object):
     def run(self, trip, check_interval, on_chunk=None):
         """Returns (status, scalars) after the device latched `done`.  The gate is released on
         every exit path: later stand-alone launches of this context run unconditionally again."""
+        from .device import LaunchGraph
         P = self.P
+        interval = max(1, int(check_interval))
+        graph, chunks = None, 0
         try:
             st, sc = P.status()
             while not st.done:
-                for _ in range(max(1, int(check_interval))):
-                    trip()
+                if graph is not None:
+                    graph.launch(interval)                 # one call per trip instead of ~10
+                else:
+                    for _ in range(interval):
+                        trip()
                 st, sc = P.status()
                 if on_chunk is not None:
                     on_chunk(st, sc, P.drain_history(st))
+                chunks += 1
+                if (graph is None and chunks == 1 and not st.done and self.use_graphs and self.ctx.nranks == 1
+                        and self.ctx.get_option(2)):
+                    # the launch sequence of a trip is static and has now run un-captured: record it once
+                    # (KRY_OPT_GRAPHS; not available on the host emulation)
+                    graph = LaunchGraph.capture(self.ctx, trip)
+                    if graph is None:
+                        self.use_graphs = False
             return st, sc
         finally:
             P.release_gate()
+            if graph is not None:
+                graph._release()
 
 
 def require_plan(method, op, precon, n):

@@ -149,6 +149,10 @@ PROTOTYPES = {
     "kry_lls_status": (C.c_int, [handle, C.POINTER(LlsStatus), c_f64p, C.c_int]),
     "kry_lls_history": (C.c_int, [handle, C.c_int64, C.c_int64, C.c_void_p]),
     "kry_lls_release_gate": (C.c_int, [handle]),
+    "kry_graph_begin": (C.c_int, [handle, C.POINTER(handle)]),
+    "kry_graph_end": (C.c_int, [handle]),
+    "kry_graph_launch": (C.c_int, [handle, C.c_int]),
+    "kry_graph_destroy": (C.c_int, [handle]),
     "kry_solver_create": (C.c_int, [handle, C.c_int, handle, C.POINTER(handle)]),
     "kry_solver_destroy": (C.c_int, [handle]),
     "kry_solver_set_precon_diag": (C.c_int, [handle, C.c_void_p, C.c_int]),

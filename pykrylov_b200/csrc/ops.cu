@@ -3,6 +3,8 @@
 // (the device-resident solver loops in solvers.cu use the same kernels with
 //  solver-specific epilogues; these generic forms back LinearOperator.__mul__
 //  and user-composed iterations).
+#include <new>
+
 #include "launch.cuh"
 
 // y = A x, plus up to 3 fused  w_k . y  (w_k == nullptr means y . y)
@@ -238,4 +240,94 @@ extern "C" int kry_multi_axpy_dot(kry_ctx *c, int n_ops, const kry_axpby *ops, i
         case 2: return multi_axpy_nd<2>(c, n, n_ops, ops, dots, slot0);
         default: return multi_axpy_nd<3>(c, n, n_ops, ops, dots, slot0);
     }
+}
+
+// ------------------------------------------------------------ launch-sequence graphs
+// A static sequence of stand-alone launches on a context's stream (kry_spmv, kry_spmv_dot,
+// kry_multi_axpy_dot, kry_lls_step: one trip of an lls / SYMMLQ loop) captured once and replayed
+// with one call per trip.  The sequence must have run un-captured before (first-use allocations
+// and attribute calls do not belong into a capture); coefficients and stopping flags live in
+// device memory, so a replay does exactly what the enqueued sequence would do.
+struct kry_graph {
+    kry_ctx        *ctx;
+    cudaGraphExec_t exec;
+    int64_t         launches;     // kernel launches inside one replay
+    int64_t         l0;           // launch counter when the capture began
+};
+
+extern "C" int kry_graph_begin(kry_ctx *c, kry_graph **out)
+{
+    KRY_REQUIRE(c && out, KRY_ERR_INVALID, "kry_graph_begin: NULL argument");
+    *out = nullptr;
+    KRY_REQUIRE(!c->closed, KRY_ERR_STATE, "kry_graph_begin: the context was destroyed");
+#ifdef KRY_EMULATE
+    kry_set_error("kry_graph_begin: no CUDA graphs on the host emulation");
+    return KRY_ERR_UNSUPPORTED;
+#else
+    KRY_REQUIRE(c->prof_cap == 0, KRY_ERR_STATE, "kry_graph_begin: per-launch profiling is on");
+    KRY_CUDA(cudaSetDevice(c->device));
+    kry_graph *g = new (std::nothrow) kry_graph();
+    KRY_REQUIRE(g, KRY_ERR_NOMEM, "kry_graph_begin: host allocation failed");
+    g->ctx = c;
+    g->exec = nullptr;
+    g->launches = 0;
+    g->l0 = c->launches;
+    cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) {
+        delete g;
+        KRY_CUDA(e);
+    }
+    kry_ctx_retain(c);
+    *out = g;
+    return KRY_OK;
+#endif
+}
+
+extern "C" int kry_graph_end(kry_graph *g)
+{
+    KRY_REQUIRE(g && !g->exec, KRY_ERR_INVALID, "kry_graph_end: not a graph under capture");
+#ifdef KRY_EMULATE
+    return KRY_ERR_UNSUPPORTED;
+#else
+    kry_ctx *c = g->ctx;
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+    g->launches = c->launches - g->l0;
+    c->launches = g->l0;                     // nothing has executed
+    if (e != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        kry_set_error("kry_graph_end: capture failed: %s", cudaGetErrorString(e));
+        return KRY_ERR_CUDA;
+    }
+    e = cudaGraphInstantiate(&g->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    KRY_CUDA(e);
+    return KRY_OK;
+#endif
+}
+
+extern "C" int kry_graph_launch(kry_graph *g, int times)
+{
+    KRY_REQUIRE(g && g->exec && times >= 0, KRY_ERR_INVALID, "kry_graph_launch: bad argument");
+    KRY_CTX_LIVE(g->ctx, "kry_graph_launch");
+#ifndef KRY_EMULATE
+    for (int k = 0; k < times; ++k) {
+        KRY_CUDA(cudaGraphLaunch(g->exec, g->ctx->stream));
+        g->ctx->launches += g->launches;
+    }
+#endif
+    return KRY_OK;
+}
+
+extern "C" int kry_graph_destroy(kry_graph *g)
+{
+    if (!g) return KRY_OK;
+#ifndef KRY_EMULATE
+    if (!g->ctx->closed) cudaStreamSynchronize(g->ctx->stream);
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+#endif
+    kry_ctx_release(g->ctx);
+    delete g;
+    return KRY_OK;
 }

@@ -141,7 +141,7 @@ class Context(object):
     def close(self):
         """Destroy the context after every object that still lives on it."""
         if getattr(self, "_h", None) is not None and self._h.value:
-            order = {"DeviceSolver": 0, "ScalarPlane": 0, "DeviceCsr": 1, "DeviceVector": 2}
+            order = {"LaunchGraph": -1, "DeviceSolver": 0, "ScalarPlane": 0, "DeviceCsr": 1, "DeviceVector": 2}
             for obj in sorted(list(self._children), key=lambda o: order.get(type(o).__name__, 3)):
                 obj._release()
             L.lib.kry_ctx_destroy(self._h)
@@ -496,6 +496,51 @@ def multi_axpy_dot(ctx, ops, dots=(), slot0=0):
         darr[k].u = u._h
         darr[k].w = w._h
     call("kry_multi_axpy_dot", ctx._h, len(ops), arr, len(dots), darr, int(slot0))
+
+
+class LaunchGraph(object):
+    """A captured sequence of stand-alone launches (``kry_graph``): ``LaunchGraph.capture(ctx, fn)``
+    records what ``fn()`` enqueues, ``launch(n)`` replays it n times.  Returns None where graphs are
+    not available (host emulation)."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self._h = ctx, handle
+        ctx._adopt(self)
+
+    @classmethod
+    def capture(cls, ctx, fn):
+        h = L.handle()
+        rc = L.lib.kry_graph_begin(ctx._h, C.byref(h))
+        if rc in (L.KRY_ERR_UNSUPPORTED, L.KRY_ERR_STATE):      # emulation / per-launch profiling is on
+            return None
+        if rc != L.KRY_OK:
+            raise L.KrylovDeviceError(rc, L.last_error())
+        g = cls(ctx, h)
+        try:
+            fn()
+        finally:
+            rc = L.lib.kry_graph_end(h)
+        if rc != L.KRY_OK:
+            g._release()
+            raise L.KrylovDeviceError(rc, L.last_error())
+        return g
+
+    replays = 0          # process-wide count of replayed sequences (read by the tests)
+
+    def launch(self, times=1):
+        call("kry_graph_launch", self._h, int(times))
+        LaunchGraph.replays += int(times)
+
+    def _release(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            L.lib.kry_graph_destroy(self._h)
+            self._h = L.handle()
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
 
 
 class ScalarPlane(object):

@@ -715,7 +715,7 @@ extern "C" int kry_csr_create_poisson1d(kry_ctx *c, int64_t n, int64_t rb, int64
 
 extern "C" int kry_csr_create_poisson2d(kry_ctx *c, int64_t g, int64_t rb, int64_t re, uint32_t flags, kry_csr **out)
 {
-    return stencil_rows(c, g * g, rb, re, flags, [g](int64_t r, std::vector<int> &col, std::vector<double> &val) {
+    return stencil_rows(c, g * g, rb, re, flags | KRY_CSR_SYMMETRIC, [g](int64_t r, std::vector<int> &col, std::vector<double> &val) {
         const int64_t i = r / g, j = r % g;
         if (i > 0) { col.push_back((int)(r - g)); val.push_back(-1.0); }
         if (j > 0) { col.push_back((int)(r - 1)); val.push_back(-1.0); }
