@@ -239,6 +239,14 @@ typedef struct kry_dotspec { const kry_vec *u, *w; } kry_dotspec;
 int kry_multi_axpy_dot(kry_ctx *ctx, int n_ops, const kry_axpby *ops,
                        int n_dots, const kry_dotspec *dots, int slot0);
 
+/* SpMV with its y-side update fused in:  z = a*(A x) + b*w  (op->u must be NULL: the product takes
+ * its place; coefficient rules of kry_axpby), and for n_dots == 1 the inner product
+ * dot_with . z (dot_with == NULL: z . z) into scalar slot slot0.  z may alias w, not x.  Replaces
+ * kry_spmv into a temporary followed by kry_multi_axpy_dot (lls/lsqr.py:279-281,297-299: u = A v - alpha u,
+ * v = A'u - beta v): no bit of z changes, 16 bytes per row less traffic, one launch less.          */
+int kry_spmv_axpby_dot(kry_csr *A, int trans, const kry_vec *x, const kry_axpby *op, int n_dots,
+                       const kry_vec *dot_with, int slot0);
+
 /* The only per-check-interval device->host traffic: read scalar slots. */
 #define KRY_NUM_SLOTS 64
 int kry_scalars_read(kry_ctx *ctx, int first, int count, double *host);
@@ -376,6 +384,12 @@ int kry_lls_setup(kry_lls *L, const kry_lls_params *params, const double *scalar
 int kry_lls_step(kry_lls *L, int phase);                   /* enqueue one scalar step (no sync) */
 int kry_lls_status(kry_lls *L, kry_lls_status_t *out, double *scalars, int n_scalars);
 int kry_lls_history(kry_lls *L, int64_t first, int64_t count, double *host);   /* 4 doubles per entry */
+/* Fused forms: the launch's inner products go to slots 0.. and phase `phase` of the recurrence runs in
+ * the launch's finalize (what kry_multi_axpy_dot / kry_spmv_axpby_dot followed by kry_lls_step do).   */
+int kry_lls_multi_axpy_dot(kry_lls *L, int phase, int n_ops, const kry_axpby *ops, int n_dots,
+                           const kry_dotspec *dots);
+int kry_lls_spmv_axpby_dot(kry_lls *L, int phase, kry_csr *A, int trans, const kry_vec *x,
+                           const kry_axpby *op, const kry_vec *dot_with);
 int kry_lls_release_gate(kry_lls *L);                      /* stand-alone launches run unconditionally again */
 
 /* A static sequence of stand-alone launches on the context's stream (one trip of an lls / SYMMLQ loop:

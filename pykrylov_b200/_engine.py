@@ -7,9 +7,11 @@ see; those go through the host-callback bridge (vectors stay in HBM, each
 operator application crosses PCIe) -- never through a NumPy re-implementation of
 the loop.
 """
+import os
+
 import numpy as np
 
-from .device import DeviceSolver, DeviceVector, default_context, multi_axpy_dot
+from .device import DeviceSolver, DeviceVector, default_context, multi_axpy_dot, spmv_axpby_dot
 
 
 class DevicePlan(object):
@@ -227,9 +229,33 @@ class PlaneLoop(object):
             cache[method] = P
         self.ctx, self.P = ctx, P
         self.use_graphs = True
+        self.fuse = os.environ.get("KRY_LLS_FUSE", "1") != "0"
+        self._tmp = {}
 
-    def ops(self, ops, dots=()):
-        multi_axpy_dot(self.ctx, ops, dots, slot0=0)
+    def ops(self, ops, dots=(), step=None):
+        """One fused vector pass; `step`: the phase of the recurrence that consumes its inner products,
+        run in the launch's finalize instead of a kry_lls_step launch of its own."""
+        if step is None or not dots or not self.fuse:
+            multi_axpy_dot(self.ctx, ops, dots, slot0=0)
+            if step is not None:
+                self.P.step(step)
+        else:
+            multi_axpy_dot(self.ctx, ops, dots, plane=self.P, phase=step)
+
+    def spmv_ops(self, csr, x, op, step, dot_with=None, trans=False):
+        """z = a*(A x) + b*w, the inner product dot_with . z (None: z . z) and phase `step`: one launch.
+        KRY_LLS_FUSE=0 (A/B measurements, tests) enqueues the three launches this replaces: the product
+        into a temporary, the vector pass with its inner product, the step kernel."""
+        if self.fuse:
+            spmv_axpby_dot(csr, x, op, dot_with=dot_with, trans=trans, plane=self.P, phase=step)
+            return
+        z = op["z"]
+        t = self._tmp.get(z.n)
+        if t is None:
+            t = self._tmp[z.n] = DeviceVector(self.ctx, z.n)
+        csr.spmv(x, t, trans=trans)
+        multi_axpy_dot(self.ctx, [dict(op, u=t)], [(dot_with if dot_with is not None else z, z)], slot0=0)
+        self.P.step(step)
 
     def run(self, trip, check_interval, on_chunk=None):
         """Returns (status, scalars) after the device latched `done`.  The gate is released on

@@ -139,6 +139,7 @@ PROTOTYPES = {
     "kry_spmv_dot": (C.c_int, [handle, C.c_int, handle, handle, C.c_int, C.POINTER(handle), C.c_int]),
     "kry_multi_axpy_dot": (C.c_int, [handle, C.c_int, C.POINTER(Axpby), C.c_int, C.POINTER(DotSpec),
                                      C.c_int]),
+    "kry_spmv_axpby_dot": (C.c_int, [handle, C.c_int, handle, C.POINTER(Axpby), C.c_int, handle, C.c_int]),
     "kry_scalars_read": (C.c_int, [handle, C.c_int, C.c_int, c_f64p]),
     "kry_scalars_write": (C.c_int, [handle, C.c_int, C.c_int, c_f64p]),
     "kry_lls_create": (C.c_int, [handle, C.c_int, C.POINTER(handle)]),
@@ -148,6 +149,8 @@ PROTOTYPES = {
     "kry_lls_step": (C.c_int, [handle, C.c_int]),
     "kry_lls_status": (C.c_int, [handle, C.POINTER(LlsStatus), c_f64p, C.c_int]),
     "kry_lls_history": (C.c_int, [handle, C.c_int64, C.c_int64, C.c_void_p]),
+    "kry_lls_multi_axpy_dot": (C.c_int, [handle, C.c_int, C.c_int, C.POINTER(Axpby), C.c_int, C.POINTER(DotSpec)]),
+    "kry_lls_spmv_axpby_dot": (C.c_int, [handle, C.c_int, handle, C.c_int, handle, C.POINTER(Axpby), handle]),
     "kry_lls_release_gate": (C.c_int, [handle]),
     "kry_graph_begin": (C.c_int, [handle, C.POINTER(handle)]),
     "kry_graph_end": (C.c_int, [handle]),

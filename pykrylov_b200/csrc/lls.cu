@@ -19,7 +19,7 @@
 
 #include <new>
 
-#include "launch.cuh"
+#include "vecops.cuh"
 
 constexpr int LLS_HIST_CAP = 1 << 15;
 constexpr int LLS_HIST_W = 4;
@@ -538,9 +538,13 @@ __device__ static void symmlq_step(LlsDev *st, double *sl, double *hist, int pha
     v[Y_rhs2] = -epsln * z;
 }
 
-__global__ void lls_step_kernel(LlsDev *st, double *slots, double *hist, int phase)
+// One phase of the scalar recurrence (one thread).  Not inlined: it is also the cold tail of the
+// fused vector / SpMV launches (LlsFin), whose hot loops must not pay for its registers.
+#if defined(__CUDACC__)
+__device__ __noinline__
+#endif
+static void lls_step_phase(LlsDev *st, double *slots, double *hist, int phase)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
     if (st->done) return;
     if (phase == 9) {                // CRAIG / CRAIG-MR: latch `done` behind the trip's vector updates
         if (st->window < 0) {
@@ -557,6 +561,25 @@ __global__ void lls_step_kernel(LlsDev *st, double *slots, double *hist, int pha
         case KRY_LLS_SYMMLQ: symmlq_step(st, slots, hist, phase); break;
     }
 }
+
+__global__ void lls_step_kernel(LlsDev *st, double *slots, double *hist, int phase)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    lls_step_phase(st, slots, hist, phase);
+}
+
+// Finalize of a fused launch: publish the inner products into slots 0.., then run the phase of the
+// recurrence that consumes them -- what a separate lls_step_kernel launch would do next.
+struct LlsFin {
+    LlsDev *st;
+    double *slots, *hist;
+    int     n, phase;
+    __device__ void operator()(const double *t) const
+    {
+        for (int d = 0; d < n; ++d) slots[d] = t[d];
+        lls_step_phase(st, slots, hist, phase);
+    }
+};
 #endif  // __CUDACC__ || KRY_EMULATE
 
 // ---------------------------------------------------------------- C ABI
@@ -656,6 +679,40 @@ extern "C" int kry_lls_step(kry_lls *L, int phase)
     c->launches++;
     KRY_CUDA(cudaGetLastError());
     return KRY_OK;
+}
+
+// The two fused forms of a trip's launches: the vector pass / the SpMV with its y-side update, the
+// inner products, and phase `phase` of the recurrence in the launch's finalize.
+extern "C" int kry_lls_multi_axpy_dot(kry_lls *L, int phase, int n_ops, const kry_axpby *ops, int n_dots,
+                                      const kry_dotspec *dots)
+{
+    KRY_REQUIRE(L, KRY_ERR_INVALID, "kry_lls_multi_axpy_dot: NULL argument");
+    KRY_CTX_LIVE(L->ctx, "kry_lls_multi_axpy_dot");
+    kry_ctx *c = L->ctx;
+    int64_t n = -1;
+    KRY_TRY(multi_axpy_check("kry_lls_multi_axpy_dot", c, n_ops, ops, n_dots, dots, 0, &n));
+    KRY_REQUIRE(n_dots >= 1 && n > 0, KRY_ERR_INVALID,
+                "kry_lls_multi_axpy_dot: the phase rides on a reduction (n_dots=%d, n=%lld)", n_dots, (long long)n);
+    KRY_CUDA(cudaSetDevice(c->device));
+    LlsFin fin{L->dev, c->scalars, L->hist, n_dots, phase};
+    switch (n_dots) {
+        case 1: return multi_axpy_run<1>(c, n, n_ops, ops, dots, fin);
+        case 2: return multi_axpy_run<2>(c, n, n_ops, ops, dots, fin);
+        default: return multi_axpy_run<3>(c, n, n_ops, ops, dots, fin);
+    }
+}
+
+extern "C" int kry_lls_spmv_axpby_dot(kry_lls *L, int phase, kry_csr *A, int trans, const kry_vec *x,
+                                      const kry_axpby *op, const kry_vec *dot_with)
+{
+    KRY_REQUIRE(L, KRY_ERR_INVALID, "kry_lls_spmv_axpby_dot: NULL argument");
+    KRY_TRY(spmv_axpby_check("kry_lls_spmv_axpby_dot", A, trans, x, op, 1, dot_with, 0));
+    KRY_REQUIRE(A->ctx == L->ctx, KRY_ERR_INVALID, "kry_lls_spmv_axpby_dot: operator and plane on different contexts");
+    kry_ctx *c = L->ctx;
+    KRY_CUDA(cudaSetDevice(c->device));
+    KRY_TRY(kry_halo_exchange(A, x->d));
+    LlsFin fin{L->dev, c->scalars, L->hist, 1, phase};
+    return spmv_axpby_run<1, 6>(A, trans, x, op, dot_with, fin);
 }
 
 extern "C" int kry_lls_status(kry_lls *L, kry_lls_status_t *out, double *scalars, int n_scalars)

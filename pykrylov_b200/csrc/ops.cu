@@ -5,7 +5,7 @@
 //  and user-composed iterations).
 #include <new>
 
-#include "launch.cuh"
+#include "vecops.cuh"
 
 // y = A x, plus up to 3 fused  w_k . y  (w_k == nullptr means y . y)
 template <int ND>
@@ -101,115 +101,15 @@ extern "C" int kry_spmv_dot(kry_csr *A, int trans, const kry_vec *x, kry_vec *y,
     }
 }
 
-// ------------------------------------------------------------- multi-AXPY
-struct AxpbyDev {
-    double       *z;
-    const double *u, *w;
-    double        a, b;
-    int           a_slot, b_slot, a_neg, b_neg;
-};
-
-template <int ND>
-struct MultiAxpyBody {
-    AxpbyDev      op[4];
-    int           n_ops;
-    const double *du[ND > 0 ? ND : 1], *dw[ND > 0 ? ND : 1];
-    const double *slots;
-    double        ca[4], cb[4];      // resolved coefficients (registers: all loops are unrolled)
-    __device__ void init()
-    {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            ca[k] = op[k].a;
-            cb[k] = op[k].b;
-            if (k < n_ops) {
-                if (op[k].a_slot >= 0) ca[k] = slots[op[k].a_slot];
-                if (op[k].b_slot >= 0) cb[k] = slots[op[k].b_slot];
-                if (op[k].a_neg & 1) ca[k] = -ca[k];
-                if (op[k].b_neg & 1) cb[k] = -cb[k];
-            }
-        }
-    }
-    // coefficient applied as a multiplier, or as a divisor when bit 1 of the flag is set
-    // (`u /= beta` in the reference is a true division, not a multiply by 1/beta)
-    __device__ static double term(double c, double v, int flag)
-    {
-        return (flag & 2) ? __ddiv_rn(v, c) : __dmul_rn(c, v);
-    }
-    __device__ void update(int i) const
-    {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (k >= n_ops) break;
-            const double *u = op[k].u, *w = op[k].w;
-            double r;
-            if (u && w)
-                r = __dadd_rn(term(ca[k], u[i], op[k].a_neg), term(cb[k], w[i], op[k].b_neg));
-            else if (u)
-                r = term(ca[k], u[i], op[k].a_neg);
-            else if (w)
-                r = term(cb[k], w[i], op[k].b_neg);
-            else
-                r = 0.0;
-            op[k].z[i] = r;
-        }
-    }
-    __device__ void operator()(int i, double *acc) const
-    {
-        update(i);
-#pragma unroll
-        for (int d = 0; d < ND; ++d) acc[d] = __dadd_rn(acc[d], __dmul_rn(du[d][i], dw[d][i]));
-    }
-    __device__ void operator()(int i) const { update(i); }
-};
-
-template <int ND>
-static int multi_axpy_nd(kry_ctx *c, int64_t n, int n_ops, const kry_axpby *ops,
-                         const kry_dotspec *dots, int slot0)
+int multi_axpy_check(const char *who, kry_ctx *c, int n_ops, const kry_axpby *ops, int n_dots,
+                     const kry_dotspec *dots, int slot0, int64_t *n_out)
 {
-    MultiAxpyBody<ND> b;
-    b.n_ops = n_ops;
-    b.slots = c->scalars;
-    for (int k = 0; k < n_ops; ++k) {
-        b.op[k].z = ops[k].z->d;
-        b.op[k].u = ops[k].u ? ops[k].u->d : nullptr;
-        b.op[k].w = ops[k].w ? ops[k].w->d : nullptr;
-        b.op[k].a = ops[k].a;
-        b.op[k].b = ops[k].b;
-        b.op[k].a_slot = ops[k].a_slot;
-        b.op[k].b_slot = ops[k].b_slot;
-        b.op[k].a_neg = ops[k].a_neg;
-        b.op[k].b_neg = ops[k].b_neg;
-    }
-    if constexpr (ND == 0) {
-        b.du[0] = b.dw[0] = nullptr;
-        return vec_map_launch(c, n, b, kry_gate(c));
-    } else {
-        for (int d = 0; d < ND; ++d) {
-            b.du[d] = dots[d].u->d;
-            b.dw[d] = dots[d].w->d;
-        }
-        SlotFin fin{c->scalars + slot0, ND};
-        if (c->nranks > 1) {
-            extern int kry_allreduce_sums(kry_ctx * c, int n);
-            KRY_TRY((vec_pass_launch<ND>(c, n, b, fin, kry_gate(c), 1)));
-            KRY_TRY(kry_allreduce_sums(c, ND));
-            return finalize_launch(c, fin, kry_gate(c));
-        }
-        return vec_pass_launch<ND>(c, n, b, fin, kry_gate(c), 0);
-    }
-}
-
-extern "C" int kry_multi_axpy_dot(kry_ctx *c, int n_ops, const kry_axpby *ops, int n_dots,
-                                  const kry_dotspec *dots, int slot0)
-{
-    KRY_REQUIRE(c, KRY_ERR_INVALID, "kry_multi_axpy_dot: NULL context");
+    KRY_REQUIRE(c, KRY_ERR_INVALID, "%s: NULL context", who);
     KRY_REQUIRE(n_ops >= 0 && n_ops <= 4 && n_dots >= 0 && n_dots <= 3 && n_ops + n_dots > 0,
-                KRY_ERR_INVALID, "kry_multi_axpy_dot: n_ops=%d n_dots=%d", n_ops, n_dots);
-    KRY_REQUIRE((n_ops == 0 || ops) && (n_dots == 0 || dots), KRY_ERR_INVALID,
-                "kry_multi_axpy_dot: NULL op/dot array");
+                KRY_ERR_INVALID, "%s: n_ops=%d n_dots=%d", who, n_ops, n_dots);
+    KRY_REQUIRE((n_ops == 0 || ops) && (n_dots == 0 || dots), KRY_ERR_INVALID, "%s: NULL op/dot array", who);
     KRY_REQUIRE(slot0 >= 0 && slot0 + n_dots <= KRY_NUM_SLOTS, KRY_ERR_INVALID,
-                "kry_multi_axpy_dot: scalar slots [%d,%d) out of range", slot0, slot0 + n_dots);
+                "%s: scalar slots [%d,%d) out of range", who, slot0, slot0 + n_dots);
     int64_t n = -1;
     auto chk = [&](const kry_vec *v) -> bool {
         if (!v) return true;
@@ -218,28 +118,68 @@ extern "C" int kry_multi_axpy_dot(kry_ctx *c, int n_ops, const kry_axpby *ops, i
         return v->n == n;
     };
     for (int k = 0; k < n_ops; ++k) {
-        KRY_REQUIRE(ops[k].z, KRY_ERR_INVALID, "kry_multi_axpy_dot: op %d has no output", k);
+        KRY_REQUIRE(ops[k].z, KRY_ERR_INVALID, "%s: op %d has no output", who, k);
         KRY_REQUIRE(chk(ops[k].z) && chk(ops[k].u) && chk(ops[k].w), KRY_ERR_SHAPE,
-                    "kry_multi_axpy_dot: op %d operand size/context mismatch", k);
+                    "%s: op %d operand size/context mismatch", who, k);
         KRY_REQUIRE(ops[k].a_slot < KRY_NUM_SLOTS && ops[k].b_slot < KRY_NUM_SLOTS, KRY_ERR_INVALID,
-                    "kry_multi_axpy_dot: op %d scalar slot out of range", k);
+                    "%s: op %d scalar slot out of range", who, k);
     }
     for (int d = 0; d < n_dots; ++d) {
-        KRY_REQUIRE(dots[d].u && dots[d].w, KRY_ERR_INVALID, "kry_multi_axpy_dot: dot %d NULL", d);
-        KRY_REQUIRE(chk(dots[d].u) && chk(dots[d].w), KRY_ERR_SHAPE,
-                    "kry_multi_axpy_dot: dot %d operand size/context mismatch", d);
+        KRY_REQUIRE(dots[d].u && dots[d].w, KRY_ERR_INVALID, "%s: dot %d NULL", who, d);
+        KRY_REQUIRE(chk(dots[d].u) && chk(dots[d].w), KRY_ERR_SHAPE, "%s: dot %d operand size/context mismatch", who, d);
     }
+    *n_out = n;
+    return KRY_OK;
+}
+
+extern "C" int kry_multi_axpy_dot(kry_ctx *c, int n_ops, const kry_axpby *ops, int n_dots,
+                                  const kry_dotspec *dots, int slot0)
+{
+    int64_t n = -1;
+    KRY_TRY(multi_axpy_check("kry_multi_axpy_dot", c, n_ops, ops, n_dots, dots, slot0, &n));
     KRY_CUDA(cudaSetDevice(c->device));
     if (n <= 0) {                       // empty vectors: inner products are exactly 0
         if (n_dots > 0) KRY_CUDA(cudaMemsetAsync(c->scalars + slot0, 0, n_dots * sizeof(double), c->stream));
         return KRY_OK;
     }
+    SlotFin fin{c->scalars + slot0, n_dots};
     switch (n_dots) {
-        case 0: return multi_axpy_nd<0>(c, n, n_ops, ops, dots, slot0);
-        case 1: return multi_axpy_nd<1>(c, n, n_ops, ops, dots, slot0);
-        case 2: return multi_axpy_nd<2>(c, n, n_ops, ops, dots, slot0);
-        default: return multi_axpy_nd<3>(c, n, n_ops, ops, dots, slot0);
+        case 0: return multi_axpy_run<0>(c, n, n_ops, ops, dots, fin);
+        case 1: return multi_axpy_run<1>(c, n, n_ops, ops, dots, fin);
+        case 2: return multi_axpy_run<2>(c, n, n_ops, ops, dots, fin);
+        default: return multi_axpy_run<3>(c, n, n_ops, ops, dots, fin);
     }
+}
+
+int spmv_axpby_check(const char *who, kry_csr *A, int trans, const kry_vec *x, const kry_axpby *op,
+                     int n_dots, const kry_vec *dot_with, int slot0)
+{
+    KRY_REQUIRE(op && op->z, KRY_ERR_INVALID, "%s: NULL op / output", who);
+    KRY_TRY(check_spmv_args(who, A, trans, x, op->z));
+    KRY_REQUIRE(!op->u, KRY_ERR_INVALID, "%s: op->u must be NULL (the product A x takes its place)", who);
+    KRY_REQUIRE(n_dots == 0 || n_dots == 1, KRY_ERR_INVALID, "%s: n_dots=%d", who, n_dots);
+    KRY_REQUIRE(slot0 >= 0 && slot0 + n_dots <= KRY_NUM_SLOTS, KRY_ERR_INVALID,
+                "%s: scalar slot %d out of range", who, slot0);
+    KRY_REQUIRE(op->a_slot < KRY_NUM_SLOTS && op->b_slot < KRY_NUM_SLOTS, KRY_ERR_INVALID,
+                "%s: coefficient slot out of range", who);
+    if (op->w)
+        KRY_REQUIRE(op->w->ctx == A->ctx && op->w->n == op->z->n && op->w->d != x->d, KRY_ERR_SHAPE,
+                    "%s: w must live on the operator's context, have the length of z and not alias x", who);
+    if (dot_with)
+        KRY_REQUIRE(n_dots == 1 && dot_with->ctx == A->ctx && dot_with->n == op->z->n, KRY_ERR_SHAPE,
+                    "%s: dot operand size/context mismatch", who);
+    return KRY_OK;
+}
+
+extern "C" int kry_spmv_axpby_dot(kry_csr *A, int trans, const kry_vec *x, const kry_axpby *op, int n_dots,
+                                  const kry_vec *dot_with, int slot0)
+{
+    KRY_TRY(spmv_axpby_check("kry_spmv_axpby_dot", A, trans, x, op, n_dots, dot_with, slot0));
+    KRY_CUDA(cudaSetDevice(A->ctx->device));
+    KRY_TRY(kry_halo_exchange(A, x->d));
+    SlotFin fin{A->ctx->scalars + slot0, n_dots};
+    if (n_dots == 0) return spmv_axpby_run<0>(A, trans, x, op, nullptr, NoFin());
+    return spmv_axpby_run<1>(A, trans, x, op, dot_with, fin);
 }
 
 // ------------------------------------------------------------ launch-sequence graphs

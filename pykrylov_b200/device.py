@@ -478,8 +478,7 @@ class DeviceCsr(object):
         return yv.download()
 
 
-def multi_axpy_dot(ctx, ops, dots=(), slot0=0):
-    """ops: list of dicts(z, u, w, a, b, a_slot, b_slot, a_neg, b_neg); dots: list of (u, w)."""
+def _axpby_array(ops):
     arr = (L.Axpby * max(len(ops), 1))()
     for k, o in enumerate(ops):
         arr[k].z = o["z"]._h
@@ -491,11 +490,37 @@ def multi_axpy_dot(ctx, ops, dots=(), slot0=0):
         arr[k].b_slot = int(o.get("b_slot", -1))
         arr[k].a_neg = int(o.get("a_neg", 0)) | (2 if o.get("a_div") else 0)
         arr[k].b_neg = int(o.get("b_neg", 0)) | (2 if o.get("b_div") else 0)
+    return arr
+
+
+def _dot_array(dots):
     darr = (L.DotSpec * max(len(dots), 1))()
     for k, (u, w) in enumerate(dots):
         darr[k].u = u._h
         darr[k].w = w._h
-    call("kry_multi_axpy_dot", ctx._h, len(ops), arr, len(dots), darr, int(slot0))
+    return darr
+
+
+def multi_axpy_dot(ctx, ops, dots=(), slot0=0, plane=None, phase=0):
+    """ops: list of dicts(z, u, w, a, b, a_slot, b_slot, a_neg, b_neg); dots: list of (u, w).
+    With `plane` (a ScalarPlane) the launch's finalize also runs phase `phase` of that plane's
+    recurrence (kry_lls_multi_axpy_dot); the inner products then go to slots 0.."""
+    if plane is not None:
+        call("kry_lls_multi_axpy_dot", plane._h, int(phase), len(ops), _axpby_array(ops), len(dots), _dot_array(dots))
+    else:
+        call("kry_multi_axpy_dot", ctx._h, len(ops), _axpby_array(ops), len(dots), _dot_array(dots), int(slot0))
+
+
+def spmv_axpby_dot(csr, x, op, dot=False, dot_with=None, slot0=0, trans=False, plane=None, phase=0):
+    """z = a*(A x) + b*w in one launch (`op`: a dict like multi_axpy_dot's without `u`), optionally with
+    the inner product dot_with . z (None: z . z) into slot `slot0`; with `plane` the finalize also runs
+    phase `phase` of the plane's recurrence (kry_spmv_axpby_dot / kry_lls_spmv_axpby_dot)."""
+    arr = _axpby_array([dict(op, u=None)])
+    dw = dot_with._h if dot_with is not None else None
+    if plane is not None:
+        call("kry_lls_spmv_axpby_dot", plane._h, int(phase), csr._h, int(bool(trans)), x._h, arr, dw)
+    else:
+        call("kry_spmv_axpby_dot", csr._h, int(bool(trans)), x._h, arr, int(bool(dot) or dot_with is not None), dw, int(slot0))
 
 
 class LaunchGraph(object):

@@ -113,13 +113,10 @@ class CRAIGMRFramework(KrylovMethod):
                               xNrgNorm2=xNrgNorm2), window=window, itnlim=itnlim, etol=etol)
 
             def trip():
-                csr.spmv(v, tm)
-                loop.ops([dict(z=Mu, u=tm, w=Mu, a=1.0, b_slot=SL.ALPHA, b_neg=1)], [(Mu, Mu)])
-                loop.P.step(1)
+                # Mu = A v - alpha Mu, |Mu|^2 and phase 1 (beta, |A|) in one launch; likewise A'u below
+                loop.spmv_ops(csr, v, dict(z=Mu, w=Mu, a=1.0, b_slot=SL.ALPHA, b_neg=1), step=1)
                 loop.ops([dict(z=u, u=u, a_slot=SL.U_DIV, a_div=True)])
-                csr.spmv(u, tn, trans=True)
-                loop.ops([dict(z=Nv, u=tn, w=Nv, a_slot=SL.NV_A, b_slot=SL.NV_B)], [(Nv, Nv)])
-                loop.P.step(2)                              # alpha, rotations, stopping tests
+                loop.spmv_ops(csr, u, dict(z=Nv, w=Nv, a_slot=SL.NV_A, b_slot=SL.NV_B), step=2, trans=True)
                 loop.ops([dict(z=v, u=v, a_slot=SL.V_DIV, a_div=True)])
                 loop.ops([dict(z=dbar, u=d, w=dbar, a=1.0, b_slot=SL.C0, b_neg=1), dict(z=dbar, u=dbar, a_slot=SL.C1, a_div=True),
                           dict(z=d, u=u, w=d, a=1.0, b_slot=SL.C2, b_neg=1), dict(z=d, u=d, a_slot=SL.C3, a_div=True)])

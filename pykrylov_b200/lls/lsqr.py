@@ -162,17 +162,13 @@ class LSQRFramework(KrylovMethod):
                          window=window, itnlim=itnlim, damp=damp, atol=atol, btol=btol, ctol=ctol, etol=etol)
 
             def trip():
-                csr.spmv(v, tm)                                                          # A v
-                loop.ops([dict(z=Mu, u=tm, w=Mu, a=1.0, b_slot=SL.ALPHA, b_neg=1)], [(Mu, Mu)])
-                loop.P.step(1)                                                           # beta, |A|
+                # Mu = A v - alpha Mu, |Mu|^2 and phase 1 (beta, |A|) in one launch; likewise A'u below
+                loop.spmv_ops(csr, v, dict(z=Mu, w=Mu, a=1.0, b_slot=SL.ALPHA, b_neg=1), step=1)
                 loop.ops([dict(z=u, u=u, a_slot=SL.U_DIV, a_div=True)])
-                csr.spmv(u, tn, trans=True)                                              # A' u
-                loop.ops([dict(z=Nv, u=tn, w=Nv, a_slot=SL.NV_A, b_slot=SL.NV_B)], [(Nv, Nv)])
-                loop.P.step(2)                                                           # alpha, rotations
+                loop.spmv_ops(csr, u, dict(z=Nv, w=Nv, a_slot=SL.NV_A, b_slot=SL.NV_B), step=2, trans=True)
                 loop.ops([dict(z=v, u=v, a_slot=SL.V_DIV, a_div=True), dict(z=dk, u=w, a_slot=SL.C0),
                           dict(z=x, u=x, w=w, a=1.0, b_slot=SL.C1), dict(z=w, u=w, w=v, a_slot=SL.C2, b=1.0)],
-                         [(dk, dk)])
-                loop.P.step(3)                                                           # norms, stopping tests
+                         [(dk, dk)], step=3)                                             # norms, stopping tests
 
             def replay(st_, sc_, hist):
                 for r2, arn, direrr, _ in hist:

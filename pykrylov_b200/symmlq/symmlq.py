@@ -138,14 +138,14 @@ class Symmlq(KrylovMethod):
             def trip():
                 loop.P.step(1)                                       # norms, stopping tests; s = 1/beta
                 loop.ops([dict(z=v, u=y, a_slot=SL.C0)])             # v = s*y
-                csr.spmv(v, y)
-                ops = [dict(z=y, u=y, w=v, a=1.0, b=-shift)] if shift is not None else []
-                ops.append(dict(z=y, u=y, w=r1, a=1.0, b_slot=SL.C1))
-                loop.ops(ops, [(v, y)])
-                loop.P.step(2)                                       # alfa
+                if shift is None:                                    # y = A v + c1 r1, v.y and alfa: one launch
+                    loop.spmv_ops(csr, v, dict(z=y, w=r1, a=1.0, b_slot=SL.C1), step=2, dot_with=v)
+                else:
+                    csr.spmv(v, y)
+                    loop.ops([dict(z=y, u=y, w=v, a=1.0, b=-shift), dict(z=y, u=y, w=r1, a=1.0, b_slot=SL.C1)],
+                             [(v, y)], step=2)                       # alfa
                 loop.ops([dict(z=y, u=y, w=r2, a=1.0, b_slot=SL.C2), dict(z=r1, u=r2, a=1.0), dict(z=r2, u=y, a=1.0)],
-                         [(r2, y)])
-                loop.P.step(3)                                       # beta, rotation, step lengths
+                         [(r2, y)], step=3)                          # beta, rotation, step lengths
                 loop.ops([dict(z=tmp, u=w, w=v, a_slot=SL.C3, b_slot=SL.C4), dict(z=x, u=x, w=tmp, a=1.0, b=1.0),
                           dict(z=w, u=w, w=v, a_slot=SL.C5, b_slot=SL.C6, b_neg=1)])
 

@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
-"""Per-trip time of the device-resident lls / SYMMLQ loops through the public classes, with the trip
-replayed as a CUDA graph (default) and enqueued launch by launch (KRY_OPT_GRAPHS = 0), on a small
+"""Per-trip time of the device-resident lls / SYMMLQ loops through the public classes: the default (fused
+launches, trip replayed as a CUDA graph), the three-launch form of the products (KRY_LLS_FUSE=0) and
+the trip enqueued launch by launch (KRY_OPT_GRAPHS = 0), on a small
 (launch-bound) and the config-2 (bandwidth-bound) 5-point Laplacian.  Per-trip time = difference of
 two solves with different iteration caps (set-up and download cancel), best of 3."""
 import contextlib, io, json, os, sys, time
@@ -15,7 +16,7 @@ from pykrylov_b200.symmlq import Symmlq
 
 ctx = Context(0)
 out = {}
-for g, lo, hi in ((256, 60, 360), (3162, 24, 72)):
+for g, lo, hi in ((256, 100, 1100), (3162, 40, 340)):
     n = g * g
     A = DeviceCsr.poisson2d(ctx, g)
     op = CsrLinearOperator(A, symmetric=True)
@@ -23,11 +24,14 @@ for g, lo, hi in ((256, 60, 360), (3162, 24, 72)):
     for name, cls in (("lsqr", LSQRFramework), ("lsmr", LSMRFramework), ("craig", CRAIGFramework),
                       ("craigmr", CRAIGMRFramework), ("symmlq", Symmlq)):
         row = {}
-        for graphs in (1, 0):
+        if name == "symmlq" and g == 256:
+            lo, hi = 50, 250                                      # SYMMLQ converges on this operator after 269 trips
+        for graphs, fuse in ((1, 1), (1, 0), (0, 1)):
             ctx.set_option(L.KRY_OPT_GRAPHS, graphs)
-            best = 1e9
-            for _ in range(3):
-                t = []
+            os.environ["KRY_LLS_FUSE"] = str(fuse)
+            best = {lo: 1e9, hi: 1e9}
+            trips = {}
+            for rep in range(7):                                   # rep 0 warms up (transpose, pools, first-use)
                 for cap in (lo, hi):
                     s = cls(op, context=ctx)
                     ctx.sync()
@@ -35,17 +39,20 @@ for g, lo, hi in ((256, 60, 360), (3162, 24, 72)):
                     with contextlib.redirect_stdout(io.StringIO()):      # CRAIG-MR prints every trip, like the reference
                         if name == "symmlq":
                             s.solve(rhs, matvec_max=2 * cap + 2, rtol=0.0)
-                            done = (s.nMatvec - 2) // 2
+                            trips[cap] = (s.nMatvec - 2) // 2
                         else:
-                            s.solve(rhs, itnlim=cap, atol=0.0, btol=0.0, etol=0.0, conlim=1e300, show=False)
-                            done = s.itn
+                            ret = s.solve(rhs, itnlim=cap, atol=0.0, btol=0.0, etol=0.0, conlim=1e300, show=False)
+                            trips[cap] = ret[2] if name == "lsmr" else s.itn     # the reference's LSMR returns itn
                     ctx.sync()
-                    t.append((time.perf_counter() - t0, done))
-                best = min(best, (t[1][0] - t[0][0]) / max(1, t[1][1] - t[0][1]))
-            row["graph" if graphs else "enqueued"] = best * 1e6
+                    if rep:
+                        best[cap] = min(best[cap], time.perf_counter() - t0)
+            assert trips[hi] - trips[lo] >= (hi - lo) // 2, (name, trips)
+            row[("graph" if graphs else "enqueued") + ("" if fuse else "_3launch")] = (best[hi] - best[lo]) / (trips[hi] - trips[lo]) * 1e6
+            row["trips"] = [trips[lo], trips[hi]]
         ctx.set_option(L.KRY_OPT_GRAPHS, 1)
         out["%s/g%d" % (name, g)] = row
-        print("%-8s n=%9d  %8.1f us/trip as a graph   %8.1f us/trip enqueued   (%.2fx)"
-              % (name, n, row["graph"], row["enqueued"], row["enqueued"] / row["graph"]), flush=True)
+        os.environ.pop("KRY_LLS_FUSE", None)
+        print("%-8s n=%9d  %8.1f us/trip (fused launches, graph)   %8.1f (three-launch form, graph)   %8.1f (fused, enqueued)"
+              % (name, n, row["graph"], row["graph_3launch"], row["enqueued"]), flush=True)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "r2r_lls_rates.json"), "w"), indent=1)

@@ -173,6 +173,54 @@ def test_spmv_fused_dots(ctx, kname, kind, tile, threads):
             assert abs(g_ - ref) <= 1e-13 * np.sqrt(np.dot(y, y) * max(np.dot(w1, w1), np.dot(y, y)))
 
 
+@pytest.mark.parametrize("kname,kind,tile,threads", KERNELS)
+def test_spmv_with_fused_y_side_update(ctx, kname, kind, tile, threads):
+    """kry_spmv_axpby_dot: z = a (A x) + b w with the coefficient rules of the multi-AXPY (immediate,
+    slot, negated, dividing) in the SpMV's epilogue.  z is bit-identical to the two-launch form
+    (SpMV into a temporary, then the vector pass); the fused inner product agrees to rounding."""
+    rng = np.random.default_rng(7)
+    D = dev()
+    for name, trans in (("jpwh_991", False), ("random_rect", False), ("random_rect", True), ("ragged", False)):
+        M = fixtures()[name]
+        A = upload(ctx, M, transpose=trans)
+        A.set_kernel(kind, tile, threads)
+        nin, nout = (M.shape[0], M.shape[1]) if trans else (M.shape[1], M.shape[0])
+        x, w0, q = rng.standard_normal(nin), rng.standard_normal(nout), rng.standard_normal(nout)
+        ctx.set_scalars(10, [0.37, -1.25])
+        for op_kw in (dict(a=1.0, b_slot=10, b_neg=1), dict(a_slot=11, b=2.5), dict(a_slot=10, a_div=True, b_slot=11, b_div=True),
+                      dict(a=-3.0, w=None)):
+            xv, tv = ctx.vector(x), ctx.vector(nout)
+            z1, z2, qv = ctx.vector(w0), ctx.vector(w0), ctx.vector(q)
+            has_w = "w" not in op_kw
+            kw = {k: v for k, v in op_kw.items() if k != "w"}
+            # two launches
+            A.spmv(xv, tv, trans=trans)
+            D.multi_axpy_dot(ctx, [dict(z=z1, u=tv, w=z1 if has_w else None, **kw)], [(z1, z1)], slot0=20)
+            D.multi_axpy_dot(ctx, [], [(qv, z1)], slot0=21)
+            # one launch (z aliases w), z.z, then q.z
+            D.spmv_axpby_dot(A, xv, dict(z=z2, w=z2 if has_w else None, **kw), dot=True, slot0=22, trans=trans)
+            ref = z1.download()
+            assert np.array_equal(z2.download(), ref), (name, trans, op_kw)
+            z3 = ctx.vector(w0)
+            D.spmv_axpby_dot(A, xv, dict(z=z3, w=z3 if has_w else None, **kw), dot_with=qv, slot0=23, trans=trans)
+            assert np.array_equal(z3.download(), ref)
+            z4 = ctx.vector(w0)
+            D.spmv_axpby_dot(A, xv, dict(z=z4, w=z4 if has_w else None, **kw), trans=trans)       # no inner product
+            assert np.array_equal(z4.download(), ref)
+            zz, qz, zz_f, qz_f = ctx.scalars(20, 4)
+            assert abs(zz_f - zz) <= 1e-13 * zz and abs(zz - np.dot(ref, ref)) <= 1e-13 * zz
+            assert abs(qz_f - qz) <= 1e-13 * np.sqrt(zz * np.dot(q, q))
+    M = fixtures()["jpwh_991"]
+    A = upload(ctx, M)
+    xv, zv = ctx.vector(M.shape[1]), ctx.vector(M.shape[0])
+    with pytest.raises(ValueError):
+        D.spmv_axpby_dot(A, xv, dict(z=zv, w=xv))                     # w aliases the gathered vector
+    with pytest.raises(L().KrylovDeviceError):
+        D.spmv_axpby_dot(A, xv, dict(z=xv))                           # z aliases x
+    with pytest.raises(ValueError):
+        D.spmv_axpby_dot(A, xv, dict(z=ctx.vector(M.shape[0] + 1)))
+
+
 def test_spmv_shape_errors_are_valueerror(ctx):
     M = fixtures()["random_rect"]
     A = upload(ctx, M)
