@@ -229,33 +229,42 @@ class PlaneLoop(object):
             cache[method] = P
         self.ctx, self.P = ctx, P
         self.use_graphs = True
-        self.fuse = os.environ.get("KRY_LLS_FUSE", "1") != "0"
+        self.fuse = os.environ.get("KRY_LLS_FUSE", "1")
         self._tmp = {}
 
     def ops(self, ops, dots=(), step=None):
         """One fused vector pass; `step`: the phase of the recurrence that consumes its inner products,
         run in the launch's finalize instead of a kry_lls_step launch of its own."""
-        if step is None or not dots or not self.fuse:
+        if step is None or not dots or self.fuse == "0":
             multi_axpy_dot(self.ctx, ops, dots, slot0=0)
             if step is not None:
                 self.P.step(step)
         else:
             multi_axpy_dot(self.ctx, ops, dots, plane=self.P, phase=step)
 
+    # rows from which the recurrence phase after a fused SpMV runs as its own one-thread launch instead
+    # of inside the SpMV's finalize: the in-kernel call costs the row kernel 8 registers (6 instead of 8
+    # resident CTAs per SM; measured on B200, DESIGN.md section 5), a separate launch costs ~3 us
+    STEP_IN_KERNEL_BELOW = 1 << 18
+
     def spmv_ops(self, csr, x, op, step, dot_with=None, trans=False):
-        """z = a*(A x) + b*w, the inner product dot_with . z (None: z . z) and phase `step`: one launch.
-        KRY_LLS_FUSE=0 (A/B measurements, tests) enqueues the three launches this replaces: the product
-        into a temporary, the vector pass with its inner product, the step kernel."""
-        if self.fuse:
-            spmv_axpby_dot(csr, x, op, dot_with=dot_with, trans=trans, plane=self.P, phase=step)
-            return
+        """z = a*(A x) + b*w, the inner product dot_with . z (None: z . z) and phase `step`: one launch
+        (two from STEP_IN_KERNEL_BELOW rows).  KRY_LLS_FUSE: 0 enqueues the three launches this replaces
+        (the product into a temporary, the vector pass with its inner product, the step kernel), 2 / 3
+        force the phase into / out of the SpMV launch (A/B measurements, tests)."""
         z = op["z"]
-        t = self._tmp.get(z.n)
-        if t is None:
-            t = self._tmp[z.n] = DeviceVector(self.ctx, z.n)
-        csr.spmv(x, t, trans=trans)
-        multi_axpy_dot(self.ctx, [dict(op, u=t)], [(dot_with if dot_with is not None else z, z)], slot0=0)
-        self.P.step(step)
+        if self.fuse == "0":
+            t = self._tmp.get(z.n)
+            if t is None:
+                t = self._tmp[z.n] = DeviceVector(self.ctx, z.n)
+            csr.spmv(x, t, trans=trans)
+            multi_axpy_dot(self.ctx, [dict(op, u=t)], [(dot_with if dot_with is not None else z, z)], slot0=0)
+            self.P.step(step)
+        elif self.fuse == "2" or (self.fuse != "3" and z.n < self.STEP_IN_KERNEL_BELOW):
+            spmv_axpby_dot(csr, x, op, dot_with=dot_with, trans=trans, plane=self.P, phase=step)
+        else:
+            spmv_axpby_dot(csr, x, op, dot=True, dot_with=dot_with, slot0=0, trans=trans)
+            self.P.step(step)
 
     def run(self, trip, check_interval, on_chunk=None):
         """Returns (status, scalars) after the device latched `done`.  The gate is released on

@@ -24,6 +24,9 @@
 constexpr int LLS_HIST_CAP = 1 << 15;
 constexpr int LLS_HIST_W = 4;
 constexpr int LLS_NV = 64;
+#ifndef LLS_SPMV_MINB
+#define LLS_SPMV_MINB 6
+#endif
 
 // coefficient slots in the context's scalar block (0..3 receive the fused inner products)
 enum {
@@ -712,7 +715,9 @@ extern "C" int kry_lls_spmv_axpby_dot(kry_lls *L, int phase, kry_csr *A, int tra
     KRY_CUDA(cudaSetDevice(c->device));
     KRY_TRY(kry_halo_exchange(A, x->d));
     LlsFin fin{L->dev, c->scalars, L->hist, 1, phase};
-    return spmv_axpby_run<1, 6>(A, trans, x, op, dot_with, fin);
+    if (((op->a_neg | op->b_neg) & 2) == 0)          // what the trips use: plain multiplies, leaner kernel
+        return spmv_axpby_run<1, LLS_SPMV_MINB, false>(A, trans, x, op, dot_with, fin);
+    return spmv_axpby_run<1, 6, true>(A, trans, x, op, dot_with, fin);
 }
 
 extern "C" int kry_lls_status(kry_lls *L, kry_lls_status_t *out, double *scalars, int n_scalars)

@@ -64,13 +64,53 @@ struct MultiAxpyBody {
         for (int d = 0; d < ND; ++d) acc[d] = __dadd_rn(acc[d], __dmul_rn(du[d][i], dw[d][i]));
     }
     __device__ void operator()(int i) const { update(i); }
+
+    // Elements 2*i2 and 2*i2+1 with 16-byte accesses (the vector kernels run this form: twice the bytes
+    // in flight per thread).  Ops run in order on each element, later ops see the outputs of earlier
+    // ones (same thread, same addresses), exactly like update().
+    static constexpr bool kPair = true;
+    static constexpr int  kMinBlocks = 4;      // up to 64 registers: the 8 resolved coefficients stay in registers
+    __device__ void update2(int i2) const
+    {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k >= n_ops) break;
+            const double *u = op[k].u, *w = op[k].w;
+            double2 r = make_double2(0.0, 0.0);
+            if (u && w) {
+                const double2 a = ld2(u, i2), b = ld2(w, i2);
+                r.x = __dadd_rn(term(ca[k], a.x, op[k].a_neg), term(cb[k], b.x, op[k].b_neg));
+                r.y = __dadd_rn(term(ca[k], a.y, op[k].a_neg), term(cb[k], b.y, op[k].b_neg));
+            } else if (u) {
+                const double2 a = ld2(u, i2);
+                r.x = term(ca[k], a.x, op[k].a_neg);
+                r.y = term(ca[k], a.y, op[k].a_neg);
+            } else if (w) {
+                const double2 b = ld2(w, i2);
+                r.x = term(cb[k], b.x, op[k].b_neg);
+                r.y = term(cb[k], b.y, op[k].b_neg);
+            }
+            st2(op[k].z, i2, r);
+        }
+    }
+    __device__ void pair(int i2, double *acc) const
+    {
+        update2(i2);
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            const double2 a = ld2(du[d], i2), b = ld2(dw[d], i2);
+            acc[d] = __dadd_rn(acc[d], __dmul_rn(a.x, b.x));
+            acc[d] = __dadd_rn(acc[d], __dmul_rn(a.y, b.y));
+        }
+    }
+    __device__ void pair(int i2) const { update2(i2); }
 };
 
 
 // SpMV epilogue: z[row] = a * (A x)[row] + b * w[row], then (ND == 1) accumulates dw[row] * z[row]
 // (dw == nullptr: z . z).  Same coefficient rules and the same un-fused arithmetic as an op of
 // MultiAxpyBody whose `u` is the product: fusing it changes no bit of z.
-template <int ND, int MINB = 8>
+template <int ND, int MINB = 8, bool DIV = true>
 struct EpiAxpbyDot {
     // Resident CTAs per SM the row kernels are compiled for: 8 (32 registers) like the plain row kernel.
     // With the lls recurrence in the finalize (LlsFin, a call) the kernel would otherwise be allocated
@@ -92,8 +132,14 @@ struct EpiAxpbyDot {
     }
     __device__ void operator()(int row, double ax, double *acc) const
     {
-        double r = MultiAxpyBody<0>::term(ca, ax, a_neg);
-        if (w) r = __dadd_rn(r, MultiAxpyBody<0>::term(cb, w[row], b_neg));
+        double r;
+        if constexpr (DIV) {
+            r = MultiAxpyBody<0>::term(ca, ax, a_neg);
+            if (w) r = __dadd_rn(r, MultiAxpyBody<0>::term(cb, w[row], b_neg));
+        } else {                                  // the caller checked that no coefficient divides
+            r = __dmul_rn(ca, ax);
+            if (w) r = __dadd_rn(r, __dmul_rn(cb, w[row]));
+        }
         z[row] = r;
         if constexpr (ND > 0) acc[0] = __dadd_rn(acc[0], __dmul_rn(dw ? dw[row] : r, r));
     }
@@ -149,12 +195,12 @@ static int multi_axpy_run(kry_ctx *c, int64_t n, int n_ops, const kry_axpby *ops
 }
 
 // y-side fused product  z = a (A x) + b w  with ND (0 or 1) inner products into `fin`
-template <int ND, int MINB = 8, class Fin>
+template <int ND, int MINB = 8, bool DIV = true, class Fin>
 static int spmv_axpby_run(kry_csr *A, int trans, const kry_vec *x, const kry_axpby *op, const kry_vec *dot_with, Fin fin)
 {
     kry_ctx *c = A->ctx;
     GatherPlain g{x->d};
-    EpiAxpbyDot<ND, MINB> e;
+    EpiAxpbyDot<ND, MINB, DIV> e;
     e.z = op->z->d;
     e.w = op->w ? op->w->d : nullptr;
     e.dw = dot_with ? dot_with->d : nullptr;

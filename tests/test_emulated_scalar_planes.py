@@ -32,7 +32,12 @@ CASES = [("lsqr", dict()), ("lsqr", dict(damp=0.3)), ("lsqr", dict(atol=0.0, bto
 
 
 @pytest.mark.parametrize("name,kw", CASES)
-def test_scalar_plane_on_device_equals_host_path(emu_ctx, name, kw):
+def test_scalar_plane_on_device_equals_host_path(emu_ctx, name, kw, monkeypatch):
+    # Bit-for-bit equality needs the same launches on both sides: the host-scalar path enqueues the
+    # product, the vector pass and reads the inner product; KRY_LLS_FUSE=0 makes the device plane enqueue
+    # exactly those (the default fuses them into the SpMV launch, whose inner product is summed over a
+    # different grid: equal to rounding, tests/test_gpu_lls.py::test_fused_trip_launches_equal_...).
+    monkeypatch.setenv("KRY_LLS_FUSE", "0")
     import pykrylov_b200._engine as eng
     from pykrylov_b200 import _lib as L
     from pykrylov_b200.linop import linop_from_scipy
@@ -80,7 +85,8 @@ def test_scalar_plane_on_device_equals_host_path(emu_ctx, name, kw):
 
 
 @pytest.mark.parametrize("kw", [dict(), dict(shift=0.5), dict(matvec_max=40), dict(rtol=1e-14)])
-def test_symmlq_scalar_plane_on_device_equals_host_path(emu_ctx, kw):
+def test_symmlq_scalar_plane_on_device_equals_host_path(emu_ctx, kw, monkeypatch):
+    monkeypatch.setenv("KRY_LLS_FUSE", "0")               # same launches on both sides: see above
     import pykrylov_b200._engine as eng
     from pykrylov_b200.linop import csr_operator
     from pykrylov_b200.symmlq import Symmlq
