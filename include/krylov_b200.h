@@ -352,12 +352,14 @@ int kry_comm_allreduce_host(kry_ctx *ctx, double *inout, int count, int op /*0 s
 int kry_csr_shard_finalize(kry_csr *A_local, int64_t n_global, int64_t row_begin);
 
 /* ------------------------------------------------- LSQR / LSMR / CRAIG / CRAIG-MR / SYMMLQ
- * The vector work of these solvers is kry_spmv (A and A^T) + kry_multi_axpy_dot; their scalar
+ * The vector work of these solvers is SpMV with A and A^T + fused multi-AXPY passes; their scalar
  * plane -- plane rotations, norm estimates, stopping tests (reference lls/lsqr.py:277-390,
  * lls/lsmr.py:337-475, lls/craig.py:314-455, lls/craigmr.py:159-215, symmlq/symmlq.py:235-355) --
- * runs on the device in single-thread step kernels that read the inner products from the
- * context's scalar slots 0..2 and write the coefficients of the next vector launches into slots
- * 8.. (kry_axpby::a_slot / b_slot).  The host enqueues whole iterations and reads one status
+ * runs on the device, one phase at a time: in the finalize of the launch that produced the inner
+ * product it consumes (kry_lls_spmv_axpby_dot, kry_lls_multi_axpy_dot) or as a one-thread launch
+ * of its own (kry_lls_step).  A phase reads the inner products from the context's scalar slots
+ * 0..2 and writes the coefficients of the next vector launches into slots 8.. (kry_axpby::a_slot /
+ * b_slot).  The host enqueues whole iterations (or replays them: kry_graph_*) and reads one status
  * block per check interval; after the reference's stopping test has fired every later launch,
  * vector kernels included, is a no-op (kry_lls_setup installs the context's gate).
  * Coefficient slots: 8 alpha, 9 u-divisor, 10/11 (A^T u, Nv) coefficients, 12 v-divisor,

@@ -570,7 +570,8 @@ class LaunchGraph(object):
 
 class ScalarPlane(object):
     """Device-resident scalar plane of LSQR / LSMR / CRAIG / CRAIG-MR / SYMMLQ (``kry_lls``):
-    named scalars in, ``step(phase)`` enqueues one single-thread recurrence step, the status block
+    named scalars in, ``step(phase)`` enqueues one phase of the recurrence as a launch of its own (the fused launches of
+    ``multi_axpy_dot(plane=...)`` / ``spmv_axpby_dot(plane=...)`` run it in their finalize), the status block
     and the per-iteration history ring come back at the caller's check interval."""
     METHODS = {"lsqr": L.KRY_LLS_LSQR, "lsmr": L.KRY_LLS_LSMR, "craig": L.KRY_LLS_CRAIG,
                "craigmr": L.KRY_LLS_CRAIGMR, "symmlq": L.KRY_LLS_SYMMLQ}
