@@ -11,6 +11,7 @@ import os
 
 import numpy as np
 
+from ._lib import KrylovDeviceError
 from .device import DeviceSolver, DeviceVector, default_context, multi_axpy_dot, spmv_axpby_dot
 
 
@@ -289,7 +290,14 @@ class PlaneLoop(object):
                         and self.ctx.get_option(2)):
                     # the launch sequence of a trip is static and has now run un-captured: record it once
                     # (KRY_OPT_GRAPHS; not available on the host emulation)
-                    graph = LaunchGraph.capture(self.ctx, trip)
+                    try:
+                        graph = LaunchGraph.capture(self.ctx, trip)
+                    except KrylovDeviceError as exc:
+                        # nothing of a failed capture has executed: keep enqueueing the same launches
+                        import logging
+                        logging.getLogger("pykrylov_b200").warning(
+                            "trip graph capture failed (%s); the trips stay enqueued launch by launch", exc)
+                        graph = None
                     if graph is None:
                         self.use_graphs = False
             return st, sc

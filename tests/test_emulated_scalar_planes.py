@@ -116,3 +116,32 @@ def test_stand_alone_launches_run_again_after_a_plane_solve(emu_ctx):
     LSQRFramework(op, context=emu_ctx).solve(b)
     x = np.random.default_rng(3).standard_normal(20)
     assert np.array_equal(op * x, CsrRef.from_scipy(R).matvec(x))
+
+
+def test_failed_trip_capture_falls_back_to_enqueued_launches(emu_ctx, monkeypatch, caplog):
+    """If the one-off capture of a trip fails, nothing of it has executed: the loop keeps enqueueing the
+    same launches (no other code path) and says so once."""
+    from pykrylov_b200 import _lib as L
+    from pykrylov_b200 import device
+    from pykrylov_b200.linop import linop_from_scipy
+    from pykrylov_b200.lls import LSQRFramework
+    R = sp.random(300, 120, density=0.05, random_state=3, format="csr")
+    R.sort_indices()
+    b = np.random.default_rng(3).standard_normal(300)
+    op = linop_from_scipy(R, context=emu_ctx)
+    plain = LSQRFramework(op, context=emu_ctx)
+    plain.solve(b, show=False, store_resids=True, check_interval=4)
+    calls = []
+
+    def failing(ctx, fn):
+        calls.append(1)
+        raise L.KrylovDeviceError(L.KRY_ERR_CUDA, "capture failed (injected)")
+    monkeypatch.setattr(device.LaunchGraph, "capture", classmethod(lambda cls, ctx, fn: failing(ctx, fn)))
+    real_get = emu_ctx.get_option                         # the emulation always answers 0 for KRY_OPT_GRAPHS
+    monkeypatch.setattr(emu_ctx, "get_option", lambda o: 1 if o == L.KRY_OPT_GRAPHS else real_get(o), raising=False)
+    k = LSQRFramework(op, context=emu_ctx, check_interval=4)
+    with caplog.at_level("WARNING", logger="pykrylov_b200"):
+        k.solve(b, show=False, store_resids=True)
+    assert calls == [1] and any("capture failed" in r.getMessage() for r in caplog.records)
+    assert k.itn == plain.itn and k.istop == plain.istop and k.resids == plain.resids
+    assert np.array_equal(k.x, plain.x)
