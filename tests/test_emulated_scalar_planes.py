@@ -145,3 +145,39 @@ def test_failed_trip_capture_falls_back_to_enqueued_launches(emu_ctx, monkeypatc
     assert calls == [1] and any("capture failed" in r.getMessage() for r in caplog.records)
     assert k.itn == plain.itn and k.istop == plain.istop and k.resids == plain.resids
     assert np.array_equal(k.x, plain.x)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_fused_trip_forms_agree_on_random_rectangular_systems(emu_ctx, seed, monkeypatch):
+    """The three ways a trip can be enqueued -- phase of the recurrence inside the fused SpMV launch
+    (KRY_LLS_FUSE=2), as its own launch behind it (3), and the three-launch form (0) -- on random sparse
+    m x n systems (m < n and m > n, damped and not, random check intervals).  Forms 2 and 3 run the same
+    kernels on the same data and must agree bit for bit; against form 0 only the summation order of the
+    inner products differs.  Four trips: these random operators amplify a rounding-level difference by
+    ~1e3 every three trips (the same growth separates either form from a long-double LSQR)."""
+    import contextlib
+    import io
+    from pykrylov_b200.linop import linop_from_scipy
+    from pykrylov_b200.lls import LSQRFramework, LSMRFramework, CRAIGFramework, CRAIGMRFramework
+    rng = np.random.default_rng(seed)
+    m, n = int(rng.integers(20, 400)), int(rng.integers(20, 400))
+    R = sp.random(m, n, density=float(rng.uniform(0.02, 0.2)), random_state=seed, format="csr")
+    R.sort_indices()
+    for cls in (LSQRFramework, LSMRFramework, CRAIGFramework, CRAIGMRFramework):
+        consistent = cls in (CRAIGFramework, CRAIGMRFramework)
+        b = R @ rng.standard_normal(n) if consistent else rng.standard_normal(m)
+        damp = 0.0 if consistent else float(rng.choice([0.0, 0.0, 0.1, 1.0]))
+        interval = int(rng.integers(1, 9))
+        res = {}
+        for fuse in ("2", "3", "0"):
+            monkeypatch.setenv("KRY_LLS_FUSE", fuse)
+            k = cls(linop_from_scipy(R, context=emu_ctx), context=emu_ctx, check_interval=interval)
+            with contextlib.redirect_stdout(io.StringIO()):
+                k.solve(b, damp=damp, show=False, store_resids=True, itnlim=4, atol=0.0, btol=0.0, etol=0.0)
+            res[fuse] = (np.array(k.resids if len(k.resids) else k.normal_eqns_resids), np.array(k.x))
+        assert np.array_equal(res["2"][0], res["3"][0]) and np.array_equal(res["2"][1], res["3"][1]), cls.__name__
+        h, x = res["2"]
+        h0, x0 = res["0"]
+        assert len(h) == len(h0) >= 4, (cls.__name__, len(h), len(h0))     # some classes record the initial residual too
+        assert np.allclose(h, h0, rtol=1e-9, atol=0.0), cls.__name__
+        assert np.linalg.norm(x - x0) <= 1e-9 * max(np.linalg.norm(x0), 1e-300), cls.__name__
