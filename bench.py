@@ -448,7 +448,7 @@ def main_ours(args):
     A, rhs, n, lo, hi = build_problem(ctx, g, rank, world)
     nnz_total = 5 * n - 4 * g
     if rank == 0:
-        sampler.wait_first(3.0)
+        sampler.wait_first(10.0)       # NVML start-up enumerates every GPU of the box: seconds on 8 GPUs
     if args.cg_fuse is not None:
         ctx.set_option(4, args.cg_fuse)
     if args.cg_fuse_shards is not None:
