@@ -112,7 +112,8 @@ class ClockSampler(object):
     def wait_first(self, timeout_s):
         """Block until the first sample has arrived (the polling loop is then in steady state)."""
         t0 = time.time()
-        while self.proc is not None and not self.lines and time.time() - t0 < timeout_s:
+        while (self.proc is not None and self.proc.poll() is None and not self.lines
+               and time.time() - t0 < timeout_s):
             time.sleep(0.01)
 
     def _pump(self):
